@@ -1,0 +1,58 @@
+"""Build libifd_b200.so: nvcc, sm_100a only, one object per .cu compiled in parallel, linked in-tree so the
+library travels with the snapshot to the GPU box.  No torch dependency (plain C ABI)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+OUT = os.path.join(HERE, "libifd_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+
+def _sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers_mtime():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "ifd_b200.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(src, hm, force):
+    s = os.path.join(CSRC, src)
+    o = os.path.join(OBJ, src[:-3] + ".o")
+    if not force and os.path.exists(o) and os.path.getmtime(o) > max(os.path.getmtime(s), hm):
+        return o, ""
+    r = subprocess.run([NVCC] + FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed on %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    with open(o[:-2] + ".ptxas.log", "w") as f:
+        f.write(r.stderr)
+    return o, r.stderr
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    hm = _headers_mtime()
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        res = list(ex.map(lambda s: _compile(s, hm, force), srcs))
+    objs = [o for o, _ in res]
+    if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
+        r = subprocess.run([NVCC, "-shared", "-o", OUT] + objs, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if verbose:
+        for _, log in res:
+            sys.stderr.write(log)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,147 @@
+"""ConvONet-Opt on the sm_100a kernels, behind the reference's seams.
+
+  ConvONetDecoder.decode(p, c).logits     <- generator.model.decode(p, c).logits   (ConvONet/opt_defense.py:212,
+                                             src/conv_onet/models/__init__.py:67-77)
+  Restorer.optimize_points(...)           <- optimize_points(opt_points, z, c, rep_weight, iterations, printing)
+                                             (ConvONet/opt_defense.py:182-239)
+  normalize_batch_pc / init_points        <- opt_defense.py:76-83 / :149-179
+
+`c` is exactly what the reference's encode_inputs returns: a dict {'xz','xy','yz': [B,32,64,64]}.
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch import distributions as dist
+
+from . import capi, weights
+
+PLANES = ("xz", "xy", "yz")
+
+
+def planes_to_channels_last(c):
+    """dict of [B,C,R,R] (encoder output) -> one device tensor [3,B,R,R,C] in kernel layout."""
+    if isinstance(c, torch.Tensor):          # already converted
+        return c
+    capi.require_gpu()
+    x = torch.stack([c[k].detach().float() for k in PLANES]).contiguous()     # [3,B,C,R,R]
+    _, B, C, R, R2 = x.shape
+    if R != R2:
+        raise RuntimeError("feature planes must be square")
+    out = torch.empty((3, B, R, R, C), dtype=torch.float32, device=x.device)
+    capi.check(capi.lib().ifd_planes_nchw_to_cl(capi.ptr(x), capi.ptr(out), 3 * B, C, R, capi.stream()),
+               "ifd_planes_nchw_to_cl")
+    return out
+
+
+class _DecodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, planes_cl, wblob, dims, padding):
+        capi.require_gpu()
+        x = p.detach().float().contiguous()
+        B, K, _ = x.shape
+        C, H, nb = dims
+        R = planes_cl.shape[2]
+        logits = torch.empty((B, K), dtype=torch.float32, device=x.device)
+        capi.check(capi.lib().ifd_convonet_decode_fwd(capi.ptr(planes_cl), capi.ptr(wblob), capi.ptr(x), B, K, R, C, H, nb,
+                                                      padding, capi.ptr(logits), capi.stream()), "ifd_convonet_decode_fwd")
+        ctx.save_for_backward(x, planes_cl, wblob)
+        ctx.dims, ctx.padding = dims, padding
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        x, planes_cl, wblob = ctx.saved_tensors
+        B, K, _ = x.shape
+        C, H, nb = ctx.dims
+        R = planes_cl.shape[2]
+        g = grad_logits.detach().float().contiguous()
+        out = torch.empty_like(x)
+        capi.check(capi.lib().ifd_convonet_decode_bwd(capi.ptr(planes_cl), capi.ptr(wblob), capi.ptr(x), capi.ptr(g), B, K, R,
+                                                      C, H, nb, ctx.padding, capi.ptr(out), capi.stream()),
+                   "ifd_convonet_decode_bwd")
+        return out, None, None, None, None
+
+
+class ConvONetDecoder:
+    """The decoder half of ConvolutionalOccupancyNetwork, frozen, with weights packed for the kernels.
+
+    Built from the reference checkpoint interface: any state_dict with the `decoder.*` keys of
+    ConvONet/src/conv_onet/models/decoder.py."""
+
+    def __init__(self, state_dict, padding=0.1, device="cuda", prefix="decoder."):
+        self.dims = weights.convonet_decoder_dims(state_dict, prefix)
+        self.padding = float(padding)
+        blob = weights.pack_convonet_decoder(state_dict, prefix)
+        self.blob_host = blob
+        self.device = torch.device(device)
+        self.blob = torch.from_numpy(blob).to(self.device) if self.device.type == "cuda" else None
+
+    def decode(self, p, c, **kwargs):
+        planes = planes_to_channels_last(c)
+        logits = _DecodeFn.apply(p, planes, self.blob, self.dims, self.padding)
+        return dist.Bernoulli(logits=logits)
+
+
+def normalize_batch_pc(points):
+    """opt_defense.py:76-83 (torch ops; the fused loop does this on device itself)."""
+    points -= torch.mean(points, dim=1)[:, None, :]
+    d = torch.sum(points ** 2, dim=2) ** 0.5
+    points /= torch.max(d, dim=1)[0][:, None, None]
+    return points
+
+
+class Restorer:
+    """Holds what the reference keeps in module globals (generator, args.threshold, args.lr) and exposes
+    optimize_points with the reference's signature."""
+
+    def __init__(self, decoder, threshold=0.2, lr=1e-3):
+        self.decoder, self.threshold, self.lr = decoder, float(threshold), float(lr)
+        self.last_stats = None
+
+    def params(self, B_ref, rep_weight, iterations, want_stats=False, **over):
+        return capi.default_params(n_steps=iterations + 1, B_ref=int(B_ref), rep_weight=float(rep_weight),
+                                   lr=self.lr, occ_target=self.threshold, padding=self.decoder.padding,
+                                   want_stats=int(bool(want_stats)), **over)
+
+    def optimize_points(self, opt_points, z, c, rep_weight=1., iterations=1000, printing=False, B_ref=None,
+                        return_tensor=False):
+        """Same arguments as the reference.  `B_ref` (extension): the batch size of the reference call these
+        clouds belong to, when a batch is split across calls / GPUs (defaults to len(opt_points))."""
+        capi.require_gpu()
+        x = opt_points.detach().float().cuda().contiguous().clone()
+        B, K, _ = x.shape
+        planes = planes_to_channels_last(c)
+        C, H, nb = self.decoder.dims
+        R = planes.shape[2]
+        L = capi.lib()
+        P = self.params(B if B_ref is None else B_ref, rep_weight, iterations, want_stats=printing)
+        ws_bytes = L.ifd_convonet_opt_workspace_bytes(B, K)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        n_stat = iterations // 100 + 1
+        stats = torch.zeros((n_stat, 4), dtype=torch.float64, device=x.device) if printing else None
+        capi.check(L.ifd_convonet_opt(capi.ptr(planes), capi.ptr(self.decoder.blob), capi.ptr(x), None, None, B, K, R, C, H,
+                                      nb, ctypes.byref(P), capi.ptr(stats), capi.ptr(ws), ws_bytes, capi.stream()),
+                   "ifd_convonet_opt")
+        if printing:
+            self.last_stats = stats.cpu().numpy()
+            for j, (loss, occ, rep, sg) in enumerate(self.last_stats):
+                print('iter {}, loss {:.4f}'.format(j * 100, loss))
+                print('occ loss: {:.4f}, rep loss: {:.4f}\nocc value mean: {:.4f}'.format(occ, rep, sg))
+        if return_tensor:
+            return x
+        return x.cpu().numpy()
+
+    def optimize_points_host(self, opt_points_np, planes_nchw_np, rep_weight=500., iterations=200, B_ref=None):
+        """End-to-end seam with HOST buffers (numpy in, numpy out): H2D, layout conversion, loop, D2H inside
+        one C call (ifd_convonet_opt_host).  planes_nchw_np: [3,B,C,R,R] float32."""
+        capi.require_gpu()
+        x = np.ascontiguousarray(opt_points_np, dtype=np.float32).copy()
+        pl = np.ascontiguousarray(planes_nchw_np, dtype=np.float32)
+        B, K, _ = x.shape
+        _, _, C, R, _ = pl.shape
+        Cd, H, nb = self.decoder.dims
+        P = self.params(B if B_ref is None else B_ref, rep_weight, iterations)
+        capi.check(capi.lib().ifd_convonet_opt_host(pl.ctypes.data, self.decoder.blob_host.ctypes.data, x.ctypes.data, B, K, R,
+                                                    C, H, nb, ctypes.byref(P), None), "ifd_convonet_opt_host")
+        return x

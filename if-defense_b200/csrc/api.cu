@@ -1,0 +1,108 @@
+// api.cu -- library-level plumbing: error string, launch counter, device probe, and the host-buffer
+// convenience call that is the end-to-end seam (H2D -> layout conversion -> loop -> D2H).
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace ifd {
+std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+long long& launch_counter_ref() {
+  static thread_local long long n = 0;
+  return n;
+}
+
+struct HostCache {
+  void* dev = nullptr;
+  size_t bytes = 0;
+  float* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  cudaStream_t stream = nullptr;
+};
+static thread_local HostCache g_cache;
+
+static int ensure_cache(size_t dev_bytes, size_t pinned_bytes) {
+  if (!g_cache.stream) IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
+  if (g_cache.bytes < dev_bytes) {
+    if (g_cache.dev) cudaFree(g_cache.dev);
+    g_cache.dev = nullptr;
+    g_cache.bytes = 0;
+    IFD_CUDA_TRY(cudaMalloc(&g_cache.dev, dev_bytes));
+    g_cache.bytes = dev_bytes;
+  }
+  if (g_cache.pinned_bytes < pinned_bytes) {
+    if (g_cache.pinned) cudaFreeHost(g_cache.pinned);
+    g_cache.pinned = nullptr;
+    g_cache.pinned_bytes = 0;
+    IFD_CUDA_TRY(cudaMallocHost((void**)&g_cache.pinned, pinned_bytes));
+    g_cache.pinned_bytes = pinned_bytes;
+  }
+  return IFD_OK;
+}
+}  // namespace ifd
+
+using namespace ifd;
+
+extern "C" const char* ifd_last_error(void) { return last_error_ref().c_str(); }
+extern "C" int ifd_abi_version(void) { return IFD_ABI_VERSION; }
+extern "C" long long ifd_launch_count(int reset) {
+  const long long n = launch_counter_ref();
+  if (reset) launch_counter_ref() = 0;
+  return n;
+}
+extern "C" int ifd_device_cc(void) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(IFD_ERR_CUDA, "no CUDA device");
+  }
+  return prop.major * 10 + prop.minor;
+}
+
+extern "C" void ifd_release_cache(void) {
+  if (g_cache.dev) cudaFree(g_cache.dev);
+  if (g_cache.pinned) cudaFreeHost(g_cache.pinned);
+  if (g_cache.stream) cudaStreamDestroy(g_cache.stream);
+  g_cache = HostCache();
+}
+
+extern "C" int ifd_convonet_opt_host(const float* planes_nchw_host, const float* dec_weights_host, float* xyz_host,
+                                     int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* P,
+                                     double* stats_out_host) {
+  IFD_REQUIRE(planes_nchw_host && dec_weights_host && xyz_host && P && B > 0 && K > 0 && R > 0 && C > 0,
+              "ifd_convonet_opt_host: bad arguments");
+  const size_t nw = ifd_convonet_decoder_nfloats(C, H, n_blocks);
+  if (nw == 0) return fail(IFD_ERR_UNSUPPORTED, "ifd_convonet_opt_host: unsupported decoder shape");
+  const size_t plane_bytes = (size_t)3 * B * C * R * R * sizeof(float);
+  const size_t xyz_bytes = (size_t)B * K * 3 * sizeof(float);
+  const size_t w_bytes = align_up(nw * sizeof(float), 256);
+  const int n_stat = P->want_stats && stats_out_host ? (P->n_steps > 0 ? (P->n_steps - 1) / 100 + 1 : 0) : 0;
+  const size_t stat_bytes = align_up((size_t)n_stat * 4 * sizeof(double) + 8, 256);
+  const size_t ws_bytes = ifd_convonet_opt_workspace_bytes(B, K);
+  const size_t total = 2 * align_up(plane_bytes, 256) + w_bytes + align_up(xyz_bytes, 256) + stat_bytes + ws_bytes;
+  int rc = ensure_cache(total, 0);
+  if (rc) return rc;
+  char* base = (char*)g_cache.dev;
+  float* d_nchw = (float*)base; base += align_up(plane_bytes, 256);
+  float* d_cl = (float*)base; base += align_up(plane_bytes, 256);
+  float* d_w = (float*)base; base += w_bytes;
+  float* d_xyz = (float*)base; base += align_up(xyz_bytes, 256);
+  double* d_stat = (double*)base; base += stat_bytes;
+  void* d_ws = base;
+  cudaStream_t st = g_cache.stream;
+  IFD_CUDA_TRY(cudaMemcpyAsync(d_nchw, planes_nchw_host, plane_bytes, cudaMemcpyHostToDevice, st));
+  IFD_CUDA_TRY(cudaMemcpyAsync(d_w, dec_weights_host, nw * sizeof(float), cudaMemcpyHostToDevice, st));
+  IFD_CUDA_TRY(cudaMemcpyAsync(d_xyz, xyz_host, xyz_bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = ifd_planes_nchw_to_cl(d_nchw, d_cl, 3 * B, C, R, st))) return rc;
+  if ((rc = ifd_convonet_opt(d_cl, d_w, d_xyz, nullptr, nullptr, B, K, R, C, H, n_blocks, P, n_stat ? d_stat : nullptr, d_ws,
+                             ws_bytes, st)))
+    return rc;
+  IFD_CUDA_TRY(cudaMemcpyAsync(xyz_host, d_xyz, xyz_bytes, cudaMemcpyDeviceToHost, st));
+  if (n_stat) IFD_CUDA_TRY(cudaMemcpyAsync(stats_out_host, d_stat, (size_t)n_stat * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  IFD_CUDA_TRY(cudaStreamSynchronize(st));
+  return IFD_OK;
+}

@@ -1,0 +1,520 @@
+// restore.cu -- the restoration loop of optimize_points (ConvONet/opt_defense.py:182-239) as sm_100a kernels.
+//
+// Per Adam step (v1 schedule, three launches on one stream, no host sync anywhere):
+//   convonet_decode_kernel<BCE>   per point: 3-plane bilinear gather (channels-last planes, 128 B per tap),
+//                                 5-block ResNet-MLP forward, BCE gradient, MLP dgrad, gather dgrad -> g_occ
+//   knn_repulsion_kernel          per cloud chunk: brute-force kNN-5 from shared memory (reference association,
+//                                 bit-exact indices), repulsion pair terms, scatter-add into neighbours as
+//                                 integer atomics on an exact long accumulator (bitwise reproducible)
+//   adam_kernel                   g = g_occ + coef * acc ; torch-2.11 Adam update of xyz, m, v ; re-zero acc
+// then normalize_kernel (centre + unit sphere, opt_defense.py:76-83).
+#include <vector>
+
+#include "common.cuh"
+#include "convonet_point.cuh"
+#include "topk.cuh"
+
+namespace ifd {
+
+constexpr int H32 = 32;
+constexpr int kDecThreads = 128;
+constexpr int kRepThreads = 128;
+
+enum DecodeMode { kFwdOnly = 0, kBwdGiven = 1, kBce = 2 };
+
+struct DecodeArgs {
+  const float* planes;  // [3][B][R][R][C]
+  const float* W;       // packed decoder parameters
+  const float* xyz;     // [B][K][3]
+  const float* grad_logits;  // kBwdGiven
+  float* logits_out;         // optional
+  float* grad_out;           // [B][K][3]
+  double* stat_part;         // optional [gridDim.x][2]: sum bce, sum sigmoid
+  int B, K, R, n_blocks, wtotal4;
+  float denom, target, ginv;
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kDecThreads) convonet_decode_kernel(const DecodeArgs a) {
+  extern __shared__ float4 smem_w4[];
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.W);
+    for (int i = threadIdx.x; i < a.wtotal4; i += kDecThreads) smem_w4[i] = src[i];
+  }
+  __syncthreads();
+  const float* Wb = reinterpret_cast<const float*>(smem_w4);
+  const int n = a.B * a.K;
+  const int idx = blockIdx.x * kDecThreads + threadIdx.x;
+  const bool live = idx < n;
+  const int pi = live ? idx : n - 1;
+  const int b = pi / a.K;
+  const size_t plane_sz = (size_t)a.R * a.R * H32;
+  const float* const planes[3] = {a.planes + ((size_t)0 * a.B + b) * plane_sz,
+                                  a.planes + ((size_t)1 * a.B + b) * plane_sz,
+                                  a.planes + ((size_t)2 * a.B + b) * plane_sz};
+  const float px = a.xyz[(size_t)pi * 3 + 0], py = a.xyz[(size_t)pi * 3 + 1], pz = a.xyz[(size_t)pi * 3 + 2];
+  ConvPoint<H32> pt;
+  const float logit = pt.forward(Wb, planes, px, py, pz, a.R, a.denom, a.n_blocks);
+  if (live && a.logits_out) a.logits_out[pi] = logit;
+  if (MODE == kFwdOnly) return;
+
+  float glogit;
+  if (MODE == kBwdGiven) {
+    glogit = a.grad_logits[pi];
+  } else {
+    const float sg = sigmoidf_(logit);
+    glogit = (sg - a.target) * a.ginv;   // d/dlogit of K * mean_{B_ref,K} BCEWithLogits(logit, target)
+    if (a.stat_part) {                   // block-uniform branch
+      __shared__ double red[2][kDecThreads / 32];
+      double s0 = live ? (double)bce_with_logits(logit, a.target) : 0.0;
+      double s1 = live ? (double)sg : 0.0;
+      s0 = warp_sum_d(s0);
+      s1 = warp_sum_d(s1);
+      if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s0;
+        red[1][threadIdx.x >> 5] = s1;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w = 0; w < kDecThreads / 32; ++w) {
+          t0 += red[0][w];
+          t1 += red[1][w];
+        }
+        a.stat_part[blockIdx.x * 2 + 0] = t0;
+        a.stat_part[blockIdx.x * 2 + 1] = t1;
+      }
+    }
+  }
+  float gp[3];
+  pt.backward(Wb, planes, glogit, a.R, a.n_blocks, gp);
+  if (live) {
+    a.grad_out[(size_t)pi * 3 + 0] = gp[0];
+    a.grad_out[(size_t)pi * 3 + 1] = gp[1];
+    a.grad_out[(size_t)pi * 3 + 2] = gp[2];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN-k + repulsion pairs for one chunk of kRepThreads query points of one cloud.
+// acc: [B][K][3][kFxLimbs] int64 long accumulator (ifd_math.cuh); receives sum over pairs of dl/d(x).
+// loss_part: [B][gridDim.x] per-chunk sums of the pair losses.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fx_add(long long* limbs, float g) {
+  const FxTerm t = fx_term(g);
+  if (t.limb >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(limbs + t.limb), (unsigned long long)t.val);
+}
+
+template <int KK>
+__global__ void __launch_bounds__(kRepThreads) knn_repulsion_kernel(const float* __restrict__ xyz, int K, int k,
+                                                                    float radius, float h, float eps,
+                                                                    int32_t* __restrict__ idx_out,
+                                                                    float* __restrict__ loss_part,
+                                                                    long long* __restrict__ acc) {
+  extern __shared__ float4 cand[];  // [K] x y z |x|^2
+  __shared__ float red[kRepThreads / 32];
+  const int b = blockIdx.y;
+  const float* cloud = xyz + (size_t)b * K * 3;
+  for (int j = threadIdx.x; j < K; j += kRepThreads) {
+    const float x = cloud[j * 3 + 0], y = cloud[j * 3 + 1], z = cloud[j * 3 + 2];
+    cand[j] = make_float4(x, y, z, sqnorm3(x, y, z));
+  }
+  __syncthreads();
+  const int q = blockIdx.x * kRepThreads + threadIdx.x;
+  float lsum = 0.0f;
+  if (q < K) {
+    const float4 me = cand[q];
+    TopK<KK> top;
+    top.init(INFINITY);
+#pragma unroll 4
+    for (int j = 0; j < K; ++j) {
+      const float4 c = cand[j];
+      top.offer(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+    }
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+    long long* acc_b = acc + (size_t)b * K * 3 * kFxLimbs;
+#pragma unroll
+    for (int s = 1; s < KK; ++s) {       // column 0 is dropped "assuming it is self" (pn_utils.py:81-82)
+      if (s <= k) {
+        const int j = top.id[s];
+        if (idx_out) idx_out[((size_t)b * K + q) * k + (s - 1)] = j;
+        const float4 c = cand[j];
+        const float dx = sub_rn(c.x, me.x), dy = sub_rn(c.y, me.y), dz = sub_rn(c.z, me.z);
+        const RepPair p = repulsion_pair(dx, dy, dz, radius, h, eps);
+        lsum += p.loss;
+        const float gx = p.gcoef * dx, gy = p.gcoef * dy, gz = p.gcoef * dz;
+        fx_add(acc_b + ((size_t)j * 3 + 0) * kFxLimbs, gx);
+        fx_add(acc_b + ((size_t)j * 3 + 1) * kFxLimbs, gy);
+        fx_add(acc_b + ((size_t)j * 3 + 2) * kFxLimbs, gz);
+        sx -= gx;
+        sy -= gy;
+        sz -= gz;
+      }
+    }
+    fx_add(acc_b + ((size_t)q * 3 + 0) * kFxLimbs, sx);
+    fx_add(acc_b + ((size_t)q * 3 + 1) * kFxLimbs, sy);
+    fx_add(acc_b + ((size_t)q * 3 + 2) * kFxLimbs, sz);
+  }
+  // deterministic block sum of the pair losses
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < kRepThreads / 32; ++w) t += red[w];
+    loss_part[(size_t)b * gridDim.x + blockIdx.x] = t;
+  }
+}
+
+// loss[b] = sum(parts) / (K*k);  grad = fx_value(acc) * (grad_loss[b] / (K*k))    (standalone seam)
+__global__ void repulsion_finalize_kernel(const long long* __restrict__ acc, const float* __restrict__ loss_part,
+                                          int nparts, const float* __restrict__ grad_loss, int B, int K, int k,
+                                          float* __restrict__ loss_out, float* __restrict__ grad_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = B * K * 3;
+  if (e < n && grad_out) {
+    const int b = e / (K * 3);
+    const float go = grad_loss ? grad_loss[b] : 1.0f;
+    grad_out[e] = fx_value(acc + (size_t)e * kFxLimbs) * (go / (float)(K * k));
+  }
+  if (e < B && loss_out) {
+    float t = 0.0f;
+    for (int p = 0; p < nparts; ++p) t += loss_part[(size_t)e * nparts + p];
+    loss_out[e] = t / (float)(K * k);
+  }
+}
+
+// Adam step over B*K*3 coordinates; also clears the fixed-point accumulator for the next step.
+__global__ void adam_kernel(float* __restrict__ xyz, float* __restrict__ m, float* __restrict__ v,
+                            const float* __restrict__ g_occ, long long* __restrict__ acc, int n, float rep_coef,
+                            float one_minus_b1, float b2, float one_minus_b2, float eps, AdamStepConst sc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float g = g_occ[e];
+  if (acc) {
+    long long* limbs = acc + (size_t)e * kFxLimbs;
+    g = g + fx_value(limbs) * rep_coef;
+#pragma unroll
+    for (int l = 0; l < kFxLimbs; ++l) limbs[l] = 0;
+  }
+  float p = xyz[e], mm = m[e], vv = v[e];
+  adam_update(p, mm, vv, g, one_minus_b1, b2, one_minus_b2, eps, sc);
+  xyz[e] = p;
+  m[e] = mm;
+  v[e] = vv;
+}
+
+// normalize_batch_pc (opt_defense.py:76-83): one CTA per cloud.
+constexpr int kNormThreads = 256;
+__global__ void __launch_bounds__(kNormThreads) normalize_kernel(float* __restrict__ xyz, int K) {
+  __shared__ float red[3][kNormThreads / 32];
+  __shared__ float bc[3];
+  float* cloud = xyz + (size_t)blockIdx.x * K * 3;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int i = threadIdx.x; i < K; i += kNormThreads)
+    for (int a = 0; a < 3; ++a) s[a] += cloud[i * 3 + a];
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[a] += __shfl_xor_sync(0xffffffffu, s[a], o);
+    if ((threadIdx.x & 31) == 0) red[a][threadIdx.x >> 5] = s[a];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float t = 0.f;
+    for (int w = 0; w < kNormThreads / 32; ++w) t += red[threadIdx.x][w];
+    bc[threadIdx.x] = t / (float)K;
+  }
+  __syncthreads();
+  const float cx = bc[0], cy = bc[1], cz = bc[2];
+  float mx = 0.f;
+  for (int i = threadIdx.x; i < K; i += kNormThreads) {
+    const float x = sub_rn(cloud[i * 3 + 0], cx), y = sub_rn(cloud[i * 3 + 1], cy), z = sub_rn(cloud[i * 3 + 2], cz);
+    cloud[i * 3 + 0] = x;
+    cloud[i * 3 + 1] = y;
+    cloud[i * 3 + 2] = z;
+    mx = fmaxf(mx, sqrt_rn(add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = mx;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < kNormThreads / 32; ++w) t = fmaxf(t, red[0][w]);
+  for (int i = threadIdx.x; i < K * 3; i += kNormThreads) cloud[i] = div_rn(cloud[i], t);
+}
+
+// The four numbers optimize_points prints every 100 iterations (opt_defense.py:229-236).
+__global__ void stats_kernel(const double* __restrict__ dec_part, int n_dec, const float* __restrict__ loss_part,
+                             int B, int nparts, int K, int k, float rep_weight, double* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double bce = 0.0, sg = 0.0;
+  for (int i = 0; i < n_dec; ++i) {
+    bce += dec_part[2 * i];
+    sg += dec_part[2 * i + 1];
+  }
+  double rep = 0.0;
+  for (int b = 0; b < B; ++b) {
+    float t = 0.f;
+    for (int p = 0; p < nparts; ++p) t += loss_part[(size_t)b * nparts + p];
+    rep += (double)(t / (float)(K * k));
+  }
+  const double occ_loss = bce / ((double)B * K) * K;
+  const double rep_loss = rep_weight > 0.f ? rep / B * rep_weight : 0.0;
+  out[0] = occ_loss + rep_loss;
+  out[1] = occ_loss;
+  out[2] = rep_loss;
+  out[3] = sg / ((double)B * K);
+}
+
+__global__ void nchw_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  // one CTA transposes a [C][32] tile of one image into [32][C]
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* s = src + (size_t)b * C * HW;
+  float* d = dst + (size_t)b * C * HW;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < C && p < HW) ? s[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    if (c < C && p < HW) d[(size_t)p * C + c] = tile[threadIdx.x][r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static int check_decoder_cfg(int R, int C, int H, int n_blocks) {
+  if (C != 32 || H != 32) return fail(IFD_ERR_UNSUPPORTED, "ConvONet decoder kernels are built for c_dim = hidden_size = 32 "
+                                                           "(configs/convonet_3plane_mn40.yaml)");
+  if (n_blocks < 1 || n_blocks > kMaxBlocks) return fail(IFD_ERR_UNSUPPORTED, "n_blocks must be in [1, 8]");
+  if (R < 2 || R > 1024) return fail(IFD_ERR_INVALID, "plane resolution out of range");
+  return IFD_OK;
+}
+
+static float plane_denom(double padding) {
+  // xy / (1 + padding + 10e-6): the Python double is rounded to fp32 when it meets the tensor (common.py:250)
+  return (float)(1.0 + padding + 10e-6);
+}
+
+static int launch_decode(int mode, DecodeArgs a, cudaStream_t st) {
+  const int wtotal = ConvDecLayout<H32>::total(a.n_blocks);
+  a.wtotal4 = (wtotal + 3) / 4;
+  const size_t smem = (size_t)a.wtotal4 * sizeof(float4);
+  const int n = a.B * a.K;
+  const int grid = (n + kDecThreads - 1) / kDecThreads;
+  if (mode == kFwdOnly) {
+    IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_kernel<kFwdOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convonet_decode_kernel<kFwdOnly><<<grid, kDecThreads, smem, st>>>(a);
+  } else if (mode == kBwdGiven) {
+    IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_kernel<kBwdGiven>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convonet_decode_kernel<kBwdGiven><<<grid, kDecThreads, smem, st>>>(a);
+  } else {
+    IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_kernel<kBce>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convonet_decode_kernel<kBce><<<grid, kDecThreads, smem, st>>>(a);
+  }
+  IFD_LAUNCH_CHECK("convonet_decode_kernel");
+  return IFD_OK;
+}
+
+static int launch_knn_repulsion(const float* xyz, int B, int K, int k, float radius, float h, float eps,
+                                int32_t* idx_out, float* loss_part, long long* acc, cudaStream_t st) {
+  if (k + 1 > 8) return fail(IFD_ERR_UNSUPPORTED, "repulsion kNN size must be <= 7");
+  if (k + 1 > K) return fail(IFD_ERR_INVALID, "repulsion kNN size exceeds the number of points");
+  const size_t smem = (size_t)K * sizeof(float4);
+  if (smem > 200 * 1024) return fail(IFD_ERR_UNSUPPORTED, "K must be <= 12800 points per cloud");
+  dim3 grid((K + kRepThreads - 1) / kRepThreads, B);
+  IFD_CUDA_TRY(cudaFuncSetAttribute(knn_repulsion_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  knn_repulsion_kernel<8><<<grid, kRepThreads, smem, st>>>(xyz, K, k, radius, h, eps, idx_out, loss_part, acc);
+  IFD_LAUNCH_CHECK("knn_repulsion_kernel");
+  return IFD_OK;
+}
+
+static inline int rep_chunks(int K) { return (K + kRepThreads - 1) / kRepThreads; }
+
+struct OptWorkspace {
+  float* g_occ;
+  long long* acc;
+  float* m;
+  float* v;
+  float* loss_part;
+  double* dec_part;
+  size_t bytes;
+};
+static OptWorkspace carve_opt_ws(void* base, int B, int K) {
+  OptWorkspace w;
+  size_t off = 0;
+  const size_t n = (size_t)B * K * 3;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  w.acc = (long long*)take(n * kFxLimbs * sizeof(long long));
+  w.g_occ = (float*)take(n * sizeof(float));
+  w.m = (float*)take(n * sizeof(float));
+  w.v = (float*)take(n * sizeof(float));
+  w.loss_part = (float*)take((size_t)B * rep_chunks(K) * sizeof(float));
+  w.dec_part = (double*)take((size_t)((B * K + kDecThreads - 1) / kDecThreads) * 2 * sizeof(double));
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace ifd
+
+using namespace ifd;
+
+extern "C" size_t ifd_convonet_decoder_nfloats(int C, int H, int n_blocks) {
+  if (C != H || H <= 0 || n_blocks <= 0) return 0;
+  return (size_t)(4 * H + n_blocks * 3 * (H * H + H) + H + 1);
+}
+
+extern "C" int ifd_planes_nchw_to_cl(const float* nchw, float* cl, int B, int C, int R, ifd_stream_t stream) {
+  IFD_REQUIRE(nchw && cl && B > 0 && C > 0 && R > 0, "ifd_planes_nchw_to_cl: bad arguments");
+  const int HW = R * R;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nchw_to_cl_kernel<<<grid, block, 0, as_stream(stream)>>>(nchw, cl, C, HW);
+  IFD_LAUNCH_CHECK("nchw_to_cl_kernel");
+  return IFD_OK;
+}
+
+static int check_ptrs16(const void* a, const void* b) {
+  if (((uintptr_t)a | (uintptr_t)b) & 15) return fail(IFD_ERR_INVALID, "planes and weights must be 16-byte aligned");
+  return IFD_OK;
+}
+
+extern "C" int ifd_convonet_decode_fwd(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,
+                                       int R, int C, int H, int n_blocks, double padding, float* logits_out,
+                                       ifd_stream_t stream) {
+  IFD_REQUIRE(planes_cl && dec_weights && xyz && logits_out && B > 0 && K > 0, "ifd_convonet_decode_fwd: bad arguments");
+  int rc = check_decoder_cfg(R, C, H, n_blocks);
+  if (rc) return rc;
+  if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
+  DecodeArgs a{};
+  a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.logits_out = logits_out;
+  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(padding);
+  return launch_decode(kFwdOnly, a, as_stream(stream));
+}
+
+extern "C" int ifd_convonet_decode_bwd(const float* planes_cl, const float* dec_weights, const float* xyz,
+                                       const float* grad_logits, int B, int K, int R, int C, int H, int n_blocks,
+                                       double padding, float* grad_xyz_out, ifd_stream_t stream) {
+  IFD_REQUIRE(planes_cl && dec_weights && xyz && grad_logits && grad_xyz_out && B > 0 && K > 0,
+              "ifd_convonet_decode_bwd: bad arguments");
+  int rc = check_decoder_cfg(R, C, H, n_blocks);
+  if (rc) return rc;
+  if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
+  DecodeArgs a{};
+  a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_logits = grad_logits; a.grad_out = grad_xyz_out;
+  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(padding);
+  return launch_decode(kBwdGiven, a, as_stream(stream));
+}
+
+extern "C" size_t ifd_knn_repulsion_workspace_bytes(int B, int K) {
+  if (B <= 0 || K <= 0) return 0;
+  return align_up((size_t)B * K * 3 * kFxLimbs * sizeof(long long), 256) + align_up((size_t)B * rep_chunks(K) * sizeof(float), 256);
+}
+
+extern "C" int ifd_knn_repulsion(const float* xyz, int B, int K, int k, double radius, double h, double eps,
+                                 const float* grad_loss, int32_t* idx_out, float* loss_out, float* grad_xyz_out,
+                                 void* workspace, size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_REQUIRE(xyz && B > 0 && K > 0 && k > 0, "ifd_knn_repulsion: bad arguments");
+  IFD_REQUIRE(workspace, "ifd_knn_repulsion: workspace is required");
+  if (workspace_bytes < ifd_knn_repulsion_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_knn_repulsion: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  long long* acc = (long long*)workspace;
+  float* loss_part = (float*)((char*)workspace + align_up((size_t)B * K * 3 * kFxLimbs * sizeof(long long), 256));
+  IFD_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)B * K * 3 * kFxLimbs * sizeof(long long), st));
+  int rc = launch_knn_repulsion(xyz, B, K, k, (float)radius, (float)h, (float)eps, idx_out, loss_part, acc, st);
+  if (rc) return rc;
+  const int n = B * K * 3;
+  repulsion_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(acc, loss_part, rep_chunks(K), grad_loss, B, K, k, loss_out,
+                                                            grad_xyz_out);
+  IFD_LAUNCH_CHECK("repulsion_finalize_kernel");
+  return IFD_OK;
+}
+
+extern "C" void ifd_opt_params_default(ifd_opt_params* p) {
+  if (!p) return;
+  p->n_steps = 201; p->step0 = 0; p->B_ref = 1; p->knn_k = 5; p->normalize_out = 1; p->want_stats = 0;
+  p->lr = 1e-3; p->beta1 = 0.9; p->beta2 = 0.999; p->adam_eps = 1e-8;
+  p->occ_target = 0.2; p->rep_weight = 500.0;
+  p->rep_radius = 0.07; p->rep_h = 0.03; p->rep_eps = 1e-12; p->padding = 0.1;
+}
+
+extern "C" size_t ifd_convonet_opt_workspace_bytes(int B, int K) {
+  if (B <= 0 || K <= 0) return 0;
+  return carve_opt_ws(nullptr, B, K).bytes;
+}
+
+extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights, float* xyz, float* adam_m, float* adam_v,
+                                int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* P,
+                                double* stats_out, void* workspace, size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_REQUIRE(planes_cl && dec_weights && xyz && P && B > 0 && K > 0, "ifd_convonet_opt: bad arguments");
+  IFD_REQUIRE(P->n_steps >= 0 && P->step0 >= 0 && P->B_ref > 0, "ifd_convonet_opt: bad step counts / B_ref");
+  IFD_REQUIRE((adam_m == nullptr) == (adam_v == nullptr), "ifd_convonet_opt: pass both adam_m and adam_v or neither");
+  IFD_REQUIRE(!(P->step0 > 0 && !adam_m), "ifd_convonet_opt: resuming (step0 > 0) needs adam_m / adam_v");
+  int rc = check_decoder_cfg(R, C, H, n_blocks);
+  if (rc) return rc;
+  if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
+  IFD_REQUIRE(workspace, "ifd_convonet_opt: workspace is required");
+  if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_opt: workspace too small");
+  const bool rep = P->rep_weight > 0.0;
+  if (rep && (P->knn_k + 1 > 8 || P->knn_k < 1)) return fail(IFD_ERR_UNSUPPORTED, "knn_k must be in [1, 7]");
+
+  cudaStream_t st = as_stream(stream);
+  OptWorkspace w = carve_opt_ws(workspace, B, K);
+  const size_t n = (size_t)B * K * 3;
+  float* m = adam_m ? adam_m : w.m;
+  float* v = adam_v ? adam_v : w.v;
+  if (!adam_m || P->step0 == 0) {
+    IFD_CUDA_TRY(cudaMemsetAsync(m, 0, n * sizeof(float), st));
+    IFD_CUDA_TRY(cudaMemsetAsync(v, 0, n * sizeof(float), st));
+  }
+  IFD_CUDA_TRY(cudaMemsetAsync(w.acc, 0, n * kFxLimbs * sizeof(long long), st));
+
+  DecodeArgs a{};
+  a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_out = w.g_occ;
+  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(P->padding);
+  a.target = (float)P->occ_target;
+  // d/dlogit of (mean over B_ref*K) * K: autograd multiplies K, then divides by the element count
+  a.ginv = (float)K / (float)((long long)P->B_ref * K);
+  // rep_loss = mean_B(mean_{K,k}) * rep_weight: grad = rep_weight / B_ref / (K*k)
+  const float rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
+  const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
+  const int n_dec = (B * K + kDecThreads - 1) / kDecThreads;
+
+  for (int i = 0; i < P->n_steps; ++i) {
+    const bool stat = P->want_stats && stats_out && (i % 100 == 0);
+    a.stat_part = stat ? w.dec_part : nullptr;
+    if ((rc = launch_decode(kBce, a, st))) return rc;
+    if (rep && (rc = launch_knn_repulsion(xyz, B, K, P->knn_k, (float)P->rep_radius, (float)P->rep_h, (float)P->rep_eps, nullptr, w.loss_part, w.acc, st)))
+      return rc;
+    if (stat) {
+      stats_kernel<<<1, 32, 0, st>>>(w.dec_part, n_dec, w.loss_part, B, rep ? rep_chunks(K) : 0, K, P->knn_k,
+                                     (float)P->rep_weight, stats_out + (size_t)(i / 100) * 4);
+      IFD_LAUNCH_CHECK("stats_kernel");
+    }
+    const double t = (double)(P->step0 + i + 1);
+    AdamStepConst sc;
+    sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
+    sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, m, v, w.g_occ, rep ? w.acc : nullptr, (int)n, rep_coef,
+                                                            omb1, (float)P->beta2, omb2, (float)P->adam_eps, sc);
+    IFD_LAUNCH_CHECK("adam_kernel");
+  }
+  if (P->normalize_out) {
+    normalize_kernel<<<B, kNormThreads, 0, st>>>(xyz, K);
+    IFD_LAUNCH_CHECK("normalize_kernel");
+  }
+  return IFD_OK;
+}

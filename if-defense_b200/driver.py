@@ -1,0 +1,131 @@
+"""The defense driver: the functions of ConvONet/opt_defense.py (and its ONet twin) as a library.
+
+Reference call stack mirrored:
+  defend_npz_test_data :317-344 -> defend_point_cloud :255-314 -> sor_process :86-111 -> preprocess_pc :114-146
+  -> model.encode_inputs :300 -> init_points :149-179 -> optimize_points :182-239 -> normalize_batch_pc :76-83
+
+Differences, all forced by turning a script with module-level state into a library: the globals `args`,
+`generator`, `device` become fields of `Defender`; random draws take an explicit generator so that the same
+draw can be fed to the oracle.  Flag names and defaults are the reference's (opt_defense.py:21-53).
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import convonet
+from .defense import SORDefense
+
+
+class Args:
+    """argparse defaults of ConvONet/opt_defense.py:21-53."""
+    sample_npoint = 1024
+    padding_scale = 0.9
+    init_sigma = 0.01
+    iterations = 200
+    batch_size = 192
+    lr = 0.001
+    rep_weight = 500.
+    sor = True
+    sor_k = 2
+    sor_alpha = 1.1
+    threshold = 0.2       # cfg['test']['threshold']
+    input_npoint = 600    # cfg['data']['pointcloud_n'] (300 for ONet)
+
+    def __init__(self, **over):
+        for k, v in over.items():
+            if not hasattr(type(self), k):
+                raise RuntimeError("unknown option %r" % k)
+            setattr(self, k, v)
+
+
+def preprocess_pc(pc, num_points=None, padding_scale=1., rng=None):
+    """opt_defense.py:114-146 (numpy part): centre, scale by the largest bbox extent, pad; optional random
+    subset of num_points (np.random.choice without replacement; `rng` makes the draw explicit).
+    Returns (all_points [K_i,3] float32, selected [min(K_i,num_points),3] float32)."""
+    centered = pc - np.mean(pc, axis=0)
+    scale = (np.max(centered, axis=0) - np.min(centered, axis=0)).max()
+    allp = centered / scale * padding_scale
+    if num_points is not None and allp.shape[0] > num_points:
+        idx = (rng if rng is not None else np.random).choice(allp.shape[0], num_points, replace=False)
+        sel = allp[idx]
+    else:
+        sel = allp
+    return allp.astype(np.float32), sel.astype(np.float32)
+
+
+def init_points(pcs, npoint=1024, sigma=0.01, padding_scale=0.9, gen=None):
+    """opt_defense.py:149-179: K indices with replacement per cloud, + N(0, sigma^2), clamp to the padded
+    cube.  Host RNG (the kernels never draw random numbers); returns a CPU tensor [B,npoint,3]."""
+    pts = []
+    for pc in pcs:
+        pc = torch.as_tensor(pc).float().cpu()
+        pts.append(pc[torch.randint(0, pc.shape[0], (npoint,), generator=gen)])
+    pts = torch.stack(pts, 0)
+    noise = torch.randn(pts.shape, generator=gen) * sigma
+    return torch.clamp(pts + noise, min=-0.5 * padding_scale, max=0.5 * padding_scale)
+
+
+class Defender:
+    """ConvONet-Opt end to end on one GPU.  `model` is a models.ConvolutionalOccupancyNetwork (or any object
+    with encode_inputs() returning the 3-plane dict and a `decoder` holding the reference's decoder.* keys)."""
+
+    def __init__(self, model, args=None, device="cuda"):
+        self.args = args or Args()
+        self.device = torch.device(device)
+        self.model = model.to(self.device).eval()
+        for p in self.model.parameters():
+            p.requires_grad = False
+        sd = {"decoder." + k: v for k, v in self.model.decoder.state_dict().items()}
+        self.decoder = convonet.ConvONetDecoder(sd, padding=self.model.decoder.padding, device=self.device)
+        self.restorer = convonet.Restorer(self.decoder, threshold=self.args.threshold, lr=self.args.lr)
+
+    def sor_process(self, pc):
+        """opt_defense.py:86-111: SOR in batches of 32 -> list of [K_i,3] float32 arrays."""
+        sor = SORDefense(k=self.args.sor_k, alpha=self.args.sor_alpha)
+        out = []
+        for i in range(0, len(pc), 32):
+            x = torch.from_numpy(np.asarray(pc[i:i + 32])).float().to(self.device)
+            out += [o.detach().cpu().numpy().astype(np.float32) for o in sor(x)]
+        return out
+
+    def defend_point_cloud(self, pc, rng=None, gen=None, printing=False, clouds_slice=None):
+        """opt_defense.py:255-314.  pc: [N,K,3] array.  Returns float32 [N,sample_npoint,3].
+        clouds_slice=(lo, hi): restore only clouds lo..hi-1 of every reference batch position range (used by
+        the multi-GPU sharder; B_ref stays the reference batch size so results do not depend on the split)."""
+        a = self.args
+        pcs = self.sor_process(pc) if a.sor else [np.asarray(p, dtype=np.float32) for p in pc]
+        out = np.zeros((len(pcs), a.sample_npoint, 3), dtype=np.float32)
+        for lo in range(0, len(pcs), a.batch_size):
+            batch = pcs[lo:lo + a.batch_size]
+            proc = [preprocess_pc(p, num_points=a.input_npoint, padding_scale=a.padding_scale, rng=rng) for p in batch]
+            sel = torch.from_numpy(np.stack([s for _, s in proc])).float().to(self.device)
+            with torch.no_grad():
+                c = self.model.encode_inputs(sel)
+            pts = init_points([p for p, _ in proc], a.sample_npoint, a.init_sigma, a.padding_scale, gen)
+            out[lo:lo + a.batch_size] = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight,
+                                                                      iterations=a.iterations, printing=printing)
+        return out
+
+
+def get_save_name(path, tag="convonet_opt-", folder="ConvONet-Opt"):
+    """opt_defense.py:242-252."""
+    name = path.split('/')[-1]
+    save_folder = os.path.join(path[:path.rindex(name)], folder)
+    os.makedirs(save_folder, exist_ok=True)
+    return os.path.join(save_folder, tag + name)
+
+
+def defend_npz_test_data(defender, path, **kw):
+    """opt_defense.py:317-344: npz in (test_pc, test_label[, target_label]) -> npz out, same keys, test_pc
+    float32 [N,1024,3], labels uint8."""
+    npz = np.load(path)
+    test_pc = npz['test_pc'][..., :3]
+    out = defender.defend_point_cloud(test_pc, **kw)
+    save_path = get_save_name(path)
+    fields = dict(test_pc=out.astype(np.float32), test_label=npz['test_label'].astype(np.uint8))
+    if 'target_label' in npz.files:
+        fields['target_label'] = npz['target_label'].astype(np.uint8)
+    np.savez(save_path, **fields)
+    print('defense result saved to {}'.format(save_path))
+    return save_path

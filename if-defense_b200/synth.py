@@ -1,0 +1,57 @@
+"""Synthetic workload protocol: the reference ships neither data nor weights, so benchmarks
+and parity tests run on seeded synthetic clouds of ModelNet40 shape (1024 points) and seeded random-init
+weights with the reference's parameter names.  Everything here is deterministic given the seeds."""
+import os
+import types
+
+import numpy as np
+import torch
+
+from . import driver, models
+
+_AIRPLANE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "airplane.npy")
+
+
+def synth_cloud(i, n=1024):
+    """Cloud i: points on a random ellipsoid (even i) or tapered box (odd i) surface, radii U[0.3,1], 5 % of
+    the points displaced by N(0, 0.02^2) as 'adversarial' noise."""
+    r = np.random.default_rng(1000 + i)
+    radii = r.uniform(0.3, 1.0, size=3)
+    if i % 2 == 0:
+        v = r.normal(size=(n, 3))
+        pts = v / np.linalg.norm(v, axis=1, keepdims=True) * radii
+    else:
+        pts = r.uniform(-1, 1, size=(n, 3))
+        ax = r.integers(0, 3, size=n)
+        pts[np.arange(n), ax] = np.sign(pts[np.arange(n), ax])
+        pts *= radii * (1.0 - 0.3 * (pts[:, 2:3] * 0.5 + 0.5))
+    k = n // 20
+    sel = r.choice(n, k, replace=False)
+    pts[sel] += r.normal(scale=0.02, size=(k, 3))
+    return pts.astype(np.float32)
+
+
+def clouds(B, n=1024, airplane=True):
+    """[B,n,3]; cloud 0 is the one real ModelNet40 shape the reference ships (baselines/data/airplane.npy),
+    a thin-sheet hard case for kNN repulsion."""
+    out = [synth_cloud(i, n) for i in range(B)]
+    if airplane and n == 1024 and os.path.exists(_AIRPLANE):
+        out[0] = np.load(_AIRPLANE).astype(np.float32)
+    return np.stack(out)
+
+
+def make_case(B, K=1024, seed=0, T=600, device="cpu", sd=None):
+    """One ConvONet-Opt batch: weights, encoder input, feature planes `c` (as the reference's encode_inputs
+    returns them) and init points.  Encoding runs with the product's torch encoder on `device`."""
+    sd = sd if sd is not None else models.synthetic_state_dict("convonet", 0)
+    raw = clouds(B)
+    proc = [driver.preprocess_pc(raw[i], num_points=T, padding_scale=0.9, rng=np.random.default_rng(2000 + i)) for i in range(B)]
+    sel = torch.from_numpy(np.stack([s for _, s in proc]))
+    model = models.build_convonet()
+    model.load_state_dict(sd)
+    model = model.to(device).eval()
+    with torch.no_grad():
+        c = {k: v.cpu() for k, v in model.encoder(sel.to(device)).items()}
+    gen = torch.Generator().manual_seed(3000 + seed)
+    p0 = driver.init_points([p for p, _ in proc], npoint=K, sigma=0.01, padding_scale=0.9, gen=gen)
+    return types.SimpleNamespace(sd=sd, raw=raw, sel=sel, c=c, p0=p0, B=B, K=K)

@@ -1,0 +1,173 @@
+/*
+ * ifd_b200.h -- C ABI of libifd_b200.so: the B200 (sm_100a) implementation of IF-Defense's
+ * optimisation-based restoration hot path.
+ *
+ * The reference (Wuziyi616/IF-Defense) has no FFI/plugin layer: its seams are Python call sites.
+ * Each entry point below names the reference call site it replaces (file:line under the reference
+ * tree).  INTEGRATION.md shows the ctypes binding a reference maintainer would add at that seam.
+ *
+ * Conventions
+ *   - every pointer is caller-owned DEVICE memory unless the parameter name ends in `_host`;
+ *   - no allocation inside the library except in the *_host convenience calls; scratch comes from
+ *     the caller-provided workspace (query the size with the matching *_workspace_bytes);
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*); no internal host
+ *     synchronisation except in the *_host calls;
+ *   - return value: 0 on success, <0 on error (IFD_ERR_*); ifd_last_error() returns a thread-local
+ *     message.  The Python shim raises RuntimeError, the reference's only error convention
+ *     (ConvONet/defense/repulsion_loss.py:37, ConvONet/defense/SOR.py:64);
+ *   - indices are int32 (the reference uses int64 tensors; values are identical);
+ *   - results are bitwise reproducible run to run (no floating-point atomics anywhere).
+ */
+#ifndef IFD_B200_H_
+#define IFD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFD_OK 0
+#define IFD_ERR_INVALID (-1)     /* bad argument */
+#define IFD_ERR_CUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
+#define IFD_ERR_UNSUPPORTED (-3) /* shape/config outside what the kernels are built for */
+#define IFD_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define IFD_ABI_VERSION 1
+
+typedef void* ifd_stream_t; /* cudaStream_t */
+
+const char* ifd_last_error(void);
+int ifd_abi_version(void);
+/* Compute capability of the current device as major*10+minor, or <0.  The kernels are sm_100a-only. */
+int ifd_device_cc(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry kernels
+ * ---------------------------------------------------------------------------------------------- */
+
+/* knn_point (ConvONet/defense/pn_utils.py:64-83), DGCNN knn (baselines/model/dgcnn.py:7-13),
+ * PointConv knn_point (baselines/model/pointconv.py:104-116).
+ * x: [B][N][C] row-major float32 (C = 3 for point clouds; feature-space kNN up to C = 128).
+ * Ranks key(i,j) = (|x_j|^2 + (-2 x_i.x_j)) + |x_i|^2 evaluated in the reference's association
+ * (dot product = FMA chain over c, squares rounded separately and summed left to right), ascending;
+ * exact ties resolve to the lowest index.  The first `drop_first` entries of each sorted row are dropped
+ * (knn_point: drop_first = 1 "assuming it is self"; DGCNN: 0).  idx_out: [B][N][k] int32;
+ * key_out (optional): [B][N][k] float32 ranked keys.  k + drop_first <= 32. */
+int ifd_knn(const float* x, int B, int N, int C, int k, int drop_first, int32_t* idx_out, float* key_out,
+            ifd_stream_t stream);
+
+/* RepulsionLoss.get_repulsion_loss fwd + bwd (ConvONet/defense/repulsion_loss.py:18-54) fused with
+ * its knn_point and index_points (pn_utils.py:6-23,64-83).
+ *   loss_out[b]       = mean_{K,k} (radius - d) * exp(-(d/h)^2),  d = sqrt(max(|x_j - x_i|^2, eps))
+ *   grad_xyz_out      = d( sum_b grad_loss[b] * loss[b] ) / d xyz   (grad_loss == NULL means all ones)
+ * idx_out (optional): [B][K][k].  Workspace: ifd_knn_repulsion_workspace_bytes(B, K). */
+size_t ifd_knn_repulsion_workspace_bytes(int B, int K);
+int ifd_knn_repulsion(const float* xyz, int B, int K, int k, double radius, double h, double eps,
+                      const float* grad_loss, int32_t* idx_out, float* loss_out, float* grad_xyz_out,
+                      void* workspace, size_t workspace_bytes, ifd_stream_t stream);
+
+/* farthest_point_sample (baselines/model/pointnet2.py:53-74, ConvONet/defense/pn_utils.py:26-48).
+ * The reference draws the first index with torch.randint; here it is data: start_idx[B].
+ * idx_out: [B][npoint]. */
+int ifd_fps(const float* xyz, int B, int N, int npoint, const int32_t* start_idx, int32_t* idx_out,
+            ifd_stream_t stream);
+
+/* query_ball_point (baselines/model/pointnet2.py:77-98): for each of S centres the first `nsample`
+ * indices (ascending) with expanded-form d^2 <= radius_sq, padded with the first hit.  radius_sq is
+ * fp32(radius ** 2) exactly as torch casts the Python scalar (the caller squares in double, then rounds).
+ * xyz [B][N][3], new_xyz [B][S][3], idx_out [B][S][nsample].  A centre with no hit yields N everywhere
+ * (the reference's behaviour: it would then fail in index_points). */
+int ifd_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S, float radius_sq, int nsample,
+                   int32_t* idx_out, ifd_stream_t stream);
+
+/* SORDefense.outlier_removal (ConvONet/defense/SOR.py:22-49): float64 expanded-form kNN-k mean squared
+ * distance per point, threshold mean + alpha * std (unbiased).  keep_out [B][K] uint8 (1 = kept),
+ * value_out (optional) [B][K] float64. */
+int ifd_sor(const float* xyz, int B, int K, int k, double alpha, uint8_t* keep_out, double* value_out,
+            ifd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ConvONet decoder (LocalDecoder, 3 feature planes)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Packed decoder parameters in kernel layout (float32, all Linear weights TRANSPOSED to [in][out]):
+ *   fc_p.W^T [3][H], fc_p.b [H],
+ *   n_blocks x { fc_c[i].W^T [C][H], fc_c[i].b [H], blocks[i].fc_0.W^T [H][H], .b [H], blocks[i].fc_1.W^T [H][H], .b [H] },
+ *   fc_out.w [H], fc_out.b [1]
+ * Names are the reference state_dict keys under `decoder.`. 16001 floats for the
+ * shipped config (C = H = 32, n_blocks = 5). */
+size_t ifd_convonet_decoder_nfloats(int C, int H, int n_blocks);
+
+/* encode_inputs() output -> kernel layout.  The reference hands the decoder a dict of
+ * [B][C][R][R] NCHW planes (ConvONet/src/encoder/pointnet.py:68-86); the kernels read channels-last
+ * [B][R][R][C] so that one bilinear tap is one 128-byte line. */
+int ifd_planes_nchw_to_cl(const float* nchw, float* cl, int B, int C, int R, ifd_stream_t stream);
+
+/* ConvolutionalOccupancyNetwork.decode(p, c).logits (ConvONet/src/conv_onet/models/__init__.py:67-77 ->
+ * LocalDecoder.forward, models/decoder.py:69-95, sample_plane_feature :50-57, normalize_coordinate
+ * src/common.py:235-258, ResnetBlockFC src/layers.py:39-48).
+ * planes_cl: [3][B][R][R][C] in the order xz, xy, yz.  xyz [B][K][3].  logits_out [B][K]. */
+int ifd_convonet_decode_fwd(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,
+                            int R, int C, int H, int n_blocks, double padding, float* logits_out,
+                            ifd_stream_t stream);
+
+/* Backward of the above w.r.t. xyz only (the model is frozen: ConvONet/opt_defense.py:72-73).
+ * grad_logits [B][K] -> grad_xyz_out [B][K][3].  Recomputes the forward (nothing is saved). */
+int ifd_convonet_decode_bwd(const float* planes_cl, const float* dec_weights, const float* xyz,
+                            const float* grad_logits, int B, int K, int R, int C, int H, int n_blocks,
+                            double padding, float* grad_xyz_out, ifd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The restoration loop
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Everything optimize_points reads from argparse / module constants
+ * (ConvONet/opt_defense.py:33-46,59,207; defense/repulsion_loss.py:9-10). */
+typedef struct ifd_opt_params {
+  int32_t n_steps;       /* iterations + 1 (opt_defense.py:210) -> 201 */
+  int32_t step0;         /* Adam steps already taken (0 for a fresh run; >0 resumes with adam_m/adam_v) */
+  int32_t B_ref;         /* batch size of the reference call this cloud belongs to: the losses are batch
+                            means, so every gradient carries 1/B_ref */
+  int32_t knn_k;         /* 5 */
+  int32_t normalize_out; /* 1: apply normalize_batch_pc (opt_defense.py:76-83) after the last step */
+  int32_t want_stats;    /* 1: fill stats_out every 100 steps as the reference prints (:229-236) */
+  /* Python floats travel as doubles and are rounded to fp32 where torch rounds them. */
+  double lr;             /* 1e-3 */
+  double beta1, beta2;   /* 0.9, 0.999 */
+  double adam_eps;       /* 1e-8 */
+  double occ_target;     /* cfg['test']['threshold'] = 0.2 */
+  double rep_weight;     /* 500 */
+  double rep_radius, rep_h, rep_eps; /* 0.07, 0.03, 1e-12 */
+  double padding;        /* cfg['data']['padding'] = 0.1 */
+} ifd_opt_params;
+
+void ifd_opt_params_default(ifd_opt_params* p);
+
+/* optimize_points (ConvONet/opt_defense.py:182-239): n_steps x { decode -> K*mean BCEWithLogits(logit,
+ * target) + rep_weight*mean repulsion -> d/dxyz -> Adam } then centre + unit-sphere normalise.
+ * xyz [B][K][3] is updated in place (the reference also mutates opt_points in place).
+ * adam_m / adam_v: optional [B][K][3] state in/out (NULL: zero-initialised scratch in the workspace).
+ * stats_out: optional [(n_steps-1)/100 + 1][4] float64 = {loss, occ_loss, rep_loss, mean sigmoid(logit)}
+ * over the B clouds passed (batch means use B_ref). */
+size_t ifd_convonet_opt_workspace_bytes(int B, int K);
+int ifd_convonet_opt(const float* planes_cl, const float* dec_weights, float* xyz, float* adam_m, float* adam_v,
+                     int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* params,
+                     double* stats_out, void* workspace, size_t workspace_bytes, ifd_stream_t stream);
+
+/* Host-buffer convenience call (the end-to-end seam): planes in the reference's NCHW layout
+ * [3][B][C][R][R], weights, xyz are HOST pointers; does H2D, layout conversion, the loop, D2H of xyz and
+ * synchronises.  Device scratch is cached per thread between calls and released by ifd_release_cache(). */
+int ifd_convonet_opt_host(const float* planes_nchw_host, const float* dec_weights_host, float* xyz_host,
+                          int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* params,
+                          double* stats_out_host);
+void ifd_release_cache(void);
+
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+long long ifd_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFD_B200_H_ */

@@ -1,0 +1,163 @@
+/*
+ * ifd_oracle.c -- TEST INFRASTRUCTURE ONLY (the oracle's C half; never linked into the product).
+ *
+ * Plain-C restatement of the reference's INDEX-producing geometry ops with the arithmetic association
+ * fixed explicitly (fmaf chains, separately rounded squares), so that it yields the same bits on any host
+ * CPU -- unlike torch.matmul, whose K=3 kernel is host-dependent.  It is pinned against the unmodified
+ * reference through the committed fixtures in tests/golden/ (generated from /root/reference by
+ * tests/golden/make_golden.py) and, in the build container, against the reference itself.
+ *
+ * Compile with -ffp-contract=off (oracle/Makefile).  Each function cites the reference lines it restates.
+ * The reference materialises the full [N][N] matrix and calls torch.topk / sort; so does this file (a full
+ * stable sort per row), deliberately unlike the product's streaming top-k.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float key; int32_t idx; } kv_t;
+typedef struct { double key; int32_t idx; } kvd_t;
+
+static int cmp_kv(const void* a, const void* b) {
+  const kv_t* x = (const kv_t*)a; const kv_t* y = (const kv_t*)b;
+  if (x->key < y->key) return -1;
+  if (x->key > y->key) return 1;
+  return (x->idx > y->idx) - (x->idx < y->idx);   /* ties: lowest index first (library tie policy) */
+}
+static int cmp_kvd(const void* a, const void* b) {
+  const kvd_t* x = (const kvd_t*)a; const kvd_t* y = (const kvd_t*)b;
+  if (x->key < y->key) return -1;
+  if (x->key > y->key) return 1;
+  return (x->idx > y->idx) - (x->idx < y->idx);
+}
+
+/* sum_c x_c^2 with separately rounded squares, left to right (torch.sum(pc ** 2, dim)) */
+static float sqnorm(const float* x, int C) {
+  float s = x[0] * x[0];
+  for (int c = 1; c < C; ++c) { float q = x[c] * x[c]; s = s + q; }
+  return s;
+}
+/* torch.matmul over the C axis == FMA chain in c order (measured for C = 3) */
+static float dotc(const float* a, const float* b, int C) {
+  float s = a[0] * b[0];
+  for (int c = 1; c < C; ++c) s = fmaf(a[c], b[c], s);
+  return s;
+}
+
+/* knn_point (ConvONet/defense/pn_utils.py:64-83): dist = xx + inner + xx^T; (-dist).topk(k+1); drop column 0.
+ * dgcnn knn  (baselines/model/dgcnn.py:7-13): pd = -xx - inner - xx^T; pd.topk(k) -- the negation of the same
+ * key, so one routine serves both with drop_first = 1 / 0.  x: [B][N][C]. */
+void ifdo_knn(const float* x, int B, int N, int C, int k, int drop_first, int32_t* idx_out, float* key_out) {
+  kv_t* row = (kv_t*)malloc(sizeof(kv_t) * (size_t)N);
+  float* xx = (float*)malloc(sizeof(float) * (size_t)N);
+  for (int b = 0; b < B; ++b) {
+    const float* c = x + (size_t)b * N * C;
+    for (int j = 0; j < N; ++j) xx[j] = sqnorm(c + (size_t)j * C, C);
+    for (int i = 0; i < N; ++i) {
+      for (int j = 0; j < N; ++j) {
+        const float inner = -2.0f * dotc(c + (size_t)i * C, c + (size_t)j * C, C);
+        const float t = xx[j] + inner;           /* xx [B,1,N] + inner [B,N,N] */
+        row[j].key = t + xx[i];                  /* + xx^T [B,N,1] */
+        row[j].idx = j;
+      }
+      qsort(row, (size_t)N, sizeof(kv_t), cmp_kv);
+      for (int s = 0; s < k; ++s) {
+        idx_out[((size_t)b * N + i) * k + s] = row[s + drop_first].idx;
+        if (key_out) key_out[((size_t)b * N + i) * k + s] = row[s + drop_first].key;
+      }
+    }
+  }
+  free(row); free(xx);
+}
+
+/* farthest_point_sample (baselines/model/pointnet2.py:53-74; defense/pn_utils.py:26-48); start[b] replaces
+ * the reference's torch.randint draw.  torch.max(distance, -1)[1] -> first occurrence. */
+void ifdo_fps(const float* xyz, int B, int N, int npoint, const int32_t* start, int32_t* idx_out) {
+  float* dist = (float*)malloc(sizeof(float) * (size_t)N);
+  for (int b = 0; b < B; ++b) {
+    const float* c = xyz + (size_t)b * N * 3;
+    for (int j = 0; j < N; ++j) dist[j] = 1e10f;
+    int far = start[b];
+    for (int it = 0; it < npoint; ++it) {
+      idx_out[(size_t)b * npoint + it] = far;
+      const float cx = c[far * 3], cy = c[far * 3 + 1], cz = c[far * 3 + 2];
+      int best = 0;
+      for (int j = 0; j < N; ++j) {
+        const float dx = c[j * 3] - cx, dy = c[j * 3 + 1] - cy, dz = c[j * 3 + 2] - cz;
+        const float qx = dx * dx, qy = dy * dy, qz = dz * dz;
+        const float t = qx + qy;
+        const float d = t + qz;
+        if (d < dist[j]) dist[j] = d;
+        if (dist[j] > dist[best]) best = j;
+      }
+      far = best;
+    }
+  }
+  free(dist);
+}
+
+/* query_ball_point (baselines/model/pointnet2.py:77-98) with square_distance (:9-30):
+ * dist = -2 * src.dst^T ; dist += |src|^2 ; dist += |dst|^2 ; idx = N where dist > r2 ; sort ; first nsample ;
+ * N replaced by the first entry.  src = new_xyz [B][S][3], dst = xyz [B][N][3]. */
+void ifdo_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S, float r2, int nsample, int32_t* idx_out) {
+  int32_t* g = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+  for (int b = 0; b < B; ++b)
+    for (int s = 0; s < S; ++s) {
+      const float* q = new_xyz + ((size_t)b * S + s) * 3;
+      const float qq = sqnorm(q, 3);
+      int cnt = 0;
+      for (int j = 0; j < N; ++j) {
+        const float* p = xyz + ((size_t)b * N + j) * 3;
+        float d = -2.0f * dotc(q, p, 3);
+        d = d + qq;
+        d = d + sqnorm(p, 3);
+        if (!(d > r2)) g[cnt++] = j;             /* ascending j == the sort of the surviving indices */
+      }
+      int32_t* o = idx_out + ((size_t)b * S + s) * nsample;
+      for (int t = 0; t < nsample; ++t) o[t] = t < cnt ? g[t] : (cnt > 0 ? g[0] : N);
+    }
+  free(g);
+}
+
+/* SORDefense.outlier_removal (ConvONet/defense/SOR.py:22-49), float64. */
+void ifdo_sor(const float* xyz, int B, int K, int k, double alpha, uint8_t* keep, double* value_out) {
+  kvd_t* row = (kvd_t*)malloc(sizeof(kvd_t) * (size_t)K);
+  double* xx = (double*)malloc(sizeof(double) * (size_t)K);
+  double* val = (double*)malloc(sizeof(double) * (size_t)K);
+  for (int b = 0; b < B; ++b) {
+    const float* c = xyz + (size_t)b * K * 3;
+    for (int j = 0; j < K; ++j) {
+      const double x = c[j * 3], y = c[j * 3 + 1], z = c[j * 3 + 2];
+      const double a = x * x, bb = y * y, cc = z * z;
+      const double t = a + bb;
+      xx[j] = t + cc;
+    }
+    for (int i = 0; i < K; ++i) {
+      for (int j = 0; j < K; ++j) {
+        double dot = (double)c[i * 3] * (double)c[j * 3];
+        dot = fma((double)c[i * 3 + 1], (double)c[j * 3 + 1], dot);
+        dot = fma((double)c[i * 3 + 2], (double)c[j * 3 + 2], dot);
+        const double t = xx[j] + (-2.0 * dot);
+        row[j].key = t + xx[i];
+        row[j].idx = j;
+      }
+      qsort(row, (size_t)K, sizeof(kvd_t), cmp_kvd);
+      double s = 0.0;
+      for (int t = 1; t <= k; ++t) s += row[t].key;
+      val[i] = s / (double)k;
+    }
+    double mean = 0.0;
+    for (int i = 0; i < K; ++i) mean += val[i];
+    mean /= (double)K;
+    double var = 0.0;
+    for (int i = 0; i < K; ++i) var += (val[i] - mean) * (val[i] - mean);
+    var /= (double)(K - 1);
+    const double thr = mean + alpha * sqrt(var);
+    for (int i = 0; i < K; ++i) {
+      keep[(size_t)b * K + i] = val[i] <= thr ? 1 : 0;
+      if (value_out) value_out[(size_t)b * K + i] = val[i];
+    }
+  }
+  free(row); free(xx); free(val);
+}
