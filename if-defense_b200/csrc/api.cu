@@ -3,6 +3,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace ifd {
@@ -13,6 +15,24 @@ std::string& last_error_ref() {
 long long& launch_counter_ref() {
   static thread_local long long n = 0;
   return n;
+}
+
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec>* g_prof = nullptr;
+
+ProfileScope::ProfileScope(int kind, cudaStream_t st) : kind_(kind), st_(st) {
+  if (!g_prof_on) return;
+  if (cudaEventCreate(&e0_) != cudaSuccess) { e0_ = nullptr; return; }
+  cudaEventRecord(e0_, st_);
+}
+ProfileScope::~ProfileScope() {
+  if (!e0_) return;
+  cudaEvent_t e1;
+  if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0_); return; }
+  cudaEventRecord(e1, st_);
+  if (!g_prof) g_prof = new std::vector<ProfRec>();
+  g_prof->push_back({kind_, e0_, e1});
 }
 
 struct HostCache {
@@ -61,6 +81,27 @@ extern "C" int ifd_device_cc(void) {
     return fail(IFD_ERR_CUDA, "no CUDA device");
   }
   return prop.major * 10 + prop.minor;
+}
+
+extern "C" void ifd_profile_enable(int on) { g_prof_on = on != 0; }
+extern "C" int ifd_profile_read(double* ms_out, long long* launches_out) {
+  for (int k = 0; k < IFD_PROFILE_KINDS; ++k) {
+    if (ms_out) ms_out[k] = 0.0;
+    if (launches_out) launches_out[k] = 0;
+  }
+  if (!g_prof) return IFD_PROFILE_KINDS;
+  cudaDeviceSynchronize();
+  for (const ProfRec& r : *g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.kind >= 0 && r.kind < IFD_PROFILE_KINDS) {
+      if (ms_out) ms_out[r.kind] += ms;
+      if (launches_out) launches_out[r.kind] += 1;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof->clear();
+  return IFD_PROFILE_KINDS;
 }
 
 extern "C" void ifd_release_cache(void) {

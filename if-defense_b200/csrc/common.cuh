@@ -42,6 +42,15 @@ inline void count_launch(int n = 1) { launch_counter_ref() += n; }
     if (!(cond)) return ::ifd::fail(IFD_ERR_INVALID, std::string(msg)); \
   } while (0)
 
+// optional per-kernel event timing (api.cu); `kind` as documented at ifd_profile_read
+struct ProfileScope {
+  ProfileScope(int kind, cudaStream_t st);
+  ~ProfileScope();
+  int kind_;
+  cudaStream_t st_;
+  cudaEvent_t e0_ = nullptr;
+};
+
 inline cudaStream_t as_stream(ifd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

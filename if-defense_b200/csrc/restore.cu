@@ -496,9 +496,16 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   for (int i = 0; i < P->n_steps; ++i) {
     const bool stat = P->want_stats && stats_out && (i % 100 == 0);
     a.stat_part = stat ? w.dec_part : nullptr;
-    if ((rc = launch_decode(kBce, a, st))) return rc;
-    if (rep && (rc = launch_knn_repulsion(xyz, B, K, P->knn_k, (float)P->rep_radius, (float)P->rep_h, (float)P->rep_eps, nullptr, w.loss_part, w.acc, st)))
-      return rc;
+    {
+      ProfileScope ps(0, st);
+      if ((rc = launch_decode(kBce, a, st))) return rc;
+    }
+    if (rep) {
+      ProfileScope ps(1, st);
+      if ((rc = launch_knn_repulsion(xyz, B, K, P->knn_k, (float)P->rep_radius, (float)P->rep_h, (float)P->rep_eps, nullptr,
+                                     w.loss_part, w.acc, st)))
+        return rc;
+    }
     if (stat) {
       stats_kernel<<<1, 32, 0, st>>>(w.dec_part, n_dec, w.loss_part, B, rep ? rep_chunks(K) : 0, K, P->knn_k,
                                      (float)P->rep_weight, stats_out + (size_t)(i / 100) * 4);
@@ -508,9 +515,12 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
     AdamStepConst sc;
     sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
     sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
-    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, m, v, w.g_occ, rep ? w.acc : nullptr, (int)n, rep_coef,
-                                                            omb1, (float)P->beta2, omb2, (float)P->adam_eps, sc);
-    IFD_LAUNCH_CHECK("adam_kernel");
+    {
+      ProfileScope ps(2, st);
+      adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, m, v, w.g_occ, rep ? w.acc : nullptr, (int)n, rep_coef,
+                                                              omb1, (float)P->beta2, omb2, (float)P->adam_eps, sc);
+      IFD_LAUNCH_CHECK("adam_kernel");
+    }
   }
   if (P->normalize_out) {
     normalize_kernel<<<B, kNormThreads, 0, st>>>(xyz, K);

@@ -167,6 +167,14 @@ void ifd_release_cache(void);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 long long ifd_launch_count(int reset);
 
+/* Per-kernel device timing for the roofline report (bench.py).  While enabled, every launch inside the
+ * restoration loop is bracketed by CUDA events on the launching stream.  ifd_profile_read synchronises the
+ * device, sums the elapsed time per kernel kind, clears the record and returns the number of kinds written:
+ * 0 = decode (gather + MLP fwd/bwd), 1 = kNN + repulsion, 2 = Adam, 3 = everything else. */
+#define IFD_PROFILE_KINDS 4
+void ifd_profile_enable(int on);
+int ifd_profile_read(double* ms_out, long long* launches_out);
+
 #ifdef __cplusplus
 }
 #endif
