@@ -23,6 +23,7 @@ class OptParams(ctypes.Structure):
         ("knn_k", ctypes.c_int32), ("normalize_out", ctypes.c_int32), ("want_stats", ctypes.c_int32),
         ("lr", _c_d), ("beta1", _c_d), ("beta2", _c_d), ("adam_eps", _c_d), ("occ_target", _c_d),
         ("rep_weight", _c_d), ("rep_radius", _c_d), ("rep_h", _c_d), ("rep_eps", _c_d), ("padding", _c_d),
+        ("decode_kernel", ctypes.c_int32), ("reserved_", ctypes.c_int32),
     ]
 
 

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "convonet_point.cuh"
+#include "decode_v2.cuh"
 #include "topk.cuh"
 
 namespace ifd {
@@ -111,13 +112,23 @@ __device__ __forceinline__ void fx_add(long long* limbs, float g) {
   if (t.limb >= 0) atomicAdd(reinterpret_cast<unsigned long long*>(limbs + t.limb), (unsigned long long)t.val);
 }
 
-template <int KK>
+// WARM = false: from-scratch scan with a sorted insertion list (first Adam step, standalone seam).
+// WARM = true : the previous step's k+1 neighbours give an upper bound tau on the (k+1)-th smallest key at the
+//               current positions; one branch-light pass collects every candidate with key <= tau (typically
+//               k+1..k+3 of them) into a small per-thread list, which is then sorted with the same
+//               (key, index) order.  The result is identical to the from-scratch scan by construction -- points
+//               move <= ~lr per step, so the bound is tight -- and the divergent insertion path (v1: 15 of 32
+//               lanes active on average) disappears from the K-long loop.
+constexpr int kWarmCap = 16;
+
+template <int KK, bool WARM>
 __global__ void __launch_bounds__(kRepThreads) knn_repulsion_kernel(const float* __restrict__ xyz, int K, int k,
                                                                     float radius, float h, float eps,
                                                                     int32_t* __restrict__ idx_out,
                                                                     float* __restrict__ loss_part,
-                                                                    long long* __restrict__ acc) {
-  extern __shared__ float4 cand[];  // [K] x y z |x|^2
+                                                                    long long* __restrict__ acc,
+                                                                    int32_t* __restrict__ nbr /* [B][K][KK] in/out */) {
+  extern __shared__ float4 cand[];  // [K] x y z |x|^2, then (WARM) int buf[kWarmCap][kRepThreads]
   __shared__ float red[kRepThreads / 32];
   const int b = blockIdx.y;
   const float* cloud = xyz + (size_t)b * K * 3;
@@ -132,10 +143,48 @@ __global__ void __launch_bounds__(kRepThreads) knn_repulsion_kernel(const float*
     const float4 me = cand[q];
     TopK<KK> top;
     top.init(INFINITY);
+    bool scan_all = !WARM;
+    if (WARM) {
+      int* buf = reinterpret_cast<int*>(cand + K) + threadIdx.x;     // column of this thread, stride kRepThreads
+      const int32_t* prev = nbr + ((size_t)b * K + q) * KK;
+      float tau = -INFINITY;
+#pragma unroll
+      for (int s = 0; s < KK; ++s)
+        if (s <= k) {
+          const float4 c = cand[prev[s]];
+          tau = fmaxf(tau, knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)));
+        }
+      int cnt = 0;
+#pragma unroll 8
+      for (int j = 0; j < K; ++j) {
+        const float4 c = cand[j];
+        const float d = knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z));
+        if (d <= tau) {
+          if (cnt < kWarmCap) buf[cnt * kRepThreads] = j;
+          ++cnt;
+        }
+      }
+      if (cnt <= kWarmCap) {
+        for (int c0 = 0; c0 < cnt; ++c0) {
+          const int j = buf[c0 * kRepThreads];
+          const float4 c = cand[j];
+          top.offer(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+        }
+      } else {
+        scan_all = true;          // a former neighbour moved far away: fall back to the full scan (rare)
+      }
+    }
+    if (scan_all) {
 #pragma unroll 4
-    for (int j = 0; j < K; ++j) {
-      const float4 c = cand[j];
-      top.offer(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+      for (int j = 0; j < K; ++j) {
+        const float4 c = cand[j];
+        top.offer(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+      }
+    }
+    if (nbr) {
+      int32_t* o = nbr + ((size_t)b * K + q) * KK;
+#pragma unroll
+      for (int s = 0; s < KK; ++s) o[s] = top.id[s];
     }
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
     long long* acc_b = acc + (size_t)b * K * 3 * kFxLimbs;
@@ -326,15 +375,34 @@ static int launch_decode(int mode, DecodeArgs a, cudaStream_t st) {
   return IFD_OK;
 }
 
+static int launch_decode_v2(const DecodeArgs& a, cudaStream_t st) {
+  DecodeV2Args v{};
+  v.planes = a.planes; v.W = a.W; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
+  v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
+  v.wtotal4 = (ConvDecLayout<H32>::total(a.n_blocks) + 3) / 4;
+  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv;
+  const size_t smem = DecodeV2Smem::bytes(v.wtotal4);
+  IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  convonet_decode_v2_kernel<<<(v.n + kV2Pts - 1) / kV2Pts, kV2Threads, smem, st>>>(v);
+  IFD_LAUNCH_CHECK("convonet_decode_v2_kernel");
+  return IFD_OK;
+}
+
 static int launch_knn_repulsion(const float* xyz, int B, int K, int k, float radius, float h, float eps,
-                                int32_t* idx_out, float* loss_part, long long* acc, cudaStream_t st) {
+                                int32_t* idx_out, float* loss_part, long long* acc, int32_t* nbr, bool warm,
+                                cudaStream_t st) {
   if (k + 1 > 8) return fail(IFD_ERR_UNSUPPORTED, "repulsion kNN size must be <= 7");
   if (k + 1 > K) return fail(IFD_ERR_INVALID, "repulsion kNN size exceeds the number of points");
-  const size_t smem = (size_t)K * sizeof(float4);
-  if (smem > 200 * 1024) return fail(IFD_ERR_UNSUPPORTED, "K must be <= 12800 points per cloud");
+  const size_t smem = (size_t)K * sizeof(float4) + (warm ? (size_t)kWarmCap * kRepThreads * sizeof(int) : 0);
+  if (smem > 200 * 1024) return fail(IFD_ERR_UNSUPPORTED, "K must be <= 12000 points per cloud");
   dim3 grid((K + kRepThreads - 1) / kRepThreads, B);
-  IFD_CUDA_TRY(cudaFuncSetAttribute(knn_repulsion_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  knn_repulsion_kernel<8><<<grid, kRepThreads, smem, st>>>(xyz, K, k, radius, h, eps, idx_out, loss_part, acc);
+  if (warm) {
+    IFD_CUDA_TRY(cudaFuncSetAttribute(knn_repulsion_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_repulsion_kernel<8, true><<<grid, kRepThreads, smem, st>>>(xyz, K, k, radius, h, eps, idx_out, loss_part, acc, nbr);
+  } else {
+    IFD_CUDA_TRY(cudaFuncSetAttribute(knn_repulsion_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_repulsion_kernel<8, false><<<grid, kRepThreads, smem, st>>>(xyz, K, k, radius, h, eps, idx_out, loss_part, acc, nbr);
+  }
   IFD_LAUNCH_CHECK("knn_repulsion_kernel");
   return IFD_OK;
 }
@@ -348,6 +416,7 @@ struct OptWorkspace {
   float* v;
   float* loss_part;
   double* dec_part;
+  int32_t* nbr;
   size_t bytes;
 };
 static OptWorkspace carve_opt_ws(void* base, int B, int K) {
@@ -365,6 +434,7 @@ static OptWorkspace carve_opt_ws(void* base, int B, int K) {
   w.v = (float*)take(n * sizeof(float));
   w.loss_part = (float*)take((size_t)B * rep_chunks(K) * sizeof(float));
   w.dec_part = (double*)take((size_t)((B * K + kDecThreads - 1) / kDecThreads) * 2 * sizeof(double));
+  w.nbr = (int32_t*)take((size_t)B * K * 8 * sizeof(int32_t));
   w.bytes = off;
   return w;
 }
@@ -434,7 +504,7 @@ extern "C" int ifd_knn_repulsion(const float* xyz, int B, int K, int k, double r
   long long* acc = (long long*)workspace;
   float* loss_part = (float*)((char*)workspace + align_up((size_t)B * K * 3 * kFxLimbs * sizeof(long long), 256));
   IFD_CUDA_TRY(cudaMemsetAsync(acc, 0, (size_t)B * K * 3 * kFxLimbs * sizeof(long long), st));
-  int rc = launch_knn_repulsion(xyz, B, K, k, (float)radius, (float)h, (float)eps, idx_out, loss_part, acc, st);
+  int rc = launch_knn_repulsion(xyz, B, K, k, (float)radius, (float)h, (float)eps, idx_out, loss_part, acc, nullptr, false, st);
   if (rc) return rc;
   const int n = B * K * 3;
   repulsion_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(acc, loss_part, rep_chunks(K), grad_loss, B, K, k, loss_out,
@@ -449,6 +519,7 @@ extern "C" void ifd_opt_params_default(ifd_opt_params* p) {
   p->lr = 1e-3; p->beta1 = 0.9; p->beta2 = 0.999; p->adam_eps = 1e-8;
   p->occ_target = 0.2; p->rep_weight = 500.0;
   p->rep_radius = 0.07; p->rep_h = 0.03; p->rep_eps = 1e-12; p->padding = 0.1;
+  p->decode_kernel = 0; p->reserved_ = 0;
 }
 
 extern "C" size_t ifd_convonet_opt_workspace_bytes(int B, int K) {
@@ -491,19 +562,19 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   // rep_loss = mean_B(mean_{K,k}) * rep_weight: grad = rep_weight / B_ref / (K*k)
   const float rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
   const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
-  const int n_dec = (B * K + kDecThreads - 1) / kDecThreads;
+  const int n_dec = P->decode_kernel == 1 ? (B * K + kDecThreads - 1) / kDecThreads : (B * K + kV2Pts - 1) / kV2Pts;
 
   for (int i = 0; i < P->n_steps; ++i) {
     const bool stat = P->want_stats && stats_out && (i % 100 == 0);
     a.stat_part = stat ? w.dec_part : nullptr;
     {
       ProfileScope ps(0, st);
-      if ((rc = launch_decode(kBce, a, st))) return rc;
+      if ((rc = P->decode_kernel == 1 ? launch_decode(kBce, a, st) : launch_decode_v2(a, st))) return rc;
     }
     if (rep) {
       ProfileScope ps(1, st);
       if ((rc = launch_knn_repulsion(xyz, B, K, P->knn_k, (float)P->rep_radius, (float)P->rep_h, (float)P->rep_eps, nullptr,
-                                     w.loss_part, w.acc, st)))
+                                     w.loss_part, w.acc, w.nbr, i > 0 && P->decode_kernel != 1, st)))
         return rc;
     }
     if (stat) {

@@ -141,6 +141,10 @@ typedef struct ifd_opt_params {
   double rep_weight;     /* 500 */
   double rep_radius, rep_h, rep_eps; /* 0.07, 0.03, 1e-12 */
   double padding;        /* cfg['data']['padding'] = 0.1 */
+  int32_t decode_kernel; /* 0: production decode kernel (v2: cooperative gather, 2 points/thread, FFMA2);
+                            1: the first-generation thread-per-point kernel (kept as the step-level seam and for
+                            A/B profiles; same arithmetic, different reduction order in the gather backward) */
+  int32_t reserved_;
 } ifd_opt_params;
 
 void ifd_opt_params_default(ifd_opt_params* p);
