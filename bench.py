@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-kernel", type=int, default=0, help="ifd_opt_params.decode_kernel (0 = production default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -156,7 +157,7 @@ def main():
     dec = convonet.ConvONetDecoder(sd, padding=0.1)
     C, H, nb = dec.dims
     R = batches[0][1].shape[2]
-    P = capi.default_params(n_steps=ITERS + 1, B_ref=B)
+    P = capi.default_params(n_steps=ITERS + 1, B_ref=B, decode_kernel=args.decode_kernel)
     ws_bytes = L.ifd_convonet_opt_workspace_bytes(B, K)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
     x = torch.empty((B, K, 3), dtype=torch.float32, device="cuda")

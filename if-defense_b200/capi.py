@@ -50,6 +50,7 @@ SIGNATURES = {
                                        ctypes.POINTER(OptParams), _vp]),
     "ifd_release_cache": (None, []),
     "ifd_launch_count": (ctypes.c_longlong, [_c_int]),
+    "ifd_selftest_umma": (_c_int, [_vp, _vp, _vp, _vp]),
     "ifd_profile_enable": (None, [_c_int]),
     "ifd_profile_read": (_c_int, [_vp, _vp]),
 }

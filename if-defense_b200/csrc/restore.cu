@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "convonet_point.cuh"
 #include "decode_v2.cuh"
+#include "decode_v3.cuh"
 #include "topk.cuh"
 
 namespace ifd {
@@ -388,6 +389,19 @@ static int launch_decode_v2(const DecodeArgs& a, cudaStream_t st) {
   return IFD_OK;
 }
 
+static int launch_decode_v3(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
+  DecodeV3Args v{};
+  v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
+  v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
+  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv;
+  const size_t smem = DecodeV3Smem::bytes(a.n_blocks);
+  if (smem > 227 * 1024) return fail(IFD_ERR_UNSUPPORTED, "decode v3 supports n_blocks <= 6");
+  IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  convonet_decode_v3_kernel<<<(v.n + kV3Pts - 1) / kV3Pts, kV3Threads, smem, st>>>(v);
+  IFD_LAUNCH_CHECK("convonet_decode_v3_kernel");
+  return IFD_OK;
+}
+
 static int launch_knn_repulsion(const float* xyz, int B, int K, int k, float radius, float h, float eps,
                                 int32_t* idx_out, float* loss_part, long long* acc, int32_t* nbr, bool warm,
                                 cudaStream_t st) {
@@ -417,6 +431,7 @@ struct OptWorkspace {
   float* loss_part;
   double* dec_part;
   int32_t* nbr;
+  float* wimg;
   size_t bytes;
 };
 static OptWorkspace carve_opt_ws(void* base, int B, int K) {
@@ -435,6 +450,7 @@ static OptWorkspace carve_opt_ws(void* base, int B, int K) {
   w.loss_part = (float*)take((size_t)B * rep_chunks(K) * sizeof(float));
   w.dec_part = (double*)take((size_t)((B * K + kDecThreads - 1) / kDecThreads) * 2 * sizeof(double));
   w.nbr = (int32_t*)take((size_t)B * K * 8 * sizeof(int32_t));
+  w.wimg = (float*)take((size_t)2 * 3 * kMaxBlocks * kV3ImgFloats * sizeof(float));
   w.bytes = off;
   return w;
 }
@@ -562,14 +578,22 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   // rep_loss = mean_B(mean_{K,k}) * rep_weight: grad = rep_weight / B_ref / (K*k)
   const float rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
   const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
-  const int n_dec = P->decode_kernel == 1 ? (B * K + kDecThreads - 1) / kDecThreads : (B * K + kV2Pts - 1) / kV2Pts;
+  const int n_dec = P->decode_kernel == 1 ? (B * K + kDecThreads - 1) / kDecThreads : (B * K + kV2Pts - 1) / kV2Pts;   // v2, v3: 512-point tiles
 
+  const int dk = P->decode_kernel == 0 ? 2 : P->decode_kernel;
+  if (dk < 1 || dk > 3) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0..3");
+  if (dk == 3) {
+    const int nl = 3 * n_blocks;
+    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg);
+    IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
+  }
   for (int i = 0; i < P->n_steps; ++i) {
     const bool stat = P->want_stats && stats_out && (i % 100 == 0);
     a.stat_part = stat ? w.dec_part : nullptr;
     {
       ProfileScope ps(0, st);
-      if ((rc = P->decode_kernel == 1 ? launch_decode(kBce, a, st) : launch_decode_v2(a, st))) return rc;
+      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+      if (rc) return rc;
     }
     if (rep) {
       ProfileScope ps(1, st);
@@ -597,5 +621,12 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
     normalize_kernel<<<B, kNormThreads, 0, st>>>(xyz, K);
     IFD_LAUNCH_CHECK("normalize_kernel");
   }
+  return IFD_OK;
+}
+
+extern "C" int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream) {
+  IFD_REQUIRE(A && Bm && D, "ifd_selftest_umma: null pointer");
+  umma_selftest_kernel<<<1, 128, 0, as_stream(stream)>>>(A, Bm, D);
+  IFD_LAUNCH_CHECK("umma_selftest_kernel");
   return IFD_OK;
 }

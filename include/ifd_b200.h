@@ -141,9 +141,10 @@ typedef struct ifd_opt_params {
   double rep_weight;     /* 500 */
   double rep_radius, rep_h, rep_eps; /* 0.07, 0.03, 1e-12 */
   double padding;        /* cfg['data']['padding'] = 0.1 */
-  int32_t decode_kernel; /* 0: production decode kernel (v2: cooperative gather, 2 points/thread, FFMA2);
-                            1: the first-generation thread-per-point kernel (kept as the step-level seam and for
-                            A/B profiles; same arithmetic, different reduction order in the gather backward) */
+  int32_t decode_kernel; /* which decode kernel the loop launches -- 0: the production default;
+                            1: v1, thread-per-point fp32 SIMT (the step-level seam; from-scratch kNN every step);
+                            2: v2, fp32 SIMT, cooperative gather, 2 points/thread, FFMA2, generic layer bodies;
+                            3: v3, ResNet-MLP on tcgen05 tensor cores (3xTF32, A in TMEM, fp32-class accuracy) */
   int32_t reserved_;
 } ifd_opt_params;
 
@@ -175,6 +176,10 @@ long long ifd_launch_count(int reset);
  * restoration loop is bracketed by CUDA events on the launching stream.  ifd_profile_read synchronises the
  * device, sums the elapsed time per kernel kind, clears the record and returns the number of kinds written:
  * 0 = decode (gather + MLP fwd/bwd), 1 = kNN + repulsion, 2 = Adam, 3 = everything else. */
+/* Tensor-core self test: D[128][32] = A[128][32] . Bm[32][32]^T (Bm is [n][k]) through the tcgen05 / TMEM /
+ * 3xTF32 path of the v3 decode kernel.  Device pointers. */
+int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream);
+
 #define IFD_PROFILE_KINDS 4
 void ifd_profile_enable(int on);
 int ifd_profile_read(double* ms_out, long long* launches_out);

@@ -90,6 +90,44 @@ def test_production_kernels_equal_first_generation(conv, dec, planes):
     np.testing.assert_allclose(sa, sb, rtol=1e-6)
 
 
+def test_tensor_core_selftest():
+    """tcgen05 / TMEM / 3xTF32 plumbing: D = A . B^T for one 128 x 32 x 32 tile against float64."""
+    rng = np.random.default_rng(0)
+    A = (rng.normal(size=(128, 32)) * rng.uniform(0.01, 3.0, size=(128, 1))).astype(np.float32)
+    Bm = rng.normal(size=(32, 32)).astype(np.float32) / 5.0
+    Ad, Bd = dev(A), dev(Bm)
+    D = torch.zeros((128, 32), dtype=torch.float32, device="cuda")
+    capi.check(capi.lib().ifd_selftest_umma(capi.ptr(Ad), capi.ptr(Bd), capi.ptr(D), capi.stream()))
+    torch.cuda.synchronize()
+    want = A.astype(np.float64) @ Bm.astype(np.float64).T
+    scale = (np.abs(A).astype(np.float64) @ np.abs(Bm).astype(np.float64).T)
+    err = np.abs(D.cpu().numpy() - want) / scale
+    assert err.max() < 2e-6, err.max()         # fp32-class: a plain fp32 FMA chain gives ~1e-7..1e-6 here
+
+
+def test_tensor_core_decode_kernel(conv, dec, planes):
+    """decode v3 (ResNet-MLP on tcgen05, 3xTF32) against the fp32 SIMT kernels and the reference fixtures at the
+    same tolerances as the fp32 path."""
+    for n_steps, tol in ((1, 1e-6), (2, 1e-6), (10, 5e-6), (20, 2e-5)):
+        x, _ = run_opt(dec, planes, conv["p0"], n_steps, decode_kernel=3)
+        assert np.abs(x - conv["trace/xyz_%d" % (n_steps - 1)]).max() < tol, n_steps
+    a, sa = run_opt(dec, planes, conv["p0"], 5, decode_kernel=3, stats=True)
+    b, sb = run_opt(dec, planes, conv["p0"], 5, decode_kernel=2, stats=True)
+    assert np.abs(a - b).max() < 1e-6
+    np.testing.assert_allclose(sa, sb, rtol=1e-5)
+    m, v = dev(conv["trace/late_m"]).clone(), dev(conv["trace/late_v"]).clone()
+    x, _ = run_opt(dec, planes, conv["trace/late_xyz"], 1, m=m, v=v, step0=150, decode_kernel=3)
+    assert np.abs(x - conv["trace/late_xyz_next"]).max() < 1e-6
+    case = synth.make_case(3, K=1024, seed=5, device="cuda")         # ragged last tile
+    d3 = convonet.ConvONetDecoder(case.sd)
+    pl = convonet.planes_to_channels_last({k: v.cuda() for k, v in case.c.items()})
+    a, _ = run_opt(d3, pl, case.p0[:, :1000].contiguous(), 12, decode_kernel=3)
+    b, _ = run_opt(d3, pl, case.p0[:, :1000].contiguous(), 12, decode_kernel=2)
+    assert np.abs(a - b).max() < 5e-6
+    a2, _ = run_opt(d3, pl, case.p0[:, :1000].contiguous(), 12, decode_kernel=3)
+    assert np.array_equal(a, a2)                                     # bitwise reproducible
+
+
 def test_201_steps_statistical_parity(conv, dec, planes):
     """At 201 steps the reference does not reproduce itself (8-thread vs 1-thread CPU runs differ by 3e-2
     max-abs, median 1.5e-4): parity is distributional, measured against that noise floor."""
