@@ -624,6 +624,33 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   return IFD_OK;
 }
 
+extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,
+                                            int R, int C, int H, int n_blocks, double padding, double occ_target, int B_ref,
+                                            int decode_kernel, float* grad_xyz_out, void* workspace, size_t workspace_bytes,
+                                            ifd_stream_t stream) {
+  IFD_REQUIRE(planes_cl && dec_weights && xyz && grad_xyz_out && B > 0 && K > 0 && B_ref > 0, "ifd_convonet_decode_bce_grad: bad arguments");
+  int rc = check_decoder_cfg(R, C, H, n_blocks);
+  if (rc) return rc;
+  if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
+  IFD_REQUIRE(workspace, "ifd_convonet_decode_bce_grad: workspace is required");
+  if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_decode_bce_grad: workspace too small");
+  const int dk = decode_kernel == 0 ? 2 : decode_kernel;
+  if (dk < 1 || dk > 3) return fail(IFD_ERR_INVALID, "decode_kernel must be 0..3");
+  cudaStream_t st = as_stream(stream);
+  OptWorkspace w = carve_opt_ws(workspace, B, K);
+  DecodeArgs a{};
+  a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_out = grad_xyz_out;
+  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(padding);
+  a.target = (float)occ_target;
+  a.ginv = (float)K / (float)((long long)B_ref * K);
+  if (dk == 3) {
+    const int nl = 3 * n_blocks;
+    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg);
+    IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
+  }
+  return dk == 1 ? launch_decode(kBce, a, st) : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+}
+
 extern "C" int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream) {
   IFD_REQUIRE(A && Bm && D, "ifd_selftest_umma: null pointer");
   umma_selftest_kernel<<<1, 128, 0, as_stream(stream)>>>(A, Bm, D);

@@ -119,6 +119,15 @@ int ifd_convonet_decode_bwd(const float* planes_cl, const float* dec_weights, co
                             const float* grad_logits, int B, int K, int R, int C, int H, int n_blocks,
                             double padding, float* grad_xyz_out, ifd_stream_t stream);
 
+/* The fused "decode + BCE-with-logits gradient" step of the loop as a seam of its own (opt_defense.py:212-216
+ * followed by backward to xyz): grad_xyz_out = d( K * mean_{B_ref,K} BCEWithLogits(logit, occ_target) ) / d xyz,
+ * computed by the decode kernel selected with decode_kernel (see ifd_opt_params).  logits are not returned.
+ * Workspace: ifd_convonet_opt_workspace_bytes(B, K). */
+int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,
+                                 int R, int C, int H, int n_blocks, double padding, double occ_target, int B_ref,
+                                 int decode_kernel, float* grad_xyz_out, void* workspace, size_t workspace_bytes,
+                                 ifd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * The restoration loop
  * ---------------------------------------------------------------------------------------------- */

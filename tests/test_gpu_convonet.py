@@ -105,6 +105,37 @@ def test_tensor_core_selftest():
     assert err.max() < 2e-6, err.max()         # fp32-class: a plain fp32 FMA chain gives ~1e-7..1e-6 here
 
 
+def bce_grad(dec, planes, xyz, kernel, B_ref=None):
+    x = dev(xyz)
+    B, K, _ = x.shape
+    L = capi.lib()
+    ws = torch.empty(L.ifd_convonet_opt_workspace_bytes(B, K), dtype=torch.uint8, device="cuda")
+    g = torch.empty_like(x)
+    capi.check(L.ifd_convonet_decode_bce_grad(capi.ptr(planes), capi.ptr(dec.blob), capi.ptr(x), B, K, planes.shape[2], 32, 32, 5,
+                                              0.1, 0.2, B if B_ref is None else B_ref, kernel, capi.ptr(g), capi.ptr(ws),
+                                              ws.numel(), capi.stream()))
+    torch.cuda.synchronize()
+    return g.cpu().numpy()
+
+
+def test_bce_grad_seam_all_kernels(conv, conv_sd, conv_planes, dec, planes):
+    """d(K * mean BCE(logit, 0.2))/dxyz from the three decode kernels against torch autograd on the oracle."""
+    import torch.nn.functional as F
+    from oracle import torch_port as tp
+    p = torch.from_numpy(conv["p0"]).requires_grad_()
+    lg = tp.convonet_decode(conv_sd, p, conv_planes)
+    (F.binary_cross_entropy_with_logits(lg, torch.full_like(lg, 0.2), reduction="none").mean() * p.shape[1]).backward()
+    want = p.grad.numpy()
+    scale = np.abs(want).max()
+    errs = {}
+    for kernel in (1, 2, 3):
+        g = bce_grad(dec, planes, conv["p0"], kernel)
+        errs[kernel] = np.abs(g - want).max() / scale
+    print("bce-grad max error / max|grad| per kernel:", errs)
+    assert errs[1] < 2e-6 and errs[2] < 2e-6
+    assert errs[3] < 2e-5          # 3xTF32 tensor-core path: fp32-class, ~2^-21 per product term
+
+
 def test_tensor_core_decode_kernel(conv, dec, planes):
     """decode v3 (ResNet-MLP on tcgen05, 3xTF32) against the fp32 SIMT kernels and the reference fixtures at the
     same tolerances as the fp32 path."""
