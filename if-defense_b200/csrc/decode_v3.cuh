@@ -61,7 +61,8 @@ struct DecodeV3Args {
 
 struct DecodeV3Smem {
   static __host__ __device__ size_t bytes(int n_blocks) {
-    return (size_t)3 * n_blocks * kV3ImgFloats * 4 + (size_t)32 * kV3Stride * 4 + (size_t)kV3Pts * 16 + 256;
+    return (size_t)3 * n_blocks * kV3ImgFloats * 4 + (size_t)32 * kV3Stride * 4 + (size_t)kV3Pts * 16 + 256 +
+           (size_t)(3 * n_blocks + 6) * 32 * 4;       // + per-layer biases, fc_p (W^T 3x32, b), fc_out (w, b)
   }
 };
 
@@ -71,11 +72,11 @@ __device__ __forceinline__ void v3_layer(const float (&x)[32], uint32_t (&d)[32]
                                          uint32_t img_saddr, uint64_t* bar, uint32_t& parity, int group, bool leader) {
   // `d` doubles as the staging registers of the two tcgen05.st (it is dead until the final tcgen05.ld)
 #pragma unroll
-  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi(x[k]);
+  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi_fast(x[k]);
   umma::tmem_st32(lane_taddr + 32, d);
   umma::tmem_wait_st();
 #pragma unroll
-  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_lo(x[k]);
+  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_lo_fast(x[k], d[k]);
   umma::tmem_st32(lane_taddr + 64, d);
   umma::tmem_wait_st();
   umma::fence_before_sync();
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
   float4* gpart = reinterpret_cast<float4*>(feat + 32 * kV3Stride);         // [kV3Pts]
   uint64_t* bars = reinterpret_cast<uint64_t*>(gpart + kV3Pts);             // [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  const float* Wb = a.W;                                                    // small per-layer vectors: read through L1
+  float* vec = reinterpret_cast<float*>(reinterpret_cast<char*>(bars) + 256);   // [n_layers][32] biases | fc_p 4x32 | fc_out 2x32
+  const float* Wb = a.W;
 
   const int tile0 = blockIdx.x * kV3Pts;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,6 +129,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
     const float4* src = reinterpret_cast<const float4*>(a.Wimg);
     float4* dst = reinterpret_cast<float4*>(wimg);
     for (int i = threadIdx.x; i < n_layers * kV3ImgFloats / 4; i += kV3Threads) dst[i] = src[i];
+  }
+  for (int i = threadIdx.x; i < (n_layers + 6) * 32; i += kV3Threads) {
+    const int row = i >> 5, c = i & 31;
+    float v;
+    if (row < n_layers) v = Wb[L::kBlk0 + row * L::kLayer + 1024 + c];
+    else if (row < n_layers + 4) v = Wb[(row - n_layers) * 32 + c];          // fc_p W^T rows 0..2, then fc_p.b
+    else if (row == n_layers + 4) v = Wb[L::out_w(a.n_blocks) + c];
+    else v = c == 0 ? Wb[L::out_b(a.n_blocks)] : 0.0f;
+    vec[i] = v;
   }
   // ---------------- forward gather: warp w serves tile slots 32w .. 32w+31 (its own threads' points)
   for (int it = 0; it < 8; ++it) {
@@ -175,19 +186,20 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
   float net[32], x[32];
   uint32_t d[32];
   uint32_t mask_a[kMaxBlocks], mask_h[kMaxBlocks];
+  const float* fcp = vec + n_layers * 32;
 #pragma unroll
   for (int o = 0; o < 32; ++o) {
-    float v = Wb[L::kFcpB + o];
-    v = fmaf(Wb[L::kFcpW + 0 * 32 + o], p0, v);
-    v = fmaf(Wb[L::kFcpW + 1 * 32 + o], p1, v);
-    v = fmaf(Wb[L::kFcpW + 2 * 32 + o], p2, v);
+    float v = fcp[3 * 32 + o];
+    v = fmaf(fcp[0 * 32 + o], p0, v);
+    v = fmaf(fcp[1 * 32 + o], p1, v);
+    v = fmaf(fcp[2 * 32 + o], p2, v);
     net[o] = v;
   }
 #pragma unroll 1
   for (int blk = 0; blk < a.n_blocks; ++blk) {
-    const float* bc = Wb + L::fc_c(blk) + 1024;
-    const float* b0 = Wb + L::fc_0(blk) + 1024;
-    const float* b1 = Wb + L::fc_1(blk) + 1024;
+    const float* bc = vec + (3 * blk + 0) * 32;
+    const float* b0 = vec + (3 * blk + 1) * 32;
+    const float* b1 = vec + (3 * blk + 2) * 32;
 #pragma unroll
     for (int k = 0; k < 32; ++k) x[k] = feat[k * kV3Stride + slot];
     v3_layer(x, d, tile_taddr, lane_taddr, wimg_saddr + (3 * blk + 0) * kV3ImgFloats * 4, bar, parity, group, leader);
@@ -212,8 +224,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
 #pragma unroll
     for (int k = 0; k < 32; ++k) net[k] += __uint_as_float(d[k]) + b1[k];   // net = net + fc_1(relu(h))
   }
-  const float* wo = Wb + L::out_w(a.n_blocks);
-  float logit = Wb[L::out_b(a.n_blocks)];
+  const float* wo = vec + (n_layers + 4) * 32;
+  float logit = vec[(n_layers + 5) * 32];
   uint32_t mask_f = 0;
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
@@ -287,7 +299,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
     for (int dd = 0; dd < 3; ++dd) {
       float s = 0.0f;
 #pragma unroll
-      for (int o = 0; o < 32; ++o) s = fmaf(Wb[L::kFcpW + dd * 32 + o], gnet[o], s);
+      for (int o = 0; o < 32; ++o) s = fmaf(fcp[dd * 32 + o], gnet[o], s);
       g[dd] = s;
     }
     gpart[slot] = make_float4(g[0], g[1], g[2], 0.f);

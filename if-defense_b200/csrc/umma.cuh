@@ -123,6 +123,12 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
 }
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return tf32_rna(x); }
 __device__ __forceinline__ uint32_t tf32_lo(float x) { return tf32_rna(x - __uint_as_float(tf32_rna(x))); }
+// Hot-path variants: round-to-nearest (ties away) by integer arithmetic on the bit pattern -- 2 instructions
+// instead of the 3 of cvt.rna (which also screens Inf/NaN; activations on this path are finite).  x - hi is exact.
+__device__ __forceinline__ uint32_t tf32_hi_fast(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo_fast(float x, uint32_t hi) {
+  return (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+}
 
 // Byte offset of element (n, k) inside a K-major no-swizzle image of an [N][K] fp32/tf32 matrix, laid out as
 // [K/4][N/8] core matrices of 128 bytes: LBO = (N/8)*128, SBO = 128.
