@@ -95,14 +95,17 @@ class Restorer:
     """Holds what the reference keeps in module globals (generator, args.threshold, args.lr) and exposes
     optimize_points with the reference's signature."""
 
-    def __init__(self, decoder, threshold=0.2, lr=1e-3):
+    def __init__(self, decoder, threshold=0.2, lr=1e-3, decode_kernel=0):
+        """decode_kernel: 0 = production default (tcgen05 tensor-core MLP, 3xTF32); 2 = fp32 SIMT kernels, for
+        bit-level trajectory comparisons with an fp32 reference (see include/ifd_b200.h, ifd_opt_params)."""
         self.decoder, self.threshold, self.lr = decoder, float(threshold), float(lr)
+        self.decode_kernel = int(decode_kernel)
         self.last_stats = None
 
     def params(self, B_ref, rep_weight, iterations, want_stats=False, **over):
         return capi.default_params(n_steps=iterations + 1, B_ref=int(B_ref), rep_weight=float(rep_weight),
                                    lr=self.lr, occ_target=self.threshold, padding=self.decoder.padding,
-                                   want_stats=int(bool(want_stats)), **over)
+                                   want_stats=int(bool(want_stats)), decode_kernel=self.decode_kernel, **over)
 
     def optimize_points(self, opt_points, z, c, rep_weight=1., iterations=1000, printing=False, B_ref=None,
                         return_tensor=False):

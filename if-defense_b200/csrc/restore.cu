@@ -148,19 +148,40 @@ __global__ void __launch_bounds__(kRepThreads) knn_repulsion_kernel(const float*
     if (WARM) {
       int* buf = reinterpret_cast<int*>(cand + K) + threadIdx.x;     // column of this thread, stride kRepThreads
       const int32_t* prev = nbr + ((size_t)b * K + q) * KK;
+      // -2 * dot(i, j) == dot(-2 * x_i, x_j) bit for bit (scaling by a power of two commutes with rounding),
+      // so the factor is folded into the query once instead of once per candidate
+      const float mx = -2.0f * me.x, my = -2.0f * me.y, mz = -2.0f * me.z;
       float tau = -INFINITY;
 #pragma unroll
       for (int s = 0; s < KK; ++s)
         if (s <= k) {
           const float4 c = cand[prev[s]];
-          tau = fmaxf(tau, knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)));
+          tau = fmaxf(tau, add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w));
         }
       int cnt = 0;
-#pragma unroll 8
-      for (int j = 0; j < K; ++j) {
+      const int K8 = K & ~7;
+      for (int j0 = 0; j0 < K8; j0 += 8) {
+        float d[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {          // branch-free: eight independent dependency chains in flight
+          const float4 c = cand[j0 + u];
+          d[u] = add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w);
+        }
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) any |= d[u] <= tau;
+        if (any) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (d[u] <= tau) {
+              if (cnt < kWarmCap) buf[cnt * kRepThreads] = j0 + u;
+              ++cnt;
+            }
+        }
+      }
+      for (int j = K8; j < K; ++j) {
         const float4 c = cand[j];
-        const float d = knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z));
-        if (d <= tau) {
+        if (add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w) <= tau) {
           if (cnt < kWarmCap) buf[cnt * kRepThreads] = j;
           ++cnt;
         }
@@ -580,7 +601,7 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
   const int n_dec = P->decode_kernel == 1 ? (B * K + kDecThreads - 1) / kDecThreads : (B * K + kV2Pts - 1) / kV2Pts;   // v2, v3: 512-point tiles
 
-  const int dk = P->decode_kernel == 0 ? 2 : P->decode_kernel;
+  const int dk = P->decode_kernel == 0 ? 3 : P->decode_kernel;
   if (dk < 1 || dk > 3) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0..3");
   if (dk == 3) {
     const int nl = 3 * n_blocks;
@@ -598,7 +619,7 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
     if (rep) {
       ProfileScope ps(1, st);
       if ((rc = launch_knn_repulsion(xyz, B, K, P->knn_k, (float)P->rep_radius, (float)P->rep_h, (float)P->rep_eps, nullptr,
-                                     w.loss_part, w.acc, w.nbr, i > 0 && P->decode_kernel != 1, st)))
+                                     w.loss_part, w.acc, w.nbr, i > 0 && dk != 1, st)))
         return rc;
     }
     if (stat) {
@@ -634,7 +655,7 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
   IFD_REQUIRE(workspace, "ifd_convonet_decode_bce_grad: workspace is required");
   if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_decode_bce_grad: workspace too small");
-  const int dk = decode_kernel == 0 ? 2 : decode_kernel;
+  const int dk = decode_kernel == 0 ? 3 : decode_kernel;
   if (dk < 1 || dk > 3) return fail(IFD_ERR_INVALID, "decode_kernel must be 0..3");
   cudaStream_t st = as_stream(stream);
   OptWorkspace w = carve_opt_ws(workspace, B, K);

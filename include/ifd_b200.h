@@ -150,7 +150,7 @@ typedef struct ifd_opt_params {
   double rep_weight;     /* 500 */
   double rep_radius, rep_h, rep_eps; /* 0.07, 0.03, 1e-12 */
   double padding;        /* cfg['data']['padding'] = 0.1 */
-  int32_t decode_kernel; /* which decode kernel the loop launches -- 0: the production default;
+  int32_t decode_kernel; /* which decode kernel the loop launches -- 0: the production default (= 3);
                             1: v1, thread-per-point fp32 SIMT (the step-level seam; from-scratch kNN every step);
                             2: v2, fp32 SIMT, cooperative gather, 2 points/thread, FFMA2, generic layer bodies;
                             3: v3, ResNet-MLP on tcgen05 tensor cores (3xTF32, A in TMEM, fp32-class accuracy) */

