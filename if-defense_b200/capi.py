@@ -50,6 +50,12 @@ SIGNATURES = {
                                   ctypes.POINTER(OptParams), _vp, _vp, _c_sz, _vp]),
     "ifd_convonet_opt_host": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        ctypes.POINTER(OptParams), _vp]),
+    "ifd_onet_decoder_nfloats": (_c_sz, []),
+    "ifd_onet_workspace_bytes": (_c_sz, [_c_int, _c_int]),
+    "ifd_onet_prepare": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _c_sz, _vp]),
+    "ifd_onet_decode_fwd": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
+    "ifd_onet_decode_bwd": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _vp, _vp, _c_sz, _vp]),
+    "ifd_onet_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, ctypes.POINTER(OptParams), _vp, _vp, _c_sz, _vp]),
     "ifd_release_cache": (None, []),
     "ifd_launch_count": (ctypes.c_longlong, [_c_int]),
     "ifd_selftest_umma": (_c_int, [_vp, _vp, _vp, _vp]),

@@ -1,0 +1,579 @@
+// onet.cu -- ONet-Opt: DecoderCBatchNorm forward + dgrad on the tensor cores, and the restoration loop.
+//
+// Reference: ONet/im2mesh/onet/models/decoder.py:115-133 (DecoderCBatchNorm.forward), ONet/im2mesh/layers.py:98-107
+// (CResnetBlockConv1d), :226-242 (CBatchNorm1d), ONet/opt_defense.py:182-239 (optimize_points).
+//
+// The model is in eval() (ONet/opt_defense.py:71), so each of the 11 conditional batch norms is a per-cloud,
+// per-channel affine  y = s_b[ch] * x + t_b[ch]  that is constant over the 201 iterations: it is folded once per
+// batch (onet_fold_cbn_kernel) and applied as the prologue of the GEMM that consumes it.
+//
+// The ten 256x256 layers per direction are real GEMMs (M = B*K points, N = K = 256): one tcgen05 kernel,
+//   Y[M][256] = prologue(A)[M][256] . W^T  (+ bias, + residual)                       forward
+//   Y[M][256] = (G[M][256] . W) * s_b * [s_b * Xsaved + t_b > 0]  (+ residual)        dgrad through CBN+ReLU
+// A CTA owns 128 rows; thread r owns row r: it reads a 32-column chunk of its row, applies the prologue, splits it
+// into TF32 hi/lo and writes it to TMEM with tcgen05.st (A operand in TMEM, no shared-memory staging); the weight
+// chunk [256 x 32] hi/lo streams from a pre-packed K-major image in L2 into a double-buffered shared-memory slot;
+// twelve tcgen05.mma (3xTF32 x four K=8 steps, M=128, N=256) accumulate into 256 TMEM columns.  Activations of the
+// forward pass are kept in HBM (11 x [M][256] fp32) for the dgrad masks -- 740 MB at B=64, K=1024.
+#include "common.cuh"
+#include "ifd_math.cuh"
+#include "umma.cuh"
+
+namespace ifd {
+
+constexpr int kOH = 256;          // hidden size
+constexpr int kOC = 512;          // c_dim
+constexpr int kOnetCbn = 11;      // block{0..4}.bn_{0,1}, bn
+constexpr int kGemmThreads = 128;
+constexpr int kChunk = 32;                              // K columns per pipeline step
+constexpr int kChunkImgFloats = 2 * kOH * kChunk;       // hi + lo of a [256 x 32] chunk
+constexpr int kLayerImgFloats = (kOH / kChunk) * kChunkImgFloats;   // 131072 floats = 512 KB
+
+// ---------------------------------------------------------------------------------------------- packing
+// One layer's weight W[n][k] (row-major [256][256]) -> chunked K-major UMMA images, hi then lo per chunk.
+// transpose = 1 packs W^T (the dgrad operand).
+__global__ void onet_pack_layer_kernel(const float* __restrict__ W, int transpose, float* __restrict__ img) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= kOH * kOH) return;
+  const int n = e / kOH, k = e % kOH;                     // element (n, k) of the B operand [N][K]
+  const float w = transpose ? W[k * kOH + n] : W[n * kOH + k];
+  const int kc = k / kChunk, kl = k % kChunk;
+  float* chunk = img + (size_t)kc * kChunkImgFloats;
+  const uint32_t off = umma::img_offset(n, kl, kOH) / 4;
+  chunk[off] = __uint_as_float(umma::tf32_hi(w));
+  chunk[kOH * kChunk + off] = __uint_as_float(umma::tf32_lo(w));
+}
+
+// Fold the 11 eval-mode CBNs: s[cbn][b][ch] = gamma / sqrt(var + 1e-5), t = beta - mean * s,
+// gamma = Wg c_b + bg, beta = Wb c_b + bb  (layers.py:226-242).  One warp per (cbn, b, ch).
+struct CbnParams {
+  const float* Wg; const float* bg; const float* Wb; const float* bb; const float* mean; const float* var;
+};
+struct CbnTable { CbnParams p[kOnetCbn]; };
+__global__ void onet_fold_cbn_kernel(const CbnTable tab, const float* __restrict__ c, int B, float* __restrict__ s_out,
+                                     float* __restrict__ t_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= kOnetCbn * B * kOH) return;
+  const int ch = warp % kOH, b = (warp / kOH) % B, j = warp / (kOH * B);
+  const CbnParams p = tab.p[j];
+  const float* cb = c + (size_t)b * kOC;
+  float g = 0.f, be = 0.f;
+  for (int k = lane; k < kOC; k += 32) {
+    g = fmaf(p.Wg[(size_t)ch * kOC + k], cb[k], g);
+    be = fmaf(p.Wb[(size_t)ch * kOC + k], cb[k], be);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    g += __shfl_xor_sync(0xffffffffu, g, o);
+    be += __shfl_xor_sync(0xffffffffu, be, o);
+  }
+  if (lane == 0) {
+    g += p.bg[ch];
+    be += p.bb[ch];
+    const float inv = 1.0f / sqrtf(p.var[ch] + 1e-5f);
+    const float s = g * inv;
+    s_out[((size_t)j * B + b) * kOH + ch] = s;
+    t_out[((size_t)j * B + b) * kOH + ch] = be - p.mean[ch] * s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- the GEMM
+struct GemmArgs {
+  const float* A;        // [M][256] input rows
+  const float* pro_s;    // [B][256] prologue scale (nullptr: identity prologue, no ReLU)
+  const float* pro_t;    // [B][256]
+  const float* img;      // packed weight images of this layer / direction
+  const float* bias;     // [256] or nullptr
+  const float* resid;    // [M][256] or nullptr
+  const float* mask_x;   // dgrad epilogue: saved forward activation [M][256] (nullptr: plain epilogue)
+  const float* mask_s;   // [B][256]
+  const float* mask_t;   // [B][256]
+  float* out;            // [M][256]
+  int M, K;              // rows, points per cloud
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmArgs a) {
+  extern __shared__ float4 smem4[];
+  float* bbuf = reinterpret_cast<float*>(smem4);                    // [2][kChunkImgFloats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + 2 * kChunkImgFloats);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x == 32) {
+    umma::mbar_init(&bars[0], 1);
+    umma::mbar_init(&bars[1], 1);
+    umma::fence_mbar_init();
+  }
+  {  // weight chunk 0
+    const float4* src = reinterpret_cast<const float4*>(a.img);
+    float4* dst = reinterpret_cast<float4*>(bbuf);
+    for (int i = threadIdx.x; i < kChunkImgFloats / 4; i += kGemmThreads) dst[i] = src[i];
+  }
+  umma::fence_proxy_async();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t lane_t = tmem + ((uint32_t)(warp * 32) << 16);
+  const int row = blockIdx.x * kGemmThreads + threadIdx.x;
+  const int rowc = min(row, a.M - 1);
+  const int b = rowc / a.K;
+  const float* arow = a.A + (size_t)rowc * kOH;
+  const bool leader = threadIdx.x == 0;
+  uint32_t parity[2] = {0u, 0u};
+  constexpr uint32_t idesc = umma::idesc_tf32(128, kOH);
+
+#pragma unroll 1
+  for (int kc = 0; kc < kOH / kChunk; ++kc) {
+    const int buf = kc & 1;
+    float x[32];
+    {
+      const float4* p4 = reinterpret_cast<const float4*>(arow + kc * kChunk);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = __ldg(p4 + q);
+        x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+      }
+    }
+    if (a.pro_s) {
+      const float4* s4 = reinterpret_cast<const float4*>(a.pro_s + (size_t)b * kOH + kc * kChunk);
+      const float4* t4 = reinterpret_cast<const float4*>(a.pro_t + (size_t)b * kOH + kc * kChunk);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 s = __ldg(s4 + q), t = __ldg(t4 + q);
+        x[4 * q + 0] = fmaxf(fmaf(s.x, x[4 * q + 0], t.x), 0.0f);
+        x[4 * q + 1] = fmaxf(fmaf(s.y, x[4 * q + 1], t.y), 0.0f);
+        x[4 * q + 2] = fmaxf(fmaf(s.z, x[4 * q + 2], t.z), 0.0f);
+        x[4 * q + 3] = fmaxf(fmaf(s.w, x[4 * q + 3], t.w), 0.0f);
+      }
+    }
+    if (kc >= 1) {
+      if (kc >= 2) {                      // MMA kc-2 read A/B slot `buf`: it must have completed
+        umma::mbar_wait(&bars[buf], parity[buf]);
+        parity[buf] ^= 1;
+        umma::fence_after_sync();
+      }
+      const float4* src = reinterpret_cast<const float4*>(a.img + (size_t)kc * kChunkImgFloats);
+      float4* dst = reinterpret_cast<float4*>(bbuf + (size_t)buf * kChunkImgFloats);
+      for (int i = threadIdx.x; i < kChunkImgFloats / 4; i += kGemmThreads) dst[i] = __ldg(src + i);
+      umma::fence_proxy_async();
+    }
+    uint32_t u[32];
+    const uint32_t a_hi = lane_t + 256 + buf * 64, a_lo = a_hi + 32;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) u[k] = umma::tf32_hi_fast(x[k]);
+    umma::tmem_st32(a_hi, u);
+    umma::tmem_wait_st();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) u[k] = umma::tf32_lo_fast(x[k], u[k]);
+    umma::tmem_st32(a_lo, u);
+    umma::tmem_wait_st();
+    umma::fence_before_sync();
+    __syncthreads();
+    if (leader) {
+      umma::fence_after_sync();
+      const uint32_t ta_hi = tmem + 256 + buf * 64, ta_lo = ta_hi + 32;
+      const uint32_t sb = umma::smem_u32(bbuf + (size_t)buf * kChunkImgFloats);
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {        // lo.hi, hi.lo, hi.hi
+        const uint32_t ta = part == 0 ? ta_lo : ta_hi;
+        const uint32_t bs = sb + (part == 1 ? (uint32_t)(kOH * kChunk * 4) : 0u);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma::mma_tf32_ts(tmem, ta + s * 8, umma::smem_desc_kmajor(bs + s * 2 * (kOH / 8) * 128, (kOH / 8) * 128, 128), idesc,
+                            (kc | part | s) ? 1u : 0u);
+      }
+      umma::commit(&bars[buf]);
+    }
+    __syncwarp();
+  }
+  // the last commit covers every earlier MMA
+  umma::mbar_wait(&bars[1], parity[1]);
+  umma::fence_after_sync();
+
+  float* orow = a.out + (size_t)rowc * kOH;
+  const bool live = row < a.M;
+#pragma unroll 1
+  for (int cg = 0; cg < kOH / 32; ++cg) {
+    uint32_t d[32];
+    umma::tmem_ld32(lane_t + cg * 32, d);
+    float y[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(d[k]);
+    if (a.mask_x) {                     // dgrad through relu(s * x + t): scale by s where the pre-activation was positive
+      const float4* x4 = reinterpret_cast<const float4*>(a.mask_x + (size_t)rowc * kOH + cg * 32);
+      const float4* s4 = reinterpret_cast<const float4*>(a.mask_s + (size_t)b * kOH + cg * 32);
+      const float4* t4 = reinterpret_cast<const float4*>(a.mask_t + (size_t)b * kOH + cg * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 xs = __ldg(x4 + q), s = __ldg(s4 + q), t = __ldg(t4 + q);
+        y[4 * q + 0] = fmaf(s.x, xs.x, t.x) > 0.0f ? y[4 * q + 0] * s.x : 0.0f;
+        y[4 * q + 1] = fmaf(s.y, xs.y, t.y) > 0.0f ? y[4 * q + 1] * s.y : 0.0f;
+        y[4 * q + 2] = fmaf(s.z, xs.z, t.z) > 0.0f ? y[4 * q + 2] * s.z : 0.0f;
+        y[4 * q + 3] = fmaf(s.w, xs.w, t.w) > 0.0f ? y[4 * q + 3] * s.w : 0.0f;
+      }
+    }
+    if (a.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(a.bias + cg * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 bv = __ldg(b4 + q);
+        y[4 * q + 0] += bv.x; y[4 * q + 1] += bv.y; y[4 * q + 2] += bv.z; y[4 * q + 3] += bv.w;
+      }
+    }
+    if (a.resid) {
+      const float4* r4 = reinterpret_cast<const float4*>(a.resid + (size_t)rowc * kOH + cg * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 rv = r4[q];     // plain load: the dgrad residual buffer is updated in place by this kernel
+        y[4 * q + 0] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
+      }
+    }
+    if (live) {
+      float4* o4 = reinterpret_cast<float4*>(orow + cg * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o4[q] = make_float4(y[4 * q + 0], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+    }
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------- thin layers
+// net0[m][n] = Wp[n][:] . p_m + bp[n]        (fc_p: Conv1d(3, 256, 1))
+__global__ void onet_fcp_kernel(const float* __restrict__ xyz, const float* __restrict__ Wp, const float* __restrict__ bp,
+                                int M, float* __restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)M * kOH) return;
+  const int m = (int)(e / kOH), n = (int)(e % kOH);
+  float v = bp[n];
+  v = fmaf(Wp[n * 3 + 0], xyz[(size_t)m * 3 + 0], v);
+  v = fmaf(Wp[n * 3 + 1], xyz[(size_t)m * 3 + 1], v);
+  v = fmaf(Wp[n * 3 + 2], xyz[(size_t)m * 3 + 2], v);
+  out[e] = v;
+}
+
+// One warp per row: logit = w_out . relu(s_f * net + t_f) + b_out ; then either store the logit (forward seam), or
+// turn it into the gradient of the loss w.r.t. net:  g_net = glogit * w_out * [pre > 0] * s_f  with
+// glogit = grad_logits[m] (seam) or (sigmoid(logit) - target) * ginv (loop).
+__global__ void onet_head_kernel(const float* __restrict__ net, const float* __restrict__ s, const float* __restrict__ t,
+                                 const float* __restrict__ wout, const float* __restrict__ bout, int M, int K,
+                                 float* __restrict__ logits_out, const float* __restrict__ grad_logits, int bce, float target,
+                                 float ginv, float* __restrict__ gnet_out, double* __restrict__ stat_part) {
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  double s0 = 0.0, s1 = 0.0;
+  if (m < M) {
+    const int b = m / K;
+    const float* row = net + (size_t)m * kOH;
+    const float* sb = s + (size_t)b * kOH;
+    const float* tb = t + (size_t)b * kOH;
+    float pre[8], acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int n = lane + 32 * i;
+      pre[i] = fmaf(sb[n], row[n], tb[n]);
+      acc = fmaf(wout[n], fmaxf(pre[i], 0.0f), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float logit = acc + bout[0];
+    if (logits_out && lane == 0) logits_out[m] = logit;
+    if (gnet_out) {
+      const float sg = sigmoidf_(logit);
+      const float gl = bce ? (sg - target) * ginv : grad_logits[m];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = lane + 32 * i;
+        gnet_out[(size_t)m * kOH + n] = pre[i] > 0.0f ? gl * wout[n] * sb[n] : 0.0f;
+      }
+      if (stat_part && lane == 0) {
+        s0 = (double)bce_with_logits(logit, target);
+        s1 = (double)sg;
+      }
+    }
+  }
+  if (stat_part) {                       // block-uniform
+    __shared__ double red[2][8];
+    if (lane == 0) {
+      red[0][warp_in_block] = s0;
+      red[1][warp_in_block] = s1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        t0 += red[0][w];
+        t1 += red[1][w];
+      }
+      stat_part[blockIdx.x * 2 + 0] = t0;
+      stat_part[blockIdx.x * 2 + 1] = t1;
+    }
+  }
+}
+
+// g_p[m][d] = sum_n Wp[n][d] * g_net0[m][n]      (one warp per row)
+__global__ void onet_fcp_bwd_kernel(const float* __restrict__ gnet, const float* __restrict__ Wp, int M, float* __restrict__ gp) {
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float* row = gnet + (size_t)m * kOH;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = lane + 32 * i;
+    const float g = row[n];
+    g0 = fmaf(Wp[n * 3 + 0], g, g0);
+    g1 = fmaf(Wp[n * 3 + 1], g, g1);
+    g2 = fmaf(Wp[n * 3 + 2], g, g2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    g0 += __shfl_xor_sync(0xffffffffu, g0, o);
+    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+    g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+  }
+  if (lane == 0) {
+    gp[(size_t)m * 3 + 0] = g0;
+    gp[(size_t)m * 3 + 1] = g1;
+    gp[(size_t)m * 3 + 2] = g2;
+  }
+}
+
+}  // namespace ifd
+
+using namespace ifd;
+
+// ------------------------------------------------------------------------------------------------ host side
+namespace {
+struct OnetWs {
+  float* img;      // [2 dirs][10 layers][kLayerImgFloats]
+  float* s;        // [11][B][256]
+  float* t;
+  float* act;      // [11][M][256]: net_0, h_0, net_1, h_1, ..., net_4, h_4, net_5
+  float* g0;       // [M][256] gradient ping
+  float* g1;       // [M][256] gradient pong
+  double* stat;    // [M/8 blocks][2]
+  size_t bytes;
+};
+OnetWs carve_onet(void* base, int B, int K) {
+  OnetWs w;
+  size_t off = 0;
+  const size_t M = (size_t)B * K;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  w.img = (float*)take((size_t)2 * 10 * kLayerImgFloats * 4);
+  w.s = (float*)take((size_t)kOnetCbn * B * kOH * 4);
+  w.t = (float*)take((size_t)kOnetCbn * B * kOH * 4);
+  w.act = (float*)take((size_t)11 * M * kOH * 4);
+  w.g0 = (float*)take(M * kOH * 4);
+  w.g1 = (float*)take(M * kOH * 4);
+  w.stat = (double*)take(((M + 7) / 8) * 2 * sizeof(double));
+  w.bytes = off;
+  return w;
+}
+int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+  const size_t smem = (size_t)2 * kChunkImgFloats * 4 + 64;
+  IFD_CUDA_TRY(cudaFuncSetAttribute(onet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  onet_gemm_kernel<<<(a.M + kGemmThreads - 1) / kGemmThreads, kGemmThreads, smem, st>>>(a);
+  IFD_LAUNCH_CHECK("onet_gemm_kernel");
+  return IFD_OK;
+}
+}  // namespace
+
+// Packed ONet decoder parameters (float32), in this order (names = reference state_dict keys under `decoder.`):
+//   fc_p.weight [256][3], fc_p.bias [256],
+//   11 x CBN { conv_gamma.weight [256][512], conv_gamma.bias [256], conv_beta.weight [256][512], conv_beta.bias [256],
+//              bn.running_mean [256], bn.running_var [256] }   in the order block0.bn_0, block0.bn_1, ..., block4.bn_1, bn
+//   10 x { weight [256][256], bias [256] }                     in the order block0.fc_0, block0.fc_1, ..., block4.fc_1
+//   fc_out.weight [256], fc_out.bias [1]
+namespace {
+constexpr size_t kCbnFloats = 2 * ((size_t)kOH * kOC + kOH) + 2 * kOH;
+constexpr size_t kFcFloats = (size_t)kOH * kOH + kOH;
+constexpr size_t kOffCbn = (size_t)kOH * 3 + kOH;
+constexpr size_t kOffFc = kOffCbn + kOnetCbn * kCbnFloats;
+constexpr size_t kOffOut = kOffFc + 10 * kFcFloats;
+constexpr size_t kOnetFloats = kOffOut + kOH + 1;
+}  // namespace
+
+extern "C" size_t ifd_onet_decoder_nfloats(void) { return kOnetFloats; }
+extern "C" size_t ifd_onet_workspace_bytes(int B, int K) {
+  if (B <= 0 || K <= 0) return 0;
+  return carve_onet(nullptr, B, K).bytes + ifd_convonet_opt_workspace_bytes(B, K);
+}
+
+// Once per batch: pack the weight images and fold the CBNs for the given latent codes c [B][512].
+extern "C" int ifd_onet_prepare(const float* dec_weights, const float* c, int B, int K, void* workspace, size_t workspace_bytes,
+                                ifd_stream_t stream) {
+  IFD_REQUIRE(dec_weights && c && workspace && B > 0 && K > 0, "ifd_onet_prepare: bad arguments");
+  if (workspace_bytes < ifd_onet_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_onet_prepare: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  OnetWs w = carve_onet(workspace, B, K);
+  for (int l = 0; l < 10; ++l)
+    for (int dir = 0; dir < 2; ++dir) {
+      onet_pack_layer_kernel<<<(kOH * kOH + 255) / 256, 256, 0, st>>>(dec_weights + kOffFc + l * kFcFloats, dir,
+                                                                     w.img + ((size_t)dir * 10 + l) * kLayerImgFloats);
+      IFD_LAUNCH_CHECK("onet_pack_layer_kernel");
+    }
+  CbnTable tab;
+  for (int j = 0; j < kOnetCbn; ++j) {
+    const float* p = dec_weights + kOffCbn + j * kCbnFloats;
+    tab.p[j].Wg = p;
+    tab.p[j].bg = p + (size_t)kOH * kOC;
+    tab.p[j].Wb = p + (size_t)kOH * kOC + kOH;
+    tab.p[j].bb = p + 2 * (size_t)kOH * kOC + kOH;
+    tab.p[j].mean = p + 2 * ((size_t)kOH * kOC + kOH);
+    tab.p[j].var = tab.p[j].mean + kOH;
+  }
+  const size_t warps = (size_t)kOnetCbn * B * kOH;
+  onet_fold_cbn_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tab, c, B, w.s, w.t);
+  IFD_LAUNCH_CHECK("onet_fold_cbn_kernel");
+  return IFD_OK;
+}
+
+namespace {
+// forward through the decoder; activations land in w.act.  Returns through logits_out (optional).
+int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K, cudaStream_t st) {
+  const int M = B * K;
+  const size_t MH = (size_t)M * kOH;
+  onet_fcp_kernel<<<(unsigned)((MH + 255) / 256), 256, 0, st>>>(xyz, W, W + kOH * 3, M, w.act);
+  IFD_LAUNCH_CHECK("onet_fcp_kernel");
+  for (int blk = 0; blk < 5; ++blk) {
+    float* net = w.act + (size_t)(2 * blk) * MH;
+    float* h = w.act + (size_t)(2 * blk + 1) * MH;
+    float* net_next = w.act + (size_t)(2 * blk + 2) * MH;
+    GemmArgs a{};
+    a.M = M; a.K = K;
+    a.A = net; a.pro_s = w.s + (size_t)(2 * blk) * B * kOH; a.pro_t = w.t + (size_t)(2 * blk) * B * kOH;
+    a.img = w.img + (size_t)(2 * blk) * kLayerImgFloats;
+    a.bias = W + kOffFc + (2 * blk) * kFcFloats + (size_t)kOH * kOH;
+    a.out = h;
+    int rc = launch_gemm(a, st);
+    if (rc) return rc;
+    GemmArgs c{};
+    c.M = M; c.K = K;
+    c.A = h; c.pro_s = w.s + (size_t)(2 * blk + 1) * B * kOH; c.pro_t = w.t + (size_t)(2 * blk + 1) * B * kOH;
+    c.img = w.img + (size_t)(2 * blk + 1) * kLayerImgFloats;
+    c.bias = W + kOffFc + (2 * blk + 1) * kFcFloats + (size_t)kOH * kOH;
+    c.resid = net;
+    c.out = net_next;
+    if ((rc = launch_gemm(c, st))) return rc;
+  }
+  return IFD_OK;
+}
+// dgrad from g_net5 (in w.g0) down to grad_xyz
+int onet_backward(const float* W, const OnetWs& w, int B, int K, float* grad_xyz, cudaStream_t st) {
+  const int M = B * K;
+  const size_t MH = (size_t)M * kOH;
+  float* gnet = w.g0;
+  float* gtmp = w.g1;
+  for (int blk = 4; blk >= 0; --blk) {
+    const float* net = w.act + (size_t)(2 * blk) * MH;
+    const float* h = w.act + (size_t)(2 * blk + 1) * MH;
+    GemmArgs a{};                                   // g_h = (g_net . W1) * s1 * [cbn1(h) > 0]
+    a.M = M; a.K = K; a.A = gnet;
+    a.img = w.img + ((size_t)10 + 2 * blk + 1) * kLayerImgFloats;
+    a.mask_x = h; a.mask_s = w.s + (size_t)(2 * blk + 1) * B * kOH; a.mask_t = w.t + (size_t)(2 * blk + 1) * B * kOH;
+    a.out = gtmp;
+    int rc = launch_gemm(a, st);
+    if (rc) return rc;
+    GemmArgs c{};                                   // g_net = g_net + (g_h . W0) * s0 * [cbn0(net) > 0]   (in place on gnet)
+    c.M = M; c.K = K; c.A = gtmp;
+    c.img = w.img + ((size_t)10 + 2 * blk) * kLayerImgFloats;
+    c.mask_x = net; c.mask_s = w.s + (size_t)(2 * blk) * B * kOH; c.mask_t = w.t + (size_t)(2 * blk) * B * kOH;
+    c.resid = gnet;
+    c.out = gnet;                                   // each thread reads and writes only its own row chunk
+    if ((rc = launch_gemm(c, st))) return rc;
+  }
+  onet_fcp_bwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(gnet, W, M, grad_xyz);
+  IFD_LAUNCH_CHECK("onet_fcp_bwd_kernel");
+  return IFD_OK;
+}
+}  // namespace
+
+// OccupancyNetwork.decode(p, z, c).logits with z_dim == 0 (ONet/im2mesh/onet/models/__init__.py, decoder.py:115-133).
+// Requires ifd_onet_prepare on the same workspace.  logits_out [B][K].
+extern "C" int ifd_onet_decode_fwd(const float* dec_weights, const float* xyz, int B, int K, float* logits_out, void* workspace,
+                                   size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_REQUIRE(dec_weights && xyz && logits_out && workspace && B > 0 && K > 0, "ifd_onet_decode_fwd: bad arguments");
+  if (workspace_bytes < ifd_onet_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_onet_decode_fwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  OnetWs w = carve_onet(workspace, B, K);
+  int rc = onet_forward(dec_weights, w, xyz, B, K, st);
+  if (rc) return rc;
+  const int M = B * K;
+  onet_head_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.act + (size_t)10 * M * kOH, w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+                                               dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, logits_out, nullptr, 0, 0.f,
+                                               0.f, nullptr, nullptr);
+  IFD_LAUNCH_CHECK("onet_head_kernel");
+  return IFD_OK;
+}
+
+// Forward + backward w.r.t. xyz for given grad_logits [B][K] (the autograd seam).
+extern "C" int ifd_onet_decode_bwd(const float* dec_weights, const float* xyz, const float* grad_logits, int B, int K,
+                                   float* grad_xyz_out, void* workspace, size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_REQUIRE(dec_weights && xyz && grad_logits && grad_xyz_out && workspace && B > 0 && K > 0, "ifd_onet_decode_bwd: bad arguments");
+  if (workspace_bytes < ifd_onet_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_onet_decode_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  OnetWs w = carve_onet(workspace, B, K);
+  int rc = onet_forward(dec_weights, w, xyz, B, K, st);
+  if (rc) return rc;
+  const int M = B * K;
+  onet_head_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.act + (size_t)10 * M * kOH, w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+                                               dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, nullptr, grad_logits, 0, 0.f,
+                                               0.f, w.g0, nullptr);
+  IFD_LAUNCH_CHECK("onet_head_kernel");
+  return onet_backward(dec_weights, w, B, K, grad_xyz_out, st);
+}
+
+// Loop pieces shared with the ConvONet path (restore.cu)
+namespace ifd {
+int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int K, const ifd_opt_params* P, int i, void* conv_ws,
+                  bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st);
+int opt_begin(float* m, float* v, bool zero_state, int B, int K, void* conv_ws, cudaStream_t st);
+int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st);
+float* opt_ws_gocc(void* conv_ws, int B, int K);
+float* opt_ws_m(void* conv_ws, int B, int K);
+float* opt_ws_v(void* conv_ws, int B, int K);
+}  // namespace ifd
+
+// optimize_points for ONet (ONet/opt_defense.py:182-239): same loop, decode(p, z, c) with the CBN decoder.
+extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz, float* adam_m, float* adam_v, int B, int K,
+                            const ifd_opt_params* P, double* stats_out, void* workspace, size_t workspace_bytes,
+                            ifd_stream_t stream) {
+  IFD_REQUIRE(dec_weights && c && xyz && P && workspace && B > 0 && K > 0, "ifd_onet_opt: bad arguments");
+  IFD_REQUIRE(P->n_steps >= 0 && P->step0 >= 0 && P->B_ref > 0, "ifd_onet_opt: bad step counts / B_ref");
+  IFD_REQUIRE((adam_m == nullptr) == (adam_v == nullptr), "ifd_onet_opt: pass both adam_m and adam_v or neither");
+  IFD_REQUIRE(!(P->step0 > 0 && !adam_m), "ifd_onet_opt: resuming (step0 > 0) needs adam_m / adam_v");
+  if (workspace_bytes < ifd_onet_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_onet_opt: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  OnetWs w = carve_onet(workspace, B, K);
+  void* conv_ws = (char*)workspace + w.bytes;
+  int rc = ifd_onet_prepare(dec_weights, c, B, K, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  float* m = adam_m ? adam_m : opt_ws_m(conv_ws, B, K);
+  float* v = adam_v ? adam_v : opt_ws_v(conv_ws, B, K);
+  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, conv_ws, st))) return rc;
+  float* g_occ = opt_ws_gocc(conv_ws, B, K);
+  const int M = B * K;
+  const float ginv = (float)K / (float)((long long)P->B_ref * K);
+  const int n_dec = (M + 7) / 8;
+  for (int i = 0; i < P->n_steps; ++i) {
+    const bool stat = P->want_stats && stats_out && (i % 100 == 0);
+    {
+      ProfileScope ps(0, st);
+      if ((rc = onet_forward(dec_weights, w, xyz, B, K, st))) return rc;
+      onet_head_kernel<<<n_dec, 256, 0, st>>>(w.act + (size_t)10 * M * kOH, w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+                                              dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, nullptr, nullptr, 1,
+                                              (float)P->occ_target, ginv, w.g0, stat ? w.stat : nullptr);
+      IFD_LAUNCH_CHECK("onet_head_kernel");
+      if ((rc = onet_backward(dec_weights, w, B, K, g_occ, st))) return rc;
+    }
+    if ((rc = opt_step_tail(xyz, m, v, g_occ, B, K, P, i, conv_ws, stat, w.stat, n_dec, stats_out, true, st))) return rc;
+  }
+  return opt_finish(xyz, B, K, P->normalize_out, st);
+}

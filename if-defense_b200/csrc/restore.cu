@@ -478,6 +478,67 @@ static OptWorkspace carve_opt_ws(void* base, int B, int K) {
 
 }  // namespace ifd
 
+namespace ifd {
+// ---- loop pieces shared by the ConvONet and ONet drivers ------------------------------------------------
+float* opt_ws_gocc(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).g_occ; }
+float* opt_ws_m(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).m; }
+float* opt_ws_v(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).v; }
+
+int opt_begin(float* m, float* v, bool zero_state, int B, int K, void* ws, cudaStream_t st) {
+  OptWorkspace w = carve_opt_ws(ws, B, K);
+  const size_t n = (size_t)B * K * 3;
+  if (zero_state) {
+    IFD_CUDA_TRY(cudaMemsetAsync(m, 0, n * sizeof(float), st));
+    IFD_CUDA_TRY(cudaMemsetAsync(v, 0, n * sizeof(float), st));
+  }
+  IFD_CUDA_TRY(cudaMemsetAsync(w.acc, 0, n * kFxLimbs * sizeof(long long), st));
+  return IFD_OK;
+}
+
+// After the decoder produced g_occ for step i: kNN + repulsion, optional diagnostics, Adam.
+int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int K, const ifd_opt_params* P, int i, void* ws,
+                  bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st) {
+  OptWorkspace w = carve_opt_ws(ws, B, K);
+  const size_t n = (size_t)B * K * 3;
+  const bool rep = P->rep_weight > 0.0;
+  if (rep && (P->knn_k + 1 > 8 || P->knn_k < 1)) return fail(IFD_ERR_UNSUPPORTED, "knn_k must be in [1, 7]");
+  int rc;
+  if (rep) {
+    ProfileScope ps(1, st);
+    if ((rc = launch_knn_repulsion(xyz, B, K, P->knn_k, (float)P->rep_radius, (float)P->rep_h, (float)P->rep_eps, nullptr,
+                                   w.loss_part, w.acc, w.nbr, i > 0 && warm_ok, st)))
+      return rc;
+  }
+  if (stat) {
+    stats_kernel<<<1, 32, 0, st>>>(dec_part, n_dec, w.loss_part, B, rep ? rep_chunks(K) : 0, K, P->knn_k, (float)P->rep_weight,
+                                   stats_out + (size_t)(i / 100) * 4);
+    IFD_LAUNCH_CHECK("stats_kernel");
+  }
+  // rep_loss = mean_B(mean_{K,k}) * rep_weight: grad = rep_weight / B_ref / (K*k)
+  const float rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
+  const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
+  const double t = (double)(P->step0 + i + 1);
+  AdamStepConst sc;
+  sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
+  sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
+  {
+    ProfileScope ps(2, st);
+    adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, m, v, g_occ, rep ? w.acc : nullptr, (int)n, rep_coef, omb1,
+                                                            (float)P->beta2, omb2, (float)P->adam_eps, sc);
+    IFD_LAUNCH_CHECK("adam_kernel");
+  }
+  return IFD_OK;
+}
+
+int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st) {
+  if (normalize) {
+    normalize_kernel<<<B, kNormThreads, 0, st>>>(xyz, K);
+    IFD_LAUNCH_CHECK("normalize_kernel");
+  }
+  return IFD_OK;
+}
+}  // namespace ifd
+
 using namespace ifd;
 
 extern "C" size_t ifd_convonet_decoder_nfloats(int C, int H, int n_blocks) {
@@ -576,19 +637,11 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
   IFD_REQUIRE(workspace, "ifd_convonet_opt: workspace is required");
   if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_opt: workspace too small");
-  const bool rep = P->rep_weight > 0.0;
-  if (rep && (P->knn_k + 1 > 8 || P->knn_k < 1)) return fail(IFD_ERR_UNSUPPORTED, "knn_k must be in [1, 7]");
-
   cudaStream_t st = as_stream(stream);
   OptWorkspace w = carve_opt_ws(workspace, B, K);
-  const size_t n = (size_t)B * K * 3;
   float* m = adam_m ? adam_m : w.m;
   float* v = adam_v ? adam_v : w.v;
-  if (!adam_m || P->step0 == 0) {
-    IFD_CUDA_TRY(cudaMemsetAsync(m, 0, n * sizeof(float), st));
-    IFD_CUDA_TRY(cudaMemsetAsync(v, 0, n * sizeof(float), st));
-  }
-  IFD_CUDA_TRY(cudaMemsetAsync(w.acc, 0, n * kFxLimbs * sizeof(long long), st));
+  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, workspace, st))) return rc;
 
   DecodeArgs a{};
   a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_out = w.g_occ;
@@ -596,13 +649,9 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   a.target = (float)P->occ_target;
   // d/dlogit of (mean over B_ref*K) * K: autograd multiplies K, then divides by the element count
   a.ginv = (float)K / (float)((long long)P->B_ref * K);
-  // rep_loss = mean_B(mean_{K,k}) * rep_weight: grad = rep_weight / B_ref / (K*k)
-  const float rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
-  const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
-  const int n_dec = P->decode_kernel == 1 ? (B * K + kDecThreads - 1) / kDecThreads : (B * K + kV2Pts - 1) / kV2Pts;   // v2, v3: 512-point tiles
-
   const int dk = P->decode_kernel == 0 ? 3 : P->decode_kernel;
   if (dk < 1 || dk > 3) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0..3");
+  const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads : (B * K + kV2Pts - 1) / kV2Pts;   // v2, v3: 512-point tiles
   if (dk == 3) {
     const int nl = 3 * n_blocks;
     convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg);
@@ -616,33 +665,9 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
       rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
       if (rc) return rc;
     }
-    if (rep) {
-      ProfileScope ps(1, st);
-      if ((rc = launch_knn_repulsion(xyz, B, K, P->knn_k, (float)P->rep_radius, (float)P->rep_h, (float)P->rep_eps, nullptr,
-                                     w.loss_part, w.acc, w.nbr, i > 0 && dk != 1, st)))
-        return rc;
-    }
-    if (stat) {
-      stats_kernel<<<1, 32, 0, st>>>(w.dec_part, n_dec, w.loss_part, B, rep ? rep_chunks(K) : 0, K, P->knn_k,
-                                     (float)P->rep_weight, stats_out + (size_t)(i / 100) * 4);
-      IFD_LAUNCH_CHECK("stats_kernel");
-    }
-    const double t = (double)(P->step0 + i + 1);
-    AdamStepConst sc;
-    sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
-    sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
-    {
-      ProfileScope ps(2, st);
-      adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, m, v, w.g_occ, rep ? w.acc : nullptr, (int)n, rep_coef,
-                                                              omb1, (float)P->beta2, omb2, (float)P->adam_eps, sc);
-      IFD_LAUNCH_CHECK("adam_kernel");
-    }
+    if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1, st))) return rc;
   }
-  if (P->normalize_out) {
-    normalize_kernel<<<B, kNormThreads, 0, st>>>(xyz, K);
-    IFD_LAUNCH_CHECK("normalize_kernel");
-  }
-  return IFD_OK;
+  return opt_finish(xyz, B, K, P->normalize_out, st);
 }
 
 extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,

@@ -1,0 +1,102 @@
+"""ONet-Opt on the sm_100a kernels, behind the reference's seams.
+
+  ONetDecoder.decode(p, z, c).logits      <- generator.model.decode(opt_points, z, c).logits   (ONet/opt_defense.py:212)
+  ONetRestorer.optimize_points(...)       <- optimize_points(opt_points, z, c, rep_weight, iterations, printing)
+                                             (ONet/opt_defense.py:182-239)
+
+`c` is what the reference's encode_inputs returns for ONet: a [B,512] tensor; `z` is the empty [B,0] prior sample
+(z_dim = 0) and is ignored.
+"""
+import ctypes
+
+import torch
+from torch import distributions as dist
+
+from . import capi, weights
+
+
+class _Workspace:
+    """Caches the (large) ONet workspace per (B, K): 11 saved activation tensors + weight images."""
+
+    def __init__(self):
+        self.key, self.buf = None, None
+
+    def get(self, B, K, device):
+        if self.key != (B, K, str(device)):
+            n = capi.lib().ifd_onet_workspace_bytes(B, K)
+            self.buf = torch.empty(n, dtype=torch.uint8, device=device)
+            self.key = (B, K, str(device))
+        return self.buf
+
+
+class _DecodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, c, dec):
+        capi.require_gpu()
+        x = p.detach().float().contiguous()
+        cc = c.detach().float().contiguous()
+        B, K, _ = x.shape
+        L = capi.lib()
+        ws = dec.ws.get(B, K, x.device)
+        capi.check(L.ifd_onet_prepare(capi.ptr(dec.blob), capi.ptr(cc), B, K, capi.ptr(ws), ws.numel(), capi.stream()), "ifd_onet_prepare")
+        logits = torch.empty((B, K), dtype=torch.float32, device=x.device)
+        capi.check(L.ifd_onet_decode_fwd(capi.ptr(dec.blob), capi.ptr(x), B, K, capi.ptr(logits), capi.ptr(ws), ws.numel(),
+                                         capi.stream()), "ifd_onet_decode_fwd")
+        ctx.save_for_backward(x, cc)
+        ctx.dec = dec
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        x, cc = ctx.saved_tensors
+        dec = ctx.dec
+        B, K, _ = x.shape
+        L = capi.lib()
+        ws = dec.ws.get(B, K, x.device)
+        capi.check(L.ifd_onet_prepare(capi.ptr(dec.blob), capi.ptr(cc), B, K, capi.ptr(ws), ws.numel(), capi.stream()), "ifd_onet_prepare")
+        g = grad_logits.detach().float().contiguous()
+        out = torch.empty_like(x)
+        capi.check(L.ifd_onet_decode_bwd(capi.ptr(dec.blob), capi.ptr(x), capi.ptr(g), B, K, capi.ptr(out), capi.ptr(ws), ws.numel(),
+                                         capi.stream()), "ifd_onet_decode_bwd")
+        return out, None, None
+
+
+class ONetDecoder:
+    """DecoderCBatchNorm, frozen, eval mode, packed for the kernels (checkpoint interface: the reference's
+    `decoder.*` state_dict keys)."""
+
+    def __init__(self, state_dict, device="cuda", prefix="decoder."):
+        self.blob_host = weights.pack_onet_decoder(state_dict, prefix)
+        self.device = torch.device(device)
+        self.blob = torch.from_numpy(self.blob_host).to(self.device) if self.device.type == "cuda" else None
+        self.ws = _Workspace()
+
+    def decode(self, p, z, c, **kwargs):
+        return dist.Bernoulli(logits=_DecodeFn.apply(p, c, self))
+
+
+class ONetRestorer:
+    def __init__(self, decoder, threshold=0.2, lr=1e-3):
+        self.decoder, self.threshold, self.lr = decoder, float(threshold), float(lr)
+        self.last_stats = None
+
+    def optimize_points(self, opt_points, z, c, rep_weight=1., iterations=1000, printing=False, B_ref=None, normalize=True,
+                        return_tensor=False):
+        capi.require_gpu()
+        x = opt_points.detach().float().cuda().contiguous().clone()
+        cc = c.detach().float().cuda().contiguous()
+        B, K, _ = x.shape
+        L = capi.lib()
+        P = capi.default_params(n_steps=iterations + 1, B_ref=int(B if B_ref is None else B_ref), rep_weight=float(rep_weight),
+                                lr=self.lr, occ_target=self.threshold, want_stats=int(bool(printing)),
+                                normalize_out=int(bool(normalize)))
+        ws = self.decoder.ws.get(B, K, x.device)
+        stats = torch.zeros((iterations // 100 + 1, 4), dtype=torch.float64, device=x.device) if printing else None
+        capi.check(L.ifd_onet_opt(capi.ptr(self.decoder.blob), capi.ptr(cc), capi.ptr(x), None, None, B, K, ctypes.byref(P),
+                                  capi.ptr(stats), capi.ptr(ws), ws.numel(), capi.stream()), "ifd_onet_opt")
+        if printing:
+            self.last_stats = stats.cpu().numpy()
+            for j, (loss, occ, rep, sg) in enumerate(self.last_stats):
+                print('iter {}, loss {:.4f}'.format(j * 100, loss))
+                print('occ loss: {:.4f}, rep loss: {:.4f}\nocc value mean: {:.4f}'.format(occ, rep, sg))
+        return x if return_tensor else x.cpu().numpy()

@@ -55,3 +55,20 @@ def make_case(B, K=1024, seed=0, T=600, device="cpu", sd=None):
     gen = torch.Generator().manual_seed(3000 + seed)
     p0 = driver.init_points([p for p, _ in proc], npoint=K, sigma=0.01, padding_scale=0.9, gen=gen)
     return types.SimpleNamespace(sd=sd, raw=raw, sel=sel, c=c, p0=p0, B=B, K=K)
+
+
+def make_onet_case(B, K=1024, seed=0, T=300, device="cpu", sd=None):
+    """One ONet-Opt batch: weights, encoder input [B,300,3], latent codes c [B,512] (what the reference's
+    encode_inputs returns), init points."""
+    sd = sd if sd is not None else models.synthetic_state_dict("onet", 0)
+    raw = clouds(B)
+    proc = [driver.preprocess_pc(raw[i], num_points=T, padding_scale=0.9, rng=np.random.default_rng(2000 + i)) for i in range(B)]
+    sel = torch.from_numpy(np.stack([s for _, s in proc]))
+    model = models.build_onet()
+    model.load_state_dict(sd)
+    model = model.to(device).eval()
+    with torch.no_grad():
+        c = model.encoder(sel.to(device)).cpu()
+    gen = torch.Generator().manual_seed(3000 + seed)
+    p0 = driver.init_points([p for p, _ in proc], npoint=K, sigma=0.01, padding_scale=0.9, gen=gen)
+    return types.SimpleNamespace(sd=sd, raw=raw, sel=sel, c=c, p0=p0, B=B, K=K)

@@ -178,6 +178,39 @@ int ifd_convonet_opt_host(const float* planes_nchw_host, const float* dec_weight
                           double* stats_out_host);
 void ifd_release_cache(void);
 
+/* ------------------------------------------------------------------------------------------------
+ * ONet decoder (DecoderCBatchNorm, c_dim 512, hidden 256, z_dim 0) and its restoration loop
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Packed ONet decoder parameters (float32; names are the reference state_dict keys under `decoder.`):
+ *   fc_p.weight [256][3], fc_p.bias [256],
+ *   11 x { conv_gamma.weight [256][512], conv_gamma.bias [256], conv_beta.weight [256][512], conv_beta.bias [256],
+ *          bn.running_mean [256], bn.running_var [256] }  in the order block0.bn_0, block0.bn_1, ..., block4.bn_1, bn
+ *   10 x { weight [256][256], bias [256] }                in the order block0.fc_0, block0.fc_1, ..., block4.fc_1
+ *   fc_out.weight [256], fc_out.bias [1] */
+size_t ifd_onet_decoder_nfloats(void);
+size_t ifd_onet_workspace_bytes(int B, int K);
+
+/* Once per batch (the reference recomputes gamma(c), beta(c) in every CBN call, ONet/im2mesh/layers.py:226-242;
+ * in eval mode they are constants of the batch): packs the tensor-core weight images and folds the 11 CBNs for
+ * the latent codes c [B][512] = encode_inputs() (ONet/im2mesh/encoder/pointnet.py:85-113) into the workspace. */
+int ifd_onet_prepare(const float* dec_weights, const float* c, int B, int K, void* workspace, size_t workspace_bytes,
+                     ifd_stream_t stream);
+
+/* OccupancyNetwork.decode(p, z, c).logits, z_dim = 0 (ONet/opt_defense.py:212; ONet/im2mesh/onet/models/decoder.py:
+ * 115-133; CResnetBlockConv1d ONet/im2mesh/layers.py:98-107).  Needs ifd_onet_prepare on the same workspace. */
+int ifd_onet_decode_fwd(const float* dec_weights, const float* xyz, int B, int K, float* logits_out, void* workspace,
+                        size_t workspace_bytes, ifd_stream_t stream);
+/* Forward + backward w.r.t. xyz for grad_logits [B][K] -> grad_xyz_out [B][K][3]. */
+int ifd_onet_decode_bwd(const float* dec_weights, const float* xyz, const float* grad_logits, int B, int K,
+                        float* grad_xyz_out, void* workspace, size_t workspace_bytes, ifd_stream_t stream);
+
+/* optimize_points of ONet/opt_defense.py:182-239 (same loop as ConvONet's; decode(p, z, c) with the CBN decoder).
+ * c [B][512]; xyz [B][K][3] in place; calls ifd_onet_prepare itself. */
+int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz, float* adam_m, float* adam_v, int B, int K,
+                 const ifd_opt_params* params, double* stats_out, void* workspace, size_t workspace_bytes,
+                 ifd_stream_t stream);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 long long ifd_launch_count(int reset);
 

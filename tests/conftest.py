@@ -33,6 +33,11 @@ def pytest_collection_modifyitems(config, items):
 
 
 @pytest.fixture(scope="session")
+def conftest_golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session")
 def geo():
     return dict(np.load(os.path.join(GOLDEN, "geometry.npz")))
 

@@ -10,6 +10,8 @@ Files
                  (cloud 0 = the reference's own airplane.npy), plus a duplicate-point cloud
   convonet.npz   B=2, K=256: planes, decoder weights, logits, d(sum gl*logit)/dp, clamp cases,
                  20-step optimize_points trace, a late-state single-step case (Adam state at t=150)
+  onet.npz       ONet: B=2, K=256 logits / gradients / 20-step trace, and BASELINE configs[0]
+                 (1 cloud x 1024 points, 20 iterations); weights regenerated from the seed, pinned by checksum
 """
 import importlib.util
 import os
@@ -180,7 +182,58 @@ def convonet_case(ns):
     print("convonet.npz", {k: v.shape for k, v in out.items() if not k.startswith("sd/")})
 
 
+def onet_case():
+    """ONet-Opt: B=2, K=256 through the reference's OccupancyNetwork (eval mode, z_dim = 0), plus BASELINE.json
+    configs[0] (1 cloud x 1024 points, 20 iterations, CPU).  The 3.5 M decoder weights are NOT stored: they are
+    regenerated from the seed (ifdefense_b200.models.synthetic_state_dict) and pinned by a checksum."""
+    ns = ref_import.load("ONet")
+    _, model = ref_import.build_model(ns)
+    out = {}
+    for tag, (B, K, iters) in {"b2": (2, 256, 19), "cfg0": (1, 1024, 20)}.items():
+        case = synth.make_onet_case(B, K=K, seed=4)
+        model.load_state_dict(case.sd, strict=True)
+        with torch.no_grad():
+            c = model.encode_inputs(case.sel)
+        assert torch.equal(c, case.c), "product ONet encoder shell != reference encoder on CPU"
+        z = model.get_z_from_prior((B,), sample=False)
+        blob = weights.pack_onet_decoder(case.sd)
+        out["weights_checksum"] = np.array([np.sum(blob.astype(np.float64)), np.sum(np.abs(blob).astype(np.float64)), blob[12345]])
+        out[tag + "/c"], out[tag + "/p0"], out[tag + "/sel"] = c.numpy(), case.p0.numpy(), case.sel.numpy()
+        gl = torch.randn(B, K, generator=torch.Generator().manual_seed(6))
+        p = case.p0.clone().requires_grad_()
+        logits = model.decode(p, z, c).logits
+        (logits * gl).sum().backward()
+        out[tag + "/logits"], out[tag + "/gl"], out[tag + "/grad_p"] = logits.detach().numpy(), gl.numpy(), p.grad.numpy()
+        pts = case.p0.clone().float().requires_grad_()
+        thr = torch.ones((B, K)).float() * 0.2
+        opt = torch.optim.Adam([pts], lr=0.001)
+        for i in range(iters + 1):
+            occ = model.decode(pts, z, c).logits
+            loss = torch.mean(F.binary_cross_entropy_with_logits(occ, thr, reduction='none')) * K + \
+                torch.mean(ns.repulsion.repulsion_loss(pts)) * 500.
+            opt.zero_grad()
+            loss.backward()
+            if i == 0:
+                out[tag + "/grad_0"] = pts.grad.detach().clone().numpy()
+            opt.step()
+            if i in (0, 1, 9):
+                out[tag + "/xyz_%d" % i] = pts.detach().clone().numpy()
+        f = pts.detach()
+        out[tag + "/final_raw"] = f.numpy().copy()
+        f = f - torch.mean(f, dim=1)[:, None, :]
+        f = f / torch.max(torch.sum(f ** 2, dim=2) ** 0.5, dim=1)[0][:, None, None]
+        out[tag + "/final_normalized"] = f.numpy()
+    np.savez_compressed(os.path.join(OUT, "onet.npz"), **out)
+    print("onet.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    ns = ref_import.load("ConvONet")
-    geometry(ns)
-    convonet_case(ns)
+    which = sys.argv[1:] or ["geometry", "convonet", "onet"]
+    if "geometry" in which or "convonet" in which:
+        ns = ref_import.load("ConvONet")
+        if "geometry" in which:
+            geometry(ns)
+        if "convonet" in which:
+            convonet_case(ns)
+    if "onet" in which:
+        onet_case()
