@@ -238,12 +238,16 @@ def main():
         torch.cuda.synchronize()
         n_e2e = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
+        per_call = []
         for j in range(n_e2e):
+            tc = time.perf_counter()
             out = rest.optimize_points_host(host[j % NB][1], host[j % NB][0], rep_weight=500., iterations=ITERS, B_ref=B)
+            per_call.append(round((time.perf_counter() - tc) * 1e3, 2))
         t_e2e = time.perf_counter() - t0
         h2d = int(host[0][0].nbytes + host[0][1].nbytes + dec.blob_host.nbytes)
         e2e = {"value": B * n_e2e / t_e2e, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(out.nbytes),
-               "steps": n_e2e, "api": "Restorer.optimize_points_host -> ifd_convonet_opt_host (1 GPU, rank 0)"}
+               "steps": n_e2e, "ms_per_call": per_call,
+               "api": "Restorer.optimize_points_host -> ifd_convonet_opt_host (1 GPU, rank 0)"}
 
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

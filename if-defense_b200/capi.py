@@ -23,7 +23,7 @@ class OptParams(ctypes.Structure):
         ("knn_k", ctypes.c_int32), ("normalize_out", ctypes.c_int32), ("want_stats", ctypes.c_int32),
         ("lr", _c_d), ("beta1", _c_d), ("beta2", _c_d), ("adam_eps", _c_d), ("occ_target", _c_d),
         ("rep_weight", _c_d), ("rep_radius", _c_d), ("rep_h", _c_d), ("rep_eps", _c_d), ("padding", _c_d),
-        ("decode_kernel", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("decode_kernel", ctypes.c_int32), ("tail_kernel", ctypes.c_int32),
     ]
 
 
@@ -48,6 +48,7 @@ SIGNATURES = {
     "ifd_convonet_opt_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "ifd_convonet_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                   ctypes.POINTER(OptParams), _vp, _vp, _c_sz, _vp]),
+    "ifd_opt_tail_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, ctypes.POINTER(OptParams), _c_int, _vp, _vp, _vp]),
     "ifd_convonet_opt_host": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        ctypes.POINTER(OptParams), _vp]),
     "ifd_onet_decoder_nfloats": (_c_sz, []),
@@ -59,6 +60,7 @@ SIGNATURES = {
     "ifd_release_cache": (None, []),
     "ifd_launch_count": (ctypes.c_longlong, [_c_int]),
     "ifd_selftest_umma": (_c_int, [_vp, _vp, _vp, _vp]),
+    "ifd_test_hook": (None, [_c_int, _c_int]),
     "ifd_profile_enable": (None, [_c_int]),
     "ifd_profile_read": (_c_int, [_vp, _vp]),
 }

@@ -1,0 +1,466 @@
+// cloud_step.cuh -- everything of one Adam step that is NOT the decoder, for one cloud, in one CTA:
+//   knn_point (defense/pn_utils.py:64-83) -> repulsion pairs + their scatter-add backward
+//   (defense/repulsion_loss.py:43-53, index_points backward) -> g = g_occ + coef * g_rep -> Adam
+//   (opt_defense.py:226-228, torch/optim/adam.py single-tensor path).
+//
+// Why a redesign: ncu on the previous generation (profiles/r01_v3_*) shows the brute-force K^2 scan at 50 us and
+// the 6-limb global accumulator traffic of the separate Adam kernel at 15 us per step -- 45 % of a step.  Here
+//   * the warm-start bound tau_i (largest current key among last step's k+1 neighbours, an upper bound on the
+//     (k+1)-th smallest key) turns the scan into a range query on a uniform 16^3 grid rebuilt in shared memory
+//     every step (counting sort of the K indices): ~20 candidates per query instead of K.  The candidate set is a
+//     superset of {j : key(i,j) <= tau_i} (radius inflated by the rounding error bound of the expanded-form key),
+//     keys are evaluated in the reference's association and ranked by (key, index): bit-identical indices to the
+//     brute-force scan, ties included;
+//   * the scatter-add becomes a gather.  A mutual edge pair (i->j, j->i) contributes to i the bit-identical
+//     value twice (d^2 is symmetric and x_j - x_i = -(x_i - x_j) exactly in floating point), so only NON-mutual
+//     edges are sent to the target's inbox (shared-memory slots, one integer atomic per such edge); a hub whose
+//     inbox overflows recovers its in-edges by an ordered scan of the neighbour lists;
+//   * every point sums its terms in one canonical order (mutual terms by rank, own sum, in-edges by ascending
+//     source) in fp64, so the result does not depend on atomic arrival order: bitwise reproducible;
+//   * Adam runs in the same thread; xyz, m, v make one round trip to HBM/L2 per step.
+#pragma once
+#include "common.cuh"
+#include "ifd_math.cuh"
+#include "topk.cuh"
+
+namespace ifd {
+
+constexpr int kCsThreads = 1024;
+constexpr int kCsMaxK = 1024;               // one thread per point
+constexpr int kCsG = 16;                    // grid cells per axis
+constexpr int kCsCells = kCsG * kCsG * kCsG;
+constexpr int kCsInbox = 16;                // non-mutual in-edges kept per target before the ordered fallback
+constexpr int kCsKK = 8;                    // neighbour-list width (k + 1 <= 8)
+constexpr int kCsMaxHub = 128;              // hubs served by the warp-cooperative pass (beyond: serial fallback)
+
+struct CloudStepArgs {
+  float* xyz;            // [B][K][3] in/out
+  float* m;              // [B][K][3] Adam exp_avg in/out
+  float* v;              // [B][K][3] Adam exp_avg_sq in/out
+  const float* g_occ;    // [B][K][3] d occ_loss / d xyz of this step (decode kernel)
+  int32_t* nbr;          // [B][K][8] neighbour lists: in = previous step's (warm), out = this step's
+  float* loss_part;      // [B] sum of the pair losses of the cloud (optional)
+  float* rep_grad_out;   // [B][K][3] sum of the pair-loss gradients per point, before rep_coef (optional, diagnostics)
+  int K, k, warm;
+  int inbox_cap;         // <= kCsInbox (tests lower it to force the hub fallback)
+  float radius, h, eps, rep_coef;
+  float omb1, b2, omb2, adam_eps;
+  AdamStepConst sc;
+};
+
+struct CloudStepSmem {
+  float4 pos[kCsMaxK];                       // x y z |x|^2
+  uint32_t cell[kCsCells + 4];               // counting sort: cell[c] = first slot of cell c, cell[c + 1] = end
+  uint16_t nbr[kCsMaxK][kCsKK];              // this step's lists (column 0 = the dropped "self" column)
+  uint16_t inbox[kCsMaxK][kCsInbox];         // sources of non-mutual in-edges
+  uint32_t inbox_cnt[kCsMaxK];
+  uint16_t sorted[kCsMaxK];                  // point indices in cell order
+  float gmv[3][3 * kCsMaxK];                 // g_occ, m, v of the cloud, flat [K][3] (coalesced in, coalesced out)
+  double hubsum[kCsMaxHub][3];               // in-edge sums of hubs (points whose inbox overflowed)
+  uint16_t hub[kCsMaxHub];
+  float red[8][32];
+  uint32_t scan[32];
+  float bbox[8];
+  uint32_t nhub;
+};
+
+__device__ __forceinline__ int cs_cell(float v, float lo, float inv_h) {
+  float f = floorf((v - lo) * inv_h);                     // monotone in v: range queries stay supersets
+  f = fminf(fmaxf(f, 0.0f), (float)(kCsG - 1));           // (NaN -> 0)
+  return (int)f;
+}
+
+// gradient on the TARGET t of the pair loss of edge (source s -> target t):  gcoef * (x_t - x_s), and the loss
+__device__ __forceinline__ void cs_pair(const float4& src, const float4& tgt, float radius, float h, float eps, float& gx,
+                                        float& gy, float& gz, float& loss) {
+  const float dx = sub_rn(tgt.x, src.x), dy = sub_rn(tgt.y, src.y), dz = sub_rn(tgt.z, src.z);
+  const RepPair p = repulsion_pair(dx, dy, dz, radius, h, eps);
+  gx = p.gcoef * dx;
+  gy = p.gcoef * dy;
+  gz = p.gcoef * dz;
+  loss = p.loss;
+}
+
+__device__ __forceinline__ bool cs_row_has(const uint16_t* row, int k, int who) {
+  const uint4 r = *reinterpret_cast<const uint4*>(row);   // 8 x uint16
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  bool hit = false;
+#pragma unroll
+  for (int s = 1; s < kCsKK; ++s) {
+    const uint32_t e = (s & 1) ? (w[s >> 1] >> 16) : (w[s >> 1] & 0xffffu);
+    hit |= (s <= k) && (e == (uint32_t)who);
+  }
+  return hit;
+}
+
+__global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudStepArgs a) {
+  extern __shared__ __align__(16) unsigned char cs_raw[];
+  CloudStepSmem& S = *reinterpret_cast<CloudStepSmem*>(cs_raw);
+  const int b = blockIdx.x, i = threadIdx.x, K = a.K, k = a.k;
+  const int lane = i & 31, warp = i >> 5;
+  const bool live = i < K;
+
+  // ---- all global reads happen here, coalesced over the flat [K][3] arrays; the per-point (cell-ordered) phases
+  //      below touch shared memory only
+  const size_t cloud3 = (size_t)b * K * 3;
+  float* xs = reinterpret_cast<float*>(&S.inbox[0][0]);        // xyz staging (the inbox is not in use yet)
+  for (int e = i; e < 3 * K; e += kCsThreads) {
+    xs[e] = a.xyz[cloud3 + e];
+    S.gmv[0][e] = a.g_occ[cloud3 + e];
+    S.gmv[1][e] = a.m[cloud3 + e];
+    S.gmv[2][e] = a.v[cloud3 + e];
+  }
+  if (live && a.warm) {                                        // previous lists -> 16-bit rows
+    const int4* pv = reinterpret_cast<const int4*>(a.nbr + ((size_t)b * K + i) * kCsKK);
+    const int4 p0 = pv[0], p1 = pv[1];
+    const int prev[kCsKK] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int e0 = (unsigned)prev[2 * s] < (unsigned)K ? prev[2 * s] : i;
+      const int e1 = (unsigned)prev[2 * s + 1] < (unsigned)K ? prev[2 * s + 1] : i;
+      w[s] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+    }
+    *reinterpret_cast<uint4*>(&S.nbr[i][0]) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  for (int c = i; c < kCsCells + 4; c += kCsThreads) S.cell[c] = 0;
+  S.inbox_cnt[i] = 0;
+  if (i == 0) S.nhub = 0;
+  __syncthreads();
+  float4 me0 = make_float4(0.f, 0.f, 0.f, 0.f);        // point i (load order); re-assigned in cell order below
+  if (live) {
+    const float x = xs[3 * i + 0], y = xs[3 * i + 1], z = xs[3 * i + 2];
+    me0 = make_float4(x, y, z, sqnorm3(x, y, z));
+    S.pos[i] = me0;
+  }
+
+  // ---- bounding box of the cloud
+  {
+    float lo[3] = {live ? me0.x : INFINITY, live ? me0.y : INFINITY, live ? me0.z : INFINITY};
+    float hi[3] = {live ? me0.x : -INFINITY, live ? me0.y : -INFINITY, live ? me0.z : -INFINITY};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        lo[ax] = fminf(lo[ax], __shfl_xor_sync(0xffffffffu, lo[ax], o));
+        hi[ax] = fmaxf(hi[ax], __shfl_xor_sync(0xffffffffu, hi[ax], o));
+      }
+    if (lane == 0) {
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        S.red[ax][warp] = lo[ax];
+        S.red[3 + ax][warp] = hi[ax];
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        float l = S.red[ax][lane], h2 = S.red[3 + ax][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+          h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, o));
+        }
+        if (lane == 0) {
+          S.bbox[ax] = l;
+          S.bbox[3 + ax] = h2;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const float lox = S.bbox[0], loy = S.bbox[1], loz = S.bbox[2];
+  const float ihx = (float)kCsG / fmaxf(S.bbox[3] - lox, 1e-30f);
+  const float ihy = (float)kCsG / fmaxf(S.bbox[4] - loy, 1e-30f);
+  const float ihz = (float)kCsG / fmaxf(S.bbox[5] - loz, 1e-30f);
+  // rounding-error bound of the expanded-form key against the true squared distance (~1.5e-6 * max|x|^2)
+  float m2 = 0.0f;
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const float t = fmaxf(fabsf(S.bbox[ax]), fabsf(S.bbox[3 + ax]));
+    m2 = fmaf(t, t, m2);
+  }
+  const float key_margin = 4e-6f * m2 + 1e-30f;
+
+  // ---- counting sort of the point indices by cell
+  int cid = 0;
+  if (live) {
+    cid = (cs_cell(me0.z, loz, ihz) * kCsG + cs_cell(me0.y, loy, ihy)) * kCsG + cs_cell(me0.x, lox, ihx);
+    atomicAdd(&S.cell[cid + 1], 1u);
+  }
+  __syncthreads();
+  {
+    static_assert(kCsCells == 4 * kCsThreads, "each thread scans 4 cells");
+    uint32_t* mine = &S.cell[1 + 4 * i];
+    const uint32_t c0 = mine[0], c1 = mine[1], c2 = mine[2], c3 = mine[3];
+    const uint32_t tot = c0 + c1 + c2 + c3;
+    uint32_t inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) S.scan[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = S.scan[lane];
+      uint32_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      S.scan[lane] = winc - w;
+    }
+    __syncthreads();
+    const uint32_t ex = S.scan[warp] + inc - tot;
+    mine[0] = ex;
+    mine[1] = ex + c0;
+    mine[2] = ex + c0 + c1;
+    mine[3] = ex + c0 + c1 + c2;
+  }
+  __syncthreads();
+  if (live) S.sorted[atomicAdd(&S.cell[cid + 1], 1u)] = (uint16_t)i;
+  __syncthreads();                      // now cell[c] .. cell[c + 1] delimit cell c (cell[0] == 0)
+
+  // ---- from here on thread t owns the t-th point in CELL order: the lanes of a warp are spatial neighbours, so
+  //      their range queries walk (nearly) the same rows and candidates -- coherent loops, broadcast loads
+  const int p = live ? (int)S.sorted[i] : 0;
+  const float4 me = S.pos[p];
+
+  // ---- kNN
+  TopK<kCsKK> top;
+  top.init(INFINITY);
+  if (live) {
+    // the scan threshold and the scan itself use one expression: -2 * dot(a, b) == dot(-2 a, b) bit for bit (scaling
+    // by a power of two commutes with rounding), folded into the query once; the ranking keys are knn_key proper
+    const float mx = -2.0f * me.x, my = -2.0f * me.y, mz = -2.0f * me.z;
+    float tau = INFINITY;
+    if (a.warm) {
+      const uint4 pr = *reinterpret_cast<const uint4*>(&S.nbr[p][0]);
+      const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w};
+      tau = -INFINITY;
+#pragma unroll
+      for (int s = 0; s < kCsKK; ++s)
+        if (s <= k) {
+          const int j = (int)((s & 1) ? (pw[s >> 1] >> 16) : (pw[s >> 1] & 0xffffu));
+          const float4 c = S.pos[j];
+          tau = fmaxf(tau, add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w));
+        }
+    }
+    if (tau < INFINITY) {
+      // pass 1: collect the candidates with key <= tau (typically k+1 .. k+4 of them) in a per-thread column of
+      // shared memory (the inbox array, not yet in use); pass 2 ranks them.  Keeping the insertion network out
+      // of the scan loop matters: some lane of the warp would trigger it on almost every iteration.
+      uint16_t* col = &S.inbox[0][0] + i;                      // element c at col[c * kCsThreads]
+      const float r = sqrtf(fmaxf(tau, 0.0f) + key_margin) * 1.0001f + 1e-7f;
+      const int cx0 = cs_cell(me.x - r, lox, ihx), cx1 = cs_cell(me.x + r, lox, ihx);
+      const int cy0 = cs_cell(me.y - r, loy, ihy), cy1 = cs_cell(me.y + r, loy, ihy);
+      const int cz0 = cs_cell(me.z - r, loz, ihz), cz1 = cs_cell(me.z + r, loz, ihz);
+      int cnt = 0;
+      for (int cz = cz0; cz <= cz1; ++cz)
+        for (int cy = cy0; cy <= cy1; ++cy) {
+          const int row = (cz * kCsG + cy) * kCsG;
+          const int t1 = (int)S.cell[row + cx1 + 1];
+          for (int t = (int)S.cell[row + cx0]; t < t1; ++t) {
+            const int j = S.sorted[t];
+            const float4 c = S.pos[j];
+            const float d = add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w);
+            if (d <= tau) {
+              if (cnt < kCsInbox) col[cnt * kCsThreads] = (uint16_t)j;
+              ++cnt;
+            }
+          }
+        }
+      if (cnt <= kCsInbox) {
+        for (int c0 = 0; c0 < cnt; ++c0) {
+          const int j = col[c0 * kCsThreads];
+          const float4 c = S.pos[j];
+          top.offer_lex(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+        }
+      } else {                           // loose bound (a former neighbour moved far away): rank while scanning
+        for (int cz = cz0; cz <= cz1; ++cz)
+          for (int cy = cy0; cy <= cy1; ++cy) {
+            const int row = (cz * kCsG + cy) * kCsG;
+            const int t1 = (int)S.cell[row + cx1 + 1];
+            for (int t = (int)S.cell[row + cx0]; t < t1; ++t) {
+              const int j = S.sorted[t];
+              const float4 c = S.pos[j];
+              if (add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w) <= tau)
+                top.offer_lex(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+            }
+          }
+      }
+    } else {                             // first step (or a non-finite bound): plain scan, ascending index
+#pragma unroll 4
+      for (int j = 0; j < K; ++j) {
+        const float4 c = S.pos[j];
+        top.offer(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+      }
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int e0 = (unsigned)top.id[2 * s] < (unsigned)K ? top.id[2 * s] : p;
+      const int e1 = (unsigned)top.id[2 * s + 1] < (unsigned)K ? top.id[2 * s + 1] : p;
+      w[s] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+    }
+    *reinterpret_cast<uint4*>(&S.nbr[p][0]) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncthreads();
+
+  // ---- own edges: pair terms, mutual test, inbox pushes
+  double ax = 0.0, ay = 0.0, az = 0.0;
+  float lsum = 0.0f;
+  if (live) {
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+#pragma unroll
+    for (int s = 1; s < kCsKK; ++s)
+      if (s <= k) {
+        const int j = (unsigned)top.id[s] < (unsigned)K ? top.id[s] : p;
+        float gx, gy, gz, l;
+        cs_pair(me, S.pos[j], a.radius, a.h, a.eps, gx, gy, gz, l);       // gradient on j; on i it is the negative
+        lsum += l;
+        sx -= gx;
+        sy -= gy;
+        sz -= gz;
+        if (cs_row_has(S.nbr[j], k, p)) {      // j -> p exists too: its gradient on p is bitwise -g
+          ax += (double)(-gx);
+          ay += (double)(-gy);
+          az += (double)(-gz);
+        } else {
+          const uint32_t slot = atomicAdd(&S.inbox_cnt[j], 1u);
+          if (slot < (uint32_t)a.inbox_cap) S.inbox[j][slot] = (uint16_t)p;
+        }
+      }
+    ax += (double)sx;
+    ay += (double)sy;
+    az += (double)sz;
+  }
+  __syncthreads();
+
+  // ---- hubs: a point with more non-mutual in-edges than inbox slots (an outlier-rich or very uneven cloud) gets
+  //      them from a warp-cooperative scan of all K lists -- one thread doing that scan alone would hold the whole
+  //      CTA back (measured: one such point tripled the kernel time)
+  const int in_cnt = live ? (int)S.inbox_cnt[p] : 0;
+  if (in_cnt > a.inbox_cap) {
+    const uint32_t h = atomicAdd(&S.nhub, 1u);
+    if (h < (uint32_t)kCsMaxHub) S.hub[h] = (uint16_t)p;
+    S.inbox[p][0] = (uint16_t)(h < (uint32_t)kCsMaxHub ? h : 0xffffu);
+  }
+  __syncthreads();
+  {
+    const int nh = min((int)S.nhub, kCsMaxHub);
+    for (int h = warp; h < nh; h += kCsThreads / 32) {
+      const int j = S.hub[h];
+      const float4 tj = S.pos[j];
+      double hx = 0.0, hy = 0.0, hz = 0.0;
+      for (int q = lane; q < K; q += 32) {
+        if (!cs_row_has(S.nbr[q], k, j) || cs_row_has(S.nbr[j], k, q)) continue;
+        float gx, gy, gz, l;
+        cs_pair(S.pos[q], tj, a.radius, a.h, a.eps, gx, gy, gz, l);
+        hx += (double)gx;
+        hy += (double)gy;
+        hz += (double)gz;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        hx += __shfl_xor_sync(0xffffffffu, hx, o);
+        hy += __shfl_xor_sync(0xffffffffu, hy, o);
+        hz += __shfl_xor_sync(0xffffffffu, hz, o);
+      }
+      if (lane == 0) {
+        S.hubsum[h][0] = hx;
+        S.hubsum[h][1] = hy;
+        S.hubsum[h][2] = hz;
+      }
+    }
+    if (nh > 0) __syncthreads();           // block-uniform
+  }
+
+  // ---- in-edges from non-mutual sources, ascending source index
+  if (live) {
+    if (in_cnt <= a.inbox_cap) {
+      int last = -1;
+      for (int t = 0; t < in_cnt; ++t) {
+        int q = 0x7fffffff;
+        for (int u = 0; u < in_cnt; ++u) {
+          const int e = S.inbox[p][u];
+          if (e > last && e < q) q = e;
+        }
+        last = q;
+        float gx, gy, gz, l;
+        cs_pair(S.pos[q], me, a.radius, a.h, a.eps, gx, gy, gz, l);
+        ax += (double)gx;
+        ay += (double)gy;
+        az += (double)gz;
+      }
+    } else if (S.inbox[p][0] != 0xffffu) {     // hub served above
+      const int h = S.inbox[p][0];
+      ax += S.hubsum[h][0];
+      ay += S.hubsum[h][1];
+      az += S.hubsum[h][2];
+    } else {                                   // more than kCsMaxHub hubs: ordered scan of every list
+      for (int q = 0; q < K; ++q) {
+        if (!cs_row_has(S.nbr[q], k, p)) continue;
+        bool mutual = false;
+#pragma unroll
+        for (int s = 1; s < kCsKK; ++s) mutual |= (s <= k) && (top.id[s] == q);
+        if (mutual) continue;
+        float gx, gy, gz, l;
+        cs_pair(S.pos[q], me, a.radius, a.h, a.eps, gx, gy, gz, l);
+        ax += (double)gx;
+        ay += (double)gy;
+        az += (double)gz;
+      }
+    }
+    // ---- Adam (torch 2.11 single-tensor formula, ifd_math.cuh); results staged for the coalesced store
+    float* xo = reinterpret_cast<float*>(&S.cell[0]);           // the grid is no longer needed
+    float p3[3] = {me.x, me.y, me.z};
+    const float r3[3] = {(float)ax, (float)ay, (float)az};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float g = S.gmv[0][3 * p + c] + r3[c] * a.rep_coef;
+      float mm = S.gmv[1][3 * p + c], vv = S.gmv[2][3 * p + c];
+      adam_update(p3[c], mm, vv, g, a.omb1, a.b2, a.omb2, a.adam_eps, a.sc);
+      xo[3 * p + c] = p3[c];
+      S.gmv[0][3 * p + c] = r3[c];
+      S.gmv[1][3 * p + c] = mm;
+      S.gmv[2][3 * p + c] = vv;
+    }
+    xo[3 * kCsMaxK + p] = lsum;                                 // pair-loss sum of point p
+  }
+  __syncthreads();
+  // ---- all global writes, coalesced
+  {
+    const float* xo = reinterpret_cast<const float*>(&S.cell[0]);
+    for (int e = i; e < 3 * K; e += kCsThreads) {
+      a.xyz[cloud3 + e] = xo[e];
+      a.m[cloud3 + e] = S.gmv[1][e];
+      a.v[cloud3 + e] = S.gmv[2][e];
+      if (a.rep_grad_out) a.rep_grad_out[cloud3 + e] = S.gmv[0][e];
+    }
+    if (live) {
+      const uint4 r = *reinterpret_cast<const uint4*>(&S.nbr[i][0]);
+      int4* pv = reinterpret_cast<int4*>(a.nbr + ((size_t)b * K + i) * kCsKK);
+      pv[0] = make_int4((int)(r.x & 0xffffu), (int)(r.x >> 16), (int)(r.y & 0xffffu), (int)(r.y >> 16));
+      pv[1] = make_int4((int)(r.z & 0xffffu), (int)(r.z >> 16), (int)(r.w & 0xffffu), (int)(r.w >> 16));
+    }
+    // ---- sum of the pair losses in POINT order (the thread <-> point map above depends on atomic arrival order)
+    if (a.loss_part) {
+      float l = live ? xo[3 * kCsMaxK + i] : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+      if (lane == 0) S.red[6][warp] = l;
+      __syncthreads();
+      if (i == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < kCsThreads / 32; ++w) t += S.red[6][w];
+        a.loss_part[b] = t;
+      }
+    }
+  }
+}
+
+}  // namespace ifd

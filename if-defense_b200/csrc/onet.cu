@@ -534,7 +534,7 @@ extern "C" int ifd_onet_decode_bwd(const float* dec_weights, const float* xyz, c
 namespace ifd {
 int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int K, const ifd_opt_params* P, int i, void* conv_ws,
                   bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st);
-int opt_begin(float* m, float* v, bool zero_state, int B, int K, void* conv_ws, cudaStream_t st);
+int opt_begin(float* m, float* v, bool zero_state, int B, int K, const ifd_opt_params* P, void* conv_ws, cudaStream_t st);
 int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st);
 float* opt_ws_gocc(void* conv_ws, int B, int K);
 float* opt_ws_m(void* conv_ws, int B, int K);
@@ -557,7 +557,7 @@ extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz
   if (rc) return rc;
   float* m = adam_m ? adam_m : opt_ws_m(conv_ws, B, K);
   float* v = adam_v ? adam_v : opt_ws_v(conv_ws, B, K);
-  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, conv_ws, st))) return rc;
+  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, P, conv_ws, st))) return rc;
   float* g_occ = opt_ws_gocc(conv_ws, B, K);
   const int M = B * K;
   const float ginv = (float)K / (float)((long long)P->B_ref * K);

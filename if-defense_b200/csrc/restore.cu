@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "convonet_point.cuh"
 #include "decode_v2.cuh"
+#include "cloud_step.cuh"
 #include "decode_v3.cuh"
 #include "topk.cuh"
 
@@ -484,14 +485,22 @@ float* opt_ws_gocc(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).g_occ
 float* opt_ws_m(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).m; }
 float* opt_ws_v(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).v; }
 
-int opt_begin(float* m, float* v, bool zero_state, int B, int K, void* ws, cudaStream_t st) {
+static int g_inbox_cap = kCsInbox;   // ifd_test_hook(1, cap)
+
+// The fused per-cloud tail (cloud_step.cuh) handles one point per thread; larger clouds and k + 1 > 8 use the
+// first-generation kernels (knn_repulsion_kernel + adam_kernel), as does tail_kernel == 1.
+bool opt_tail_fused(int K, const ifd_opt_params* P) {
+  return P->tail_kernel == 0 && K <= kCsMaxK && P->knn_k + 1 <= kCsKK && P->rep_weight > 0.0;
+}
+
+int opt_begin(float* m, float* v, bool zero_state, int B, int K, const ifd_opt_params* P, void* ws, cudaStream_t st) {
   OptWorkspace w = carve_opt_ws(ws, B, K);
   const size_t n = (size_t)B * K * 3;
   if (zero_state) {
     IFD_CUDA_TRY(cudaMemsetAsync(m, 0, n * sizeof(float), st));
     IFD_CUDA_TRY(cudaMemsetAsync(v, 0, n * sizeof(float), st));
   }
-  IFD_CUDA_TRY(cudaMemsetAsync(w.acc, 0, n * kFxLimbs * sizeof(long long), st));
+  if (!opt_tail_fused(K, P)) IFD_CUDA_TRY(cudaMemsetAsync(w.acc, 0, n * kFxLimbs * sizeof(long long), st));
   return IFD_OK;
 }
 
@@ -502,6 +511,33 @@ int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int
   const size_t n = (size_t)B * K * 3;
   const bool rep = P->rep_weight > 0.0;
   if (rep && (P->knn_k + 1 > 8 || P->knn_k < 1)) return fail(IFD_ERR_UNSUPPORTED, "knn_k must be in [1, 7]");
+  if (P->tail_kernel != 0 && P->tail_kernel != 1) return fail(IFD_ERR_INVALID, "tail_kernel must be 0 or 1");
+  // rep_loss = mean_B(mean_{K,k}) * rep_weight: grad = rep_weight / B_ref / (K*k)
+  const float rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
+  const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
+  const double t = (double)(P->step0 + i + 1);
+  AdamStepConst sc;
+  sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
+  sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
+  if (opt_tail_fused(K, P)) {
+    CloudStepArgs c{};
+    c.xyz = xyz; c.m = m; c.v = v; c.g_occ = g_occ; c.nbr = w.nbr; c.loss_part = stat ? w.loss_part : nullptr;
+    c.K = K; c.k = P->knn_k; c.warm = (i > 0 && warm_ok) ? 1 : 0; c.inbox_cap = g_inbox_cap;
+    c.radius = (float)P->rep_radius; c.h = (float)P->rep_h; c.eps = (float)P->rep_eps; c.rep_coef = rep_coef;
+    c.omb1 = omb1; c.b2 = (float)P->beta2; c.omb2 = omb2; c.adam_eps = (float)P->adam_eps; c.sc = sc;
+    {
+      ProfileScope ps(1, st);
+      IFD_CUDA_TRY(cudaFuncSetAttribute(cloud_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CloudStepSmem)));
+      cloud_step_kernel<<<B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
+      IFD_LAUNCH_CHECK("cloud_step_kernel");
+    }
+    if (stat) {
+      stats_kernel<<<1, 32, 0, st>>>(dec_part, n_dec, w.loss_part, B, 1, K, P->knn_k, (float)P->rep_weight,
+                                     stats_out + (size_t)(i / 100) * 4);
+      IFD_LAUNCH_CHECK("stats_kernel");
+    }
+    return IFD_OK;
+  }
   int rc;
   if (rep) {
     ProfileScope ps(1, st);
@@ -514,13 +550,6 @@ int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int
                                    stats_out + (size_t)(i / 100) * 4);
     IFD_LAUNCH_CHECK("stats_kernel");
   }
-  // rep_loss = mean_B(mean_{K,k}) * rep_weight: grad = rep_weight / B_ref / (K*k)
-  const float rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
-  const float omb1 = (float)(1.0 - P->beta1), omb2 = (float)(1.0 - P->beta2);
-  const double t = (double)(P->step0 + i + 1);
-  AdamStepConst sc;
-  sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
-  sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
   {
     ProfileScope ps(2, st);
     adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz, m, v, g_occ, rep ? w.acc : nullptr, (int)n, rep_coef, omb1,
@@ -617,7 +646,7 @@ extern "C" void ifd_opt_params_default(ifd_opt_params* p) {
   p->lr = 1e-3; p->beta1 = 0.9; p->beta2 = 0.999; p->adam_eps = 1e-8;
   p->occ_target = 0.2; p->rep_weight = 500.0;
   p->rep_radius = 0.07; p->rep_h = 0.03; p->rep_eps = 1e-12; p->padding = 0.1;
-  p->decode_kernel = 0; p->reserved_ = 0;
+  p->decode_kernel = 0; p->tail_kernel = 0;
 }
 
 extern "C" size_t ifd_convonet_opt_workspace_bytes(int B, int K) {
@@ -641,7 +670,7 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   OptWorkspace w = carve_opt_ws(workspace, B, K);
   float* m = adam_m ? adam_m : w.m;
   float* v = adam_v ? adam_v : w.v;
-  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, workspace, st))) return rc;
+  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, P, workspace, st))) return rc;
 
   DecodeArgs a{};
   a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_out = w.g_occ;
@@ -670,6 +699,30 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   return opt_finish(xyz, B, K, P->normalize_out, st);
 }
 
+// One loop tail as a seam of its own (opt_defense.py:219-228: repulsion loss, its backward, Adam step).
+extern "C" int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const float* g_occ, int32_t* nbr, int warm, int B,
+                                 int K, const ifd_opt_params* P, int step_index, float* loss_sum_out, float* rep_grad_out,
+                                 ifd_stream_t stream) {
+  IFD_REQUIRE(xyz && adam_m && adam_v && g_occ && nbr && P && B > 0 && K > 0 && step_index >= 0, "ifd_opt_tail_step: bad arguments");
+  IFD_REQUIRE(P->B_ref > 0 && P->knn_k >= 1, "ifd_opt_tail_step: bad B_ref / knn_k");
+  if (!(K <= kCsMaxK && P->knn_k + 1 <= kCsKK)) return fail(IFD_ERR_UNSUPPORTED, "ifd_opt_tail_step: needs K <= 1024 and knn_k <= 7");
+  if (P->knn_k + 1 > K) return fail(IFD_ERR_INVALID, "ifd_opt_tail_step: kNN size exceeds the number of points");
+  cudaStream_t st = as_stream(stream);
+  const double t = (double)(step_index + 1);
+  CloudStepArgs c{};
+  c.xyz = xyz; c.m = adam_m; c.v = adam_v; c.g_occ = g_occ; c.nbr = nbr; c.loss_part = loss_sum_out; c.rep_grad_out = rep_grad_out;
+  c.K = K; c.k = P->knn_k; c.warm = warm ? 1 : 0; c.inbox_cap = g_inbox_cap;
+  c.radius = (float)P->rep_radius; c.h = (float)P->rep_h; c.eps = (float)P->rep_eps;
+  c.rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
+  c.omb1 = (float)(1.0 - P->beta1); c.b2 = (float)P->beta2; c.omb2 = (float)(1.0 - P->beta2); c.adam_eps = (float)P->adam_eps;
+  c.sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
+  c.sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
+  IFD_CUDA_TRY(cudaFuncSetAttribute(cloud_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CloudStepSmem)));
+  cloud_step_kernel<<<B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
+  IFD_LAUNCH_CHECK("cloud_step_kernel");
+  return IFD_OK;
+}
+
 extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,
                                             int R, int C, int H, int n_blocks, double padding, double occ_target, int B_ref,
                                             int decode_kernel, float* grad_xyz_out, void* workspace, size_t workspace_bytes,
@@ -695,6 +748,10 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
     IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
   }
   return dk == 1 ? launch_decode(kBce, a, st) : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+}
+
+extern "C" void ifd_test_hook(int key, int value) {
+  if (key == 1) g_inbox_cap = value < 0 ? 0 : (value > kCsInbox ? kCsInbox : value);
 }
 
 extern "C" int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream) {

@@ -40,6 +40,24 @@ struct TopK {
   __device__ __forceinline__ void offer(KeyT d, int j) {
     if (d < key[KK - 1]) insert(d, j);
   }
+
+  // Same (key, index) order for candidates offered in ARBITRARY index order (grid traversal): the index is part
+  // of the comparison instead of being implied by the visiting order.
+  __device__ __forceinline__ void offer_lex(KeyT d, int j) {
+    if (!(d < key[KK - 1] || (d == key[KK - 1] && j < id[KK - 1]))) return;
+    key[KK - 1] = d;
+    id[KK - 1] = j;
+#pragma unroll
+    for (int s = KK - 1; s > 0; --s) {
+      const bool sw = key[s] < key[s - 1] || (key[s] == key[s - 1] && id[s] < id[s - 1]);
+      const KeyT ka = key[s - 1], kb = key[s];
+      const int ia = id[s - 1], ib = id[s];
+      key[s - 1] = sw ? kb : ka;
+      key[s] = sw ? ka : kb;
+      id[s - 1] = sw ? ib : ia;
+      id[s] = sw ? ia : ib;
+    }
+  }
 };
 
 }  // namespace ifd

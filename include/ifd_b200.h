@@ -154,7 +154,9 @@ typedef struct ifd_opt_params {
                             1: v1, thread-per-point fp32 SIMT (the step-level seam; from-scratch kNN every step);
                             2: v2, fp32 SIMT, cooperative gather, 2 points/thread, FFMA2, generic layer bodies;
                             3: v3, ResNet-MLP on tcgen05 tensor cores (3xTF32, A in TMEM, fp32-class accuracy) */
-  int32_t reserved_;
+  int32_t tail_kernel;   /* what follows the decode in a step -- 0: the production default, one fused kernel per cloud
+                            (grid kNN + repulsion gather + Adam, K <= 1024, knn_k <= 7); 1: first-generation kernels
+                            (brute-force kNN + exact long accumulator, separate Adam), any K <= 12000 */
 } ifd_opt_params;
 
 void ifd_opt_params_default(ifd_opt_params* p);
@@ -169,6 +171,19 @@ size_t ifd_convonet_opt_workspace_bytes(int B, int K);
 int ifd_convonet_opt(const float* planes_cl, const float* dec_weights, float* xyz, float* adam_m, float* adam_v,
                      int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* params,
                      double* stats_out, void* workspace, size_t workspace_bytes, ifd_stream_t stream);
+
+/* The tail of one iteration as a seam of its own (opt_defense.py:219-228: rep_loss = repulsion_loss(p).mean() *
+ * rep_weight, its backward into p, then opt.step()): one fused kernel per cloud -- grid-accelerated knn_point
+ * (identical indices to the brute-force scan), repulsion pair terms gathered per point in a canonical order, Adam.
+ * xyz / adam_m / adam_v [B][K][3] are updated in place with the gradient g_occ + d(rep_loss)/dp; Adam's bias
+ * corrections use t = step_index + 1.  nbr [B][K][8] int32 receives the k+1 ranked neighbours per point (column 0
+ * is the column knn_point drops); with warm != 0 it must hold the lists of the previous call on the same points
+ * moved by a small step (the search is bounded by their current distances).  loss_sum_out (optional) [B]: sum of
+ * the pair losses per cloud; rep_grad_out (optional) [B][K][3]: summed pair-loss gradients before the
+ * rep_weight / (B_ref K k) factor.  K <= 1024, knn_k <= 7. */
+int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const float* g_occ, int32_t* nbr, int warm, int B,
+                      int K, const ifd_opt_params* params, int step_index, float* loss_sum_out, float* rep_grad_out,
+                      ifd_stream_t stream);
 
 /* Host-buffer convenience call (the end-to-end seam): planes in the reference's NCHW layout
  * [3][B][C][R][R], weights, xyz are HOST pointers; does H2D, layout conversion, the loop, D2H of xyz and
@@ -221,6 +236,10 @@ long long ifd_launch_count(int reset);
 /* Tensor-core self test: D[128][32] = A[128][32] . Bm[32][32]^T (Bm is [n][k]) through the tcgen05 / TMEM /
  * 3xTF32 path of the v3 decode kernel.  Device pointers. */
 int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream);
+
+/* Test instrumentation.  key 1: capacity (0..16, default 16) of the per-point inbox of non-mutual in-edges in the
+ * fused tail kernel; lowering it forces the ordered-scan fallback that hubs take.  Results do not depend on it. */
+void ifd_test_hook(int key, int value);
 
 #define IFD_PROFILE_KINDS 4
 void ifd_profile_enable(int on);

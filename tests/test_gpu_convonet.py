@@ -236,7 +236,7 @@ def test_full_size_properties():
     capi.lib().ifd_launch_count(1)
     x, st = run_opt(d, pl, case.p0, 201, normalize=1, stats=True)
     launches = capi.lib().ifd_launch_count(0)
-    assert launches >= 201 * 3
+    assert launches >= 201 * 2        # decode + fused per-cloud tail per Adam step
     assert x.shape == (64, 1024, 3) and np.isfinite(x).all()
     assert np.abs(x.mean(1)).max() < 1e-5
     np.testing.assert_allclose(np.linalg.norm(x, axis=2).max(1), 1.0, rtol=1e-6)
