@@ -18,7 +18,13 @@
 //   * every point sums its terms in one canonical order (mutual terms by rank, own sum, in-edges by ascending
 //     source) in fp64, so the result does not depend on atomic arrival order: bitwise reproducible;
 //   * Adam runs in the same thread; xyz, m, v make one round trip to HBM/L2 per step.
+//
+// Two CTAs (a thread-block cluster) per cloud: both build the whole grid, the cloud is split at the cell boundary
+// nearest the median (a deterministic function of the cell histogram), each CTA ranks / sums / updates the points
+// on its side, neighbour lists and non-mutual in-edges cross through distributed shared memory.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "ifd_math.cuh"
 #include "topk.cuh"
@@ -56,12 +62,15 @@ struct CloudStepSmem {
   uint32_t inbox_cnt[kCsMaxK];
   uint16_t sorted[kCsMaxK];                  // point indices in cell order
   float gmv[3][3 * kCsMaxK];                 // g_occ, m, v of the cloud, flat [K][3] (coalesced in, coalesced out)
+  uint16_t cid[kCsMaxK];                     // cell of every point (ownership: cell < split -> CTA 0)
   double hubsum[kCsMaxHub][3];               // in-edge sums of hubs (points whose inbox overflowed)
   uint16_t hub[kCsMaxHub];
   float red[8][32];
   uint32_t scan[32];
   float bbox[8];
   uint32_t nhub;
+  int split_cell, split_rank;                // first cell / first sorted rank owned by CTA 1
+  float peer_loss;
 };
 
 __device__ __forceinline__ int cs_cell(float v, float lo, float inv_h) {
@@ -69,6 +78,10 @@ __device__ __forceinline__ int cs_cell(float v, float lo, float inv_h) {
   f = fminf(fmaxf(f, 0.0f), (float)(kCsG - 1));           // (NaN -> 0)
   return (int)f;
 }
+
+// Linear index of cell (cx, cy, cz), x fastest: for fixed (cy, cz) an x-range of cells is one contiguous range of
+// the sorted point array.
+__device__ __forceinline__ int cs_index(int cx, int cy, int cz) { return (cz * kCsG + cy) * kCsG + cx; }
 
 // gradient on the TARGET t of the pair loss of edge (source s -> target t):  gcoef * (x_t - x_s), and the loss
 __device__ __forceinline__ void cs_pair(const float4& src, const float4& tgt, float radius, float h, float eps, float& gx,
@@ -93,15 +106,17 @@ __device__ __forceinline__ bool cs_row_has(const uint16_t* row, int k, int who) 
   return hit;
 }
 
-__global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudStepArgs a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudStepArgs a) {
   extern __shared__ __align__(16) unsigned char cs_raw[];
   CloudStepSmem& S = *reinterpret_cast<CloudStepSmem*>(cs_raw);
-  const int b = blockIdx.x, i = threadIdx.x, K = a.K, k = a.k;
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  const int half = (int)cluster.block_rank();                  // which side of the split this CTA owns
+  CloudStepSmem& P = *cluster.map_shared_rank(&S, half ^ 1);   // the peer CTA's shared memory
+  const int b = blockIdx.x >> 1, i = threadIdx.x, K = a.K, k = a.k;
   const int lane = i & 31, warp = i >> 5;
-  const bool live = i < K;
+  bool live = i < K;
 
-  // ---- all global reads happen here, coalesced over the flat [K][3] arrays; the per-point (cell-ordered) phases
-  //      below touch shared memory only
+  // ---- all global reads happen here, coalesced over the flat [K][3] arrays (both CTAs read the whole cloud)
   const size_t cloud3 = (size_t)b * K * 3;
   float* xs = reinterpret_cast<float*>(&S.inbox[0][0]);        // xyz staging (the inbox is not in use yet)
   for (int e = i; e < 3 * K; e += kCsThreads) {
@@ -125,7 +140,12 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
   }
   for (int c = i; c < kCsCells + 4; c += kCsThreads) S.cell[c] = 0;
   S.inbox_cnt[i] = 0;
-  if (i == 0) S.nhub = 0;
+  if (i == 0) {
+    S.nhub = 0;
+    S.split_cell = kCsCells;
+    S.split_rank = K;
+    S.peer_loss = 0.0f;
+  }
   __syncthreads();
   float4 me0 = make_float4(0.f, 0.f, 0.f, 0.f);        // point i (load order); re-assigned in cell order below
   if (live) {
@@ -186,7 +206,8 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
   // ---- counting sort of the point indices by cell
   int cid = 0;
   if (live) {
-    cid = (cs_cell(me0.z, loz, ihz) * kCsG + cs_cell(me0.y, loy, ihy)) * kCsG + cs_cell(me0.x, lox, ihx);
+    cid = cs_index(cs_cell(me0.x, lox, ihx), cs_cell(me0.y, loy, ihy), cs_cell(me0.z, loz, ihz));
+    S.cid[i] = (uint16_t)cid;
     atomicAdd(&S.cell[cid + 1], 1u);
   }
   __syncthreads();
@@ -219,6 +240,15 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
     mine[1] = ex + c0;
     mine[2] = ex + c0 + c1;
     mine[3] = ex + c0 + c1 + c2;
+    // split: the first cell whose exclusive start reaches K/2 (unique; none -> CTA 0 owns everything)
+    const uint32_t e4[5] = {ex, ex + c0, ex + c0 + c1, ex + c0 + c1 + c2, ex + tot};
+    const uint32_t halfK = (uint32_t)((K + 1) / 2);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (e4[u] < halfK && e4[u + 1] >= halfK && 4 * i + u + 1 < kCsCells) {
+        S.split_cell = 4 * i + u + 1;
+        S.split_rank = (int)e4[u + 1];
+      }
   }
   __syncthreads();
   if (live) S.sorted[atomicAdd(&S.cell[cid + 1], 1u)] = (uint16_t)i;
@@ -226,18 +256,20 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
 
   // ---- from here on thread t owns the t-th point in CELL order: the lanes of a warp are spatial neighbours, so
   //      their range queries walk (nearly) the same rows and candidates -- coherent loops, broadcast loads
-  const int p = live ? (int)S.sorted[i] : 0;
+  const int rank0 = half == 0 ? 0 : S.split_rank, rank1 = half == 0 ? S.split_rank : K;
+  live = rank0 + i < rank1;
+  const int p = live ? (int)S.sorted[rank0 + i] : (int)S.sorted[0];
   const float4 me = S.pos[p];
 
   // ---- kNN
   TopK<kCsKK> top;
   top.init(INFINITY);
-  if (live) {
+  {
     // the scan threshold and the scan itself use one expression: -2 * dot(a, b) == dot(-2 a, b) bit for bit (scaling
     // by a power of two commutes with rounding), folded into the query once; the ranking keys are knn_key proper
     const float mx = -2.0f * me.x, my = -2.0f * me.y, mz = -2.0f * me.z;
-    float tau = INFINITY;
-    if (a.warm) {
+    float tau = live ? INFINITY : -INFINITY;                   // idle lanes accept nothing
+    if (live && a.warm) {
       const uint4 pr = *reinterpret_cast<const uint4*>(&S.nbr[p][0]);
       const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w};
       tau = -INFINITY;
@@ -248,23 +280,47 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
           const float4 c = S.pos[j];
           tau = fmaxf(tau, add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w));
         }
+      if (!(tau < INFINITY)) tau = INFINITY;                   // NaN -> unbounded
     }
-    if (tau < INFINITY) {
-      // pass 1: collect the candidates with key <= tau (typically k+1 .. k+4 of them) in a per-thread column of
-      // shared memory (the inbox array, not yet in use); pass 2 ranks them.  Keeping the insertion network out
-      // of the scan loop matters: some lane of the warp would trigger it on almost every iteration.
-      uint16_t* col = &S.inbox[0][0] + i;                      // element c at col[c * kCsThreads]
-      const float r = sqrtf(fmaxf(tau, 0.0f) + key_margin) * 1.0001f + 1e-7f;
-      const int cx0 = cs_cell(me.x - r, lox, ihx), cx1 = cs_cell(me.x + r, lox, ihx);
-      const int cy0 = cs_cell(me.y - r, loy, ihy), cy1 = cs_cell(me.y + r, loy, ihy);
-      const int cz0 = cs_cell(me.z - r, loz, ihz), cz1 = cs_cell(me.z + r, loz, ihz);
-      int cnt = 0;
-      for (int cz = cz0; cz <= cz1; ++cz)
-        for (int cy = cy0; cy <= cy1; ++cy) {
-          const int row = (cz * kCsG + cy) * kCsG;
-          const int t1 = (int)S.cell[row + cx1 + 1];
-          for (int t = (int)S.cell[row + cx0]; t < t1; ++t) {
-            const int j = S.sorted[t];
+    // Cell box of this lane's query sphere.  Each lane walks its own rows and candidates with a FLAT iterator -- one
+    // action per warp iteration, either "advance to the next row" or "evaluate one candidate" -- so the warp runs
+    // for max-over-lanes (rows + candidates) iterations instead of the product of the per-row maxima that nested
+    // loops cost (measured: 2400 instructions per warp for ~300 useful per lane).
+    int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1, bz0 = 0, bz1 = -1;
+    if (live) {
+      if (tau < INFINITY) {
+        const float r = sqrtf(fmaxf(tau, 0.0f) + key_margin) * 1.0001f + 1e-7f;
+        bx0 = cs_cell(me.x - r, lox, ihx); bx1 = cs_cell(me.x + r, lox, ihx);
+        by0 = cs_cell(me.y - r, loy, ihy); by1 = cs_cell(me.y + r, loy, ihy);
+        bz0 = cs_cell(me.z - r, loz, ihz); bz1 = cs_cell(me.z + r, loz, ihz);
+      } else {
+        bx1 = by1 = bz1 = kCsG - 1;
+      }
+    }
+    // pass 1: collect the candidates with key <= tau (typically k+1 .. k+4 of them) in a per-thread column of
+    // shared memory (the inbox array, not yet in use); pass 2 ranks them.  The insertion network stays out of the
+    // scan loop: some lane of the warp would trigger it on almost every iteration.
+    uint16_t* col = &S.inbox[0][0] + i;                        // element c at col[c * kCsThreads]
+    int cnt = 0;
+    {
+      int cz = bz0, cy = by0 - 1, t = 0, t1 = 0;
+      bool more = live;
+      while (__any_sync(0xffffffffu, more)) {
+        if (more) {
+          if (t >= t1) {                                       // next row of the box
+            if (++cy > by1) {
+              cy = by0;
+              ++cz;
+            }
+            if (cz > bz1) {
+              more = false;
+            } else {
+              const int row = cs_index(0, cy, cz);
+              t = (int)S.cell[row + bx0];
+              t1 = (int)S.cell[row + bx1 + 1];
+            }
+          } else {
+            const int j = S.sorted[t++];
             const float4 c = S.pos[j];
             const float d = add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w);
             if (d <= tau) {
@@ -273,32 +329,30 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
             }
           }
         }
-      if (cnt <= kCsInbox) {
-        for (int c0 = 0; c0 < cnt; ++c0) {
-          const int j = col[c0 * kCsThreads];
-          const float4 c = S.pos[j];
-          top.offer_lex(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
-        }
-      } else {                           // loose bound (a former neighbour moved far away): rank while scanning
-        for (int cz = cz0; cz <= cz1; ++cz)
-          for (int cy = cy0; cy <= cy1; ++cy) {
-            const int row = (cz * kCsG + cy) * kCsG;
-            const int t1 = (int)S.cell[row + cx1 + 1];
-            for (int t = (int)S.cell[row + cx0]; t < t1; ++t) {
-              const int j = S.sorted[t];
-              const float4 c = S.pos[j];
-              if (add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w) <= tau)
-                top.offer_lex(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
-            }
-          }
-      }
-    } else {                             // first step (or a non-finite bound): plain scan, ascending index
-#pragma unroll 4
-      for (int j = 0; j < K; ++j) {
-        const float4 c = S.pos[j];
-        top.offer(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
       }
     }
+    if (live && cnt <= kCsInbox) {
+      for (int c0 = 0; c0 < cnt; ++c0) {
+        const int j = col[c0 * kCsThreads];
+        const float4 c = S.pos[j];
+        top.offer_lex(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+      }
+    }
+    if (live && cnt > kCsInbox) {        // loose bound (first step, or a neighbour moved far away): rank while scanning
+      for (int cz = bz0; cz <= bz1; ++cz)
+        for (int cy = by0; cy <= by1; ++cy) {
+          const int row = cs_index(0, cy, cz);
+          const int t1 = (int)S.cell[row + bx1 + 1];
+          for (int t = (int)S.cell[row + bx0]; t < t1; ++t) {
+            const int j = S.sorted[t];
+            const float4 c = S.pos[j];
+            if (add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w) <= tau)
+              top.offer_lex(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+          }
+        }
+    }
+  }
+  if (live) {
     uint32_t w[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -306,9 +360,14 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
       const int e1 = (unsigned)top.id[2 * s + 1] < (unsigned)K ? top.id[2 * s + 1] : p;
       w[s] = (uint32_t)e0 | ((uint32_t)e1 << 16);
     }
-    *reinterpret_cast<uint4*>(&S.nbr[p][0]) = make_uint4(w[0], w[1], w[2], w[3]);
+    const uint4 row16 = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(&S.nbr[p][0]) = row16;            // this CTA's copy
+    *reinterpret_cast<uint4*>(&P.nbr[p][0]) = row16;            // the peer's copy (distributed shared memory)
+    int4* pv = reinterpret_cast<int4*>(a.nbr + ((size_t)b * K + p) * kCsKK);   // warm start of the next step
+    pv[0] = make_int4(top.id[0], top.id[1], top.id[2], top.id[3]);
+    pv[1] = make_int4(top.id[4], top.id[5], top.id[6], top.id[7]);
   }
-  __syncthreads();
+  cluster.sync();                       // both CTAs now hold all K lists
 
   // ---- own edges: pair terms, mutual test, inbox pushes
   double ax = 0.0, ay = 0.0, az = 0.0;
@@ -330,15 +389,18 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
           ay += (double)(-gy);
           az += (double)(-gz);
         } else {
-          const uint32_t slot = atomicAdd(&S.inbox_cnt[j], 1u);
-          if (slot < (uint32_t)a.inbox_cap) S.inbox[j][slot] = (uint16_t)p;
+          CloudStepSmem& O = ((int)S.cid[j] >= S.split_cell) == (half == 1) ? S : P;     // the CTA that owns j
+          const uint32_t slot = atomicAdd(&O.inbox_cnt[j], 1u);
+          if (slot < (uint32_t)a.inbox_cap) O.inbox[j][slot] = (uint16_t)p;
         }
       }
     ax += (double)sx;
     ay += (double)sy;
     az += (double)sz;
   }
-  __syncthreads();
+  cluster.sync();                       // all pushes (local and remote) have landed
+  float* ls = reinterpret_cast<float*>(&S.cell[0]);             // the grid is no longer needed: per-point loss staging
+  ls[i] = 0.0f;
 
   // ---- hubs: a point with more non-mutual in-edges than inbox slots (an outlier-rich or very uneven cloud) gets
   //      them from a warp-cooperative scan of all K lists -- one thread doing that scan alone would hold the whole
@@ -415,8 +477,8 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
         az += (double)gz;
       }
     }
-    // ---- Adam (torch 2.11 single-tensor formula, ifd_math.cuh); results staged for the coalesced store
-    float* xo = reinterpret_cast<float*>(&S.cell[0]);           // the grid is no longer needed
+    // ---- Adam (torch 2.11 single-tensor formula, ifd_math.cuh)
+    const size_t o3 = cloud3 + (size_t)3 * p;
     float p3[3] = {me.x, me.y, me.z};
     const float r3[3] = {(float)ax, (float)ay, (float)az};
 #pragma unroll
@@ -424,42 +486,29 @@ __global__ void __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudSt
       const float g = S.gmv[0][3 * p + c] + r3[c] * a.rep_coef;
       float mm = S.gmv[1][3 * p + c], vv = S.gmv[2][3 * p + c];
       adam_update(p3[c], mm, vv, g, a.omb1, a.b2, a.omb2, a.adam_eps, a.sc);
-      xo[3 * p + c] = p3[c];
-      S.gmv[0][3 * p + c] = r3[c];
-      S.gmv[1][3 * p + c] = mm;
-      S.gmv[2][3 * p + c] = vv;
+      a.xyz[o3 + c] = p3[c];
+      a.m[o3 + c] = mm;
+      a.v[o3 + c] = vv;
+      if (a.rep_grad_out) a.rep_grad_out[o3 + c] = r3[c];
     }
-    xo[3 * kCsMaxK + p] = lsum;                                 // pair-loss sum of point p
+    ls[p] = lsum;                                               // pair-loss sum of point p
   }
-  __syncthreads();
-  // ---- all global writes, coalesced
-  {
-    const float* xo = reinterpret_cast<const float*>(&S.cell[0]);
-    for (int e = i; e < 3 * K; e += kCsThreads) {
-      a.xyz[cloud3 + e] = xo[e];
-      a.m[cloud3 + e] = S.gmv[1][e];
-      a.v[cloud3 + e] = S.gmv[2][e];
-      if (a.rep_grad_out) a.rep_grad_out[cloud3 + e] = S.gmv[0][e];
-    }
-    if (live) {
-      const uint4 r = *reinterpret_cast<const uint4*>(&S.nbr[i][0]);
-      int4* pv = reinterpret_cast<int4*>(a.nbr + ((size_t)b * K + i) * kCsKK);
-      pv[0] = make_int4((int)(r.x & 0xffffu), (int)(r.x >> 16), (int)(r.y & 0xffffu), (int)(r.y >> 16));
-      pv[1] = make_int4((int)(r.z & 0xffffu), (int)(r.z >> 16), (int)(r.w & 0xffffu), (int)(r.w >> 16));
-    }
-    // ---- sum of the pair losses in POINT order (the thread <-> point map above depends on atomic arrival order)
-    if (a.loss_part) {
-      float l = live ? xo[3 * kCsMaxK + i] : 0.0f;
+  // ---- sum of the pair losses in POINT order (the thread <-> point map depends on atomic arrival order), CTA 1's
+  //      part crosses to CTA 0
+  if (a.loss_part) {
+    __syncthreads();
+    float l = ls[i];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
-      if (lane == 0) S.red[6][warp] = l;
-      __syncthreads();
-      if (i == 0) {
-        float t = 0.0f;
-        for (int w = 0; w < kCsThreads / 32; ++w) t += S.red[6][w];
-        a.loss_part[b] = t;
-      }
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (lane == 0) S.red[6][warp] = l;
+    __syncthreads();
+    float t = 0.0f;
+    if (i == 0) {
+      for (int w = 0; w < kCsThreads / 32; ++w) t += S.red[6][w];
+      if (half == 1) P.peer_loss = t;
     }
+    cluster.sync();
+    if (i == 0 && half == 0) a.loss_part[b] = t + S.peer_loss;
   }
 }
 

@@ -528,7 +528,7 @@ int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int
     {
       ProfileScope ps(1, st);
       IFD_CUDA_TRY(cudaFuncSetAttribute(cloud_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CloudStepSmem)));
-      cloud_step_kernel<<<B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
+      cloud_step_kernel<<<2 * B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
       IFD_LAUNCH_CHECK("cloud_step_kernel");
     }
     if (stat) {
@@ -718,7 +718,7 @@ extern "C" int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const
   c.sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
   c.sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
   IFD_CUDA_TRY(cudaFuncSetAttribute(cloud_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CloudStepSmem)));
-  cloud_step_kernel<<<B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
+  cloud_step_kernel<<<2 * B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
   IFD_LAUNCH_CHECK("cloud_step_kernel");
   return IFD_OK;
 }
