@@ -48,6 +48,55 @@ __global__ void convonet_pack_umma_kernel(const float* __restrict__ Wb, int n_la
   b[1024 + umma::img_offset(i, o, 32) / 4] = lo;
 }
 
+// Bilinear geometry of one point, packed for warp shuffles: the lane that OWNS a point (slot = thread) computes the
+// three axes once (normalize_coordinate's division and clamps, grid_sample's unnormalise / clip / floor), and the
+// 8-lane group that gathers the point's texels receives 7 words by shuffle instead of redoing that work 8 times.
+struct V3Geom {
+  int pk[3];     // i0 | has1 << 16 | grad_on << 17   per axis
+  float f[3];    // weight of the far corner
+  int b;         // cloud of the point
+};
+__device__ __forceinline__ V3Geom v3_geom(float px, float py, float pz, int R, float denom, int b) {
+  V3Geom g;
+  const float p[3] = {px, py, pz};
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    const Axis a = axis_setup(plane_coord(p[ax], denom), R, denom);
+    g.pk[ax] = a.i0 | (a.has1 << 16) | ((a.dscale != 0.0f ? 1 : 0) << 17);
+    g.f[ax] = a.f;
+  }
+  g.b = b;
+  return g;
+}
+// the tap offsets / weights of tapset() (decode_v2.cuh) rebuilt from the packed axes -- same expressions, same bits
+struct V3Taps {
+  int off[3][4];
+  float w[3][4];
+  float f[3], near_w[3];
+  int has1[3];
+};
+__device__ __forceinline__ void v3_taps(const int (&pk)[3], const float (&f)[3], int R, V3Taps& t) {
+  int i0[3];
+#pragma unroll
+  for (int ax = 0; ax < 3; ++ax) {
+    i0[ax] = pk[ax] & 0xffff;
+    t.has1[ax] = (pk[ax] >> 16) & 1;
+    t.f[ax] = f[ax];
+    t.near_w[ax] = sub_rn(1.0f, f[ax]);
+  }
+#pragma unroll
+  for (int pl = 0; pl < 3; ++pl) {
+    const int aw = plane_axis_w(pl), ah = plane_axis_h(pl);
+    const int w0 = i0[aw], w1 = t.has1[aw] ? i0[aw] + 1 : i0[aw];
+    const int h0 = i0[ah], h1 = t.has1[ah] ? i0[ah] + 1 : i0[ah];
+    t.off[pl][0] = (h0 * R + w0) * 32; t.off[pl][1] = (h0 * R + w1) * 32;
+    t.off[pl][2] = (h1 * R + w0) * 32; t.off[pl][3] = (h1 * R + w1) * 32;
+    const float fw = t.has1[aw] ? t.f[aw] : 0.0f, fh = t.has1[ah] ? t.f[ah] : 0.0f;
+    t.w[pl][0] = t.near_w[ah] * t.near_w[aw]; t.w[pl][1] = t.near_w[ah] * fw;
+    t.w[pl][2] = fh * t.near_w[aw];           t.w[pl][3] = fh * fw;
+  }
+}
+
 struct DecodeV3Args {
   const float* planes;
   const float* W;        // plain blob (biases, fc_p, fc_out)
@@ -74,9 +123,10 @@ __device__ __forceinline__ void v3_layer(const float (&x)[32], uint32_t (&d)[32]
 #pragma unroll
   for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi_fast(x[k]);
   umma::tmem_st32(lane_taddr + 32, d);
-  umma::tmem_wait_st();
+  // lo = x - hi exactly (13 significant bits at most); the tensor core reads its top 11 -- no explicit rounding.
+  // Error per product <= 2^-21 |a||b| for this term (2^-22 with a rounded lo), same order as the dropped lo.lo term.
 #pragma unroll
-  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_lo_fast(x[k], d[k]);
+  for (int k = 0; k < 32; ++k) d[k] = __float_as_uint(x[k] - __uint_as_float(d[k]));
   umma::tmem_st32(lane_taddr + 64, d);
   umma::tmem_wait_st();
   umma::fence_before_sync();
@@ -139,14 +189,26 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
     else v = c == 0 ? Wb[L::out_b(a.n_blocks)] : 0.0f;
     vec[i] = v;
   }
-  // ---------------- forward gather: warp w serves tile slots 32w .. 32w+31 (its own threads' points)
+  // ---------------- own point (slot = thread) and its geometry
+  const int slot = threadIdx.x;
+  const int pi = min(tile0 + slot, a.n - 1);
+  const float p0 = a.xyz[(size_t)pi * 3 + 0], p1 = a.xyz[(size_t)pi * 3 + 1], p2 = a.xyz[(size_t)pi * 3 + 2];
+  const V3Geom geo = v3_geom(p0, p1, p2, a.R, a.denom, pi / a.K);
+  // ---------------- forward gather: warp w serves tile slots 32w .. 32w+31 (its own threads' points), four points
+  //                  per pass, 8 lanes x float4 = one 128-byte texel
+#pragma unroll 2
   for (int it = 0; it < 8; ++it) {
-    const int slot = warp * 32 + it * 4 + grp;
-    const int pi = min(tile0 + slot, a.n - 1);
-    const int b = pi / a.K;
-    const float px = a.xyz[(size_t)pi * 3 + 0], py = a.xyz[(size_t)pi * 3 + 1], pz = a.xyz[(size_t)pi * 3 + 2];
-    TapSet ts;
-    tapset(px, py, pz, a.R, a.denom, ts);
+    const int src = it * 4 + grp, gslot = warp * 32 + src;
+    int pk[3];
+    float fr[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      pk[ax] = __shfl_sync(0xffffffffu, geo.pk[ax], src);
+      fr[ax] = __shfl_sync(0xffffffffu, geo.f[ax], src);
+    }
+    const int b = __shfl_sync(0xffffffffu, geo.b, src);
+    V3Taps ts;
+    v3_taps(pk, fr, a.R, ts);
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
@@ -162,10 +224,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
       }
       c.x += s.x; c.y += s.y; c.z += s.z; c.w += s.w;
     }
-    feat[(j4 * 4 + 0) * kV3Stride + slot] = c.x;
-    feat[(j4 * 4 + 1) * kV3Stride + slot] = c.y;
-    feat[(j4 * 4 + 2) * kV3Stride + slot] = c.z;
-    feat[(j4 * 4 + 3) * kV3Stride + slot] = c.w;
+    feat[(j4 * 4 + 0) * kV3Stride + gslot] = c.x;
+    feat[(j4 * 4 + 1) * kV3Stride + gslot] = c.y;
+    feat[(j4 * 4 + 2) * kV3Stride + gslot] = c.z;
+    feat[(j4 * 4 + 3) * kV3Stride + gslot] = c.w;
   }
   umma::fence_proxy_async();          // weight images were written through the generic proxy
   umma::fence_before_sync();
@@ -180,9 +242,6 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
   const bool leader = (threadIdx.x & 127) == 0;
 
   // ---------------- MLP forward: thread = point
-  const int slot = threadIdx.x;
-  const int pi = min(tile0 + slot, a.n - 1);
-  const float p0 = a.xyz[(size_t)pi * 3 + 0], p1 = a.xyz[(size_t)pi * 3 + 1], p2 = a.xyz[(size_t)pi * 3 + 2];
   float net[32], x[32];
   uint32_t d[32];
   uint32_t mask_a[kMaxBlocks], mask_h[kMaxBlocks];
@@ -306,15 +365,24 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
   }
   __syncwarp();
 
-  // ---------------- backward gather (warp-local: slots 32w .. 32w+31)
+  // ---------------- backward gather (warp-local: slots 32w .. 32w+31); geometry recomputed once per point (its
+  //                  registers were handed to the MLP)
+  const V3Geom geo2 = v3_geom(p0, p1, p2, a.R, a.denom, pi / a.K);
+  const float dsc = ((float)(a.R - 1) * 0.5f) * 2.0f / a.denom;        // Axis::dscale of a live, unclipped axis
+#pragma unroll 2
   for (int it = 0; it < 8; ++it) {
-    const int gslot = warp * 32 + it * 4 + grp;
+    const int src = it * 4 + grp, gslot = warp * 32 + src;
     const int pi_raw = tile0 + gslot;
-    const int gpi = min(pi_raw, a.n - 1);
-    const int b = gpi / a.K;
-    const float px = a.xyz[(size_t)gpi * 3 + 0], py = a.xyz[(size_t)gpi * 3 + 1], pz = a.xyz[(size_t)gpi * 3 + 2];
-    TapSet ts;
-    tapset(px, py, pz, a.R, a.denom, ts);
+    int pk[3];
+    float fr[3];
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      pk[ax] = __shfl_sync(0xffffffffu, geo2.pk[ax], src);
+      fr[ax] = __shfl_sync(0xffffffffu, geo2.f[ax], src);
+    }
+    const int b = __shfl_sync(0xffffffffu, geo2.b, src);
+    V3Taps ts;
+    v3_taps(pk, fr, a.R, ts);
     const float4 gc = make_float4(feat[(j4 * 4 + 0) * kV3Stride + gslot], feat[(j4 * 4 + 1) * kV3Stride + gslot],
                                   feat[(j4 * 4 + 2) * kV3Stride + gslot], feat[(j4 * 4 + 3) * kV3Stride + gslot]);
     float gi[3] = {0.f, 0.f, 0.f};
@@ -331,19 +399,19 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         qv[t4] = s;
       }
-      const Axis& aw = ts.ax[plane_axis_w(pl)];
-      const Axis& ah = ts.ax[plane_axis_h(pl)];
-      const float q_ne = aw.has1 ? qv[1] : 0.0f;
-      const float q_sw = ah.has1 ? qv[2] : 0.0f;
-      const float q_se = (aw.has1 && ah.has1) ? qv[3] : 0.0f;
-      gi[plane_axis_w(pl)] += (q_ne - qv[0]) * (1.0f - ah.f) + (q_se - q_sw) * ah.f;
-      gi[plane_axis_h(pl)] += (q_sw - qv[0]) * (1.0f - aw.f) + (q_se - q_ne) * aw.f;
+      const int aw = plane_axis_w(pl), ah = plane_axis_h(pl);
+      const float q_ne = ts.has1[aw] ? qv[1] : 0.0f;
+      const float q_sw = ts.has1[ah] ? qv[2] : 0.0f;
+      const float q_se = (ts.has1[aw] && ts.has1[ah]) ? qv[3] : 0.0f;
+      gi[aw] += (q_ne - qv[0]) * (1.0f - ts.f[ah]) + (q_se - q_sw) * ts.f[ah];
+      gi[ah] += (q_sw - qv[0]) * (1.0f - ts.f[aw]) + (q_se - q_ne) * ts.f[aw];
     }
     if (j4 == 0 && pi_raw < a.n) {
       const float4 gp = gpart[gslot];
-      a.grad_out[(size_t)gpi * 3 + 0] = gp.x + gi[0] * ts.ax[0].dscale;
-      a.grad_out[(size_t)gpi * 3 + 1] = gp.y + gi[1] * ts.ax[1].dscale;
-      a.grad_out[(size_t)gpi * 3 + 2] = gp.z + gi[2] * ts.ax[2].dscale;
+      const size_t o = (size_t)pi_raw * 3;
+      a.grad_out[o + 0] = gp.x + gi[0] * (((pk[0] >> 17) & 1) ? dsc : 0.0f);
+      a.grad_out[o + 1] = gp.y + gi[1] * (((pk[1] >> 17) & 1) ? dsc : 0.0f);
+      a.grad_out[o + 2] = gp.z + gi[2] * (((pk[2] >> 17) & 1) ? dsc : 0.0f);
     }
   }
   umma::fence_before_sync();
