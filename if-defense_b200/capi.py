@@ -51,6 +51,8 @@ SIGNATURES = {
     "ifd_opt_tail_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, ctypes.POINTER(OptParams), _c_int, _vp, _vp, _vp]),
     "ifd_convonet_opt_host": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        ctypes.POINTER(OptParams), _vp]),
+    "ifd_convonet_opt_host_batches": (_c_int, [_c_int, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                               ctypes.POINTER(OptParams)]),
     "ifd_onet_decoder_nfloats": (_c_sz, []),
     "ifd_onet_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "ifd_onet_prepare": (_c_int, [_vp, _vp, _c_int, _c_int, _vp, _c_sz, _vp]),

@@ -148,3 +148,31 @@ class Restorer:
         capi.check(capi.lib().ifd_convonet_opt_host(pl.ctypes.data, self.decoder.blob_host.ctypes.data, x.ctypes.data, B, K, R,
                                                     C, H, nb, ctypes.byref(P), None), "ifd_convonet_opt_host")
         return x
+
+    def optimize_points_host_many(self, opt_points_list, planes_nchw_list, rep_weight=500., iterations=200, B_ref=None):
+        """The batch loop of defend_point_cloud (opt_defense.py:272-312) through one pipelined C call
+        (ifd_convonet_opt_host_batches): lists of HOST arrays in ([B,K,3] init points, [3,B,C,R,R] planes per batch,
+        all batches the same shape; pinned memory -- e.g. torch.Tensor.pin_memory().numpy() -- makes the copies
+        overlap the previous batch's loop), list of restored [B,K,3] arrays out."""
+        capi.require_gpu()
+        if len(opt_points_list) != len(planes_nchw_list):
+            raise RuntimeError("need one planes array per batch")
+        if not opt_points_list:
+            return []
+        # in/out point buffers in pinned memory (torch's caching host allocator): a D2H into pageable memory would
+        # block the host inside the batch loop and serialise the pipeline
+        keep = [torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).clone().pin_memory() for p in opt_points_list]
+        outs = [t.numpy() for t in keep]
+        pls = [np.ascontiguousarray(p, dtype=np.float32) for p in planes_nchw_list]
+        B, K, _ = outs[0].shape
+        _, _, C, R, _ = pls[0].shape
+        if any(o.shape != (B, K, 3) for o in outs) or any(p.shape != (3, B, C, R, R) for p in pls):
+            raise RuntimeError("all batches of one call must have the same shape")
+        _, H, nb = self.decoder.dims
+        P = self.params(B if B_ref is None else B_ref, rep_weight, iterations)
+        n = len(outs)
+        pp = (ctypes.c_void_p * n)(*[p.ctypes.data for p in pls])
+        xp = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outs])
+        capi.check(capi.lib().ifd_convonet_opt_host_batches(n, pp, self.decoder.blob_host.ctypes.data, xp, B, K, R, C, H, nb,
+                                                            ctypes.byref(P)), "ifd_convonet_opt_host_batches")
+        return outs

@@ -104,7 +104,9 @@ extern "C" int ifd_profile_read(double* ms_out, long long* launches_out) {
   return IFD_PROFILE_KINDS;
 }
 
+namespace ifd { void release_pipe(); }
 extern "C" void ifd_release_cache(void) {
+  release_pipe();
   if (g_cache.dev) cudaFree(g_cache.dev);
   if (g_cache.pinned) cudaFreeHost(g_cache.pinned);
   if (g_cache.stream) cudaStreamDestroy(g_cache.stream);
@@ -147,3 +149,103 @@ extern "C" int ifd_convonet_opt_host(const float* planes_nchw_host, const float*
   IFD_CUDA_TRY(cudaStreamSynchronize(st));
   return IFD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Many batches, pipelined: what defend_point_cloud (ConvONet/opt_defense.py:272-312) does batch after batch, with the
+// host<->device copies of batch j+1 / j-1 overlapped with the loop of batch j (three streams, two buffer slots).
+// Every batch still pays its own H2D of planes + init points and D2H of the restored cloud.
+namespace ifd {
+struct PipeCache {
+  void* dev = nullptr;
+  size_t bytes = 0;
+  cudaStream_t h2d = nullptr, run = nullptr, d2h = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+};
+static thread_local PipeCache g_pipe;
+static int ensure_pipe(size_t dev_bytes) {
+  if (!g_pipe.h2d) {
+    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.h2d, cudaStreamNonBlocking));
+    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run, cudaStreamNonBlocking));
+    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.d2h, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+      IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.ready[s], cudaEventDisableTiming));
+      IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.done[s], cudaEventDisableTiming));
+      IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.freed[s], cudaEventDisableTiming));
+    }
+  }
+  if (g_pipe.bytes < dev_bytes) {
+    if (g_pipe.dev) cudaFree(g_pipe.dev);
+    g_pipe.dev = nullptr;
+    g_pipe.bytes = 0;
+    IFD_CUDA_TRY(cudaMalloc(&g_pipe.dev, dev_bytes));
+    g_pipe.bytes = dev_bytes;
+  }
+  return IFD_OK;
+}
+}  // namespace ifd
+
+extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* planes_nchw_host, const float* dec_weights_host,
+                                             float* const* xyz_host, int B, int K, int R, int C, int H, int n_blocks,
+                                             const ifd_opt_params* P) {
+  IFD_REQUIRE(n_batches >= 0 && planes_nchw_host && dec_weights_host && xyz_host && P && B > 0 && K > 0 && R > 0 && C > 0,
+              "ifd_convonet_opt_host_batches: bad arguments");
+  if (n_batches == 0) return IFD_OK;
+  for (int j = 0; j < n_batches; ++j)
+    IFD_REQUIRE(planes_nchw_host[j] && xyz_host[j], "ifd_convonet_opt_host_batches: null batch pointer");
+  const size_t nw = ifd_convonet_decoder_nfloats(C, H, n_blocks);
+  if (nw == 0) return fail(IFD_ERR_UNSUPPORTED, "ifd_convonet_opt_host_batches: unsupported decoder shape");
+  const size_t plane_bytes = align_up((size_t)3 * B * C * R * R * sizeof(float), 256);
+  const size_t xyz_bytes = (size_t)B * K * 3 * sizeof(float);
+  const size_t xyz_al = align_up(xyz_bytes, 256);
+  const size_t w_bytes = align_up(nw * sizeof(float), 256);
+  const size_t ws_bytes = align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
+  const size_t total = w_bytes + ws_bytes + 2 * (2 * plane_bytes + xyz_al);
+  int rc = ensure_pipe(total);
+  if (rc) return rc;
+  char* base = (char*)g_pipe.dev;
+  float* d_w = (float*)base; base += w_bytes;
+  void* d_ws = base; base += ws_bytes;
+  float *d_nchw[2], *d_cl[2], *d_xyz[2];
+  for (int s = 0; s < 2; ++s) {
+    d_nchw[s] = (float*)base; base += plane_bytes;
+    d_cl[s] = (float*)base; base += plane_bytes;
+    d_xyz[s] = (float*)base; base += xyz_al;
+  }
+  IFD_CUDA_TRY(cudaMemcpyAsync(d_w, dec_weights_host, nw * sizeof(float), cudaMemcpyHostToDevice, g_pipe.h2d));
+  for (int j = 0; j < n_batches; ++j) {
+    const int s = j & 1;
+    if (j >= 2) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.freed[s], 0));       // slot s drained (loop + D2H of j-2)
+    IFD_CUDA_TRY(cudaMemcpyAsync(d_nchw[s], planes_nchw_host[j], (size_t)3 * B * C * R * R * sizeof(float), cudaMemcpyHostToDevice,
+                                 g_pipe.h2d));
+    IFD_CUDA_TRY(cudaMemcpyAsync(d_xyz[s], xyz_host[j], xyz_bytes, cudaMemcpyHostToDevice, g_pipe.h2d));
+    if ((rc = ifd_planes_nchw_to_cl(d_nchw[s], d_cl[s], 3 * B, C, R, g_pipe.h2d))) return rc;
+    IFD_CUDA_TRY(cudaEventRecord(g_pipe.ready[s], g_pipe.h2d));
+    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.run, g_pipe.ready[s], 0));
+    if ((rc = ifd_convonet_opt(d_cl[s], d_w, d_xyz[s], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr, d_ws, ws_bytes,
+                               g_pipe.run)))
+      return rc;
+    IFD_CUDA_TRY(cudaEventRecord(g_pipe.done[s], g_pipe.run));
+    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.done[s], 0));
+    IFD_CUDA_TRY(cudaMemcpyAsync(xyz_host[j], d_xyz[s], xyz_bytes, cudaMemcpyDeviceToHost, g_pipe.d2h));
+    IFD_CUDA_TRY(cudaEventRecord(g_pipe.freed[s], g_pipe.d2h));
+  }
+  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.d2h));
+  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.run));
+  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.h2d));
+  return IFD_OK;
+}
+
+namespace ifd {
+void release_pipe() {
+  if (g_pipe.dev) cudaFree(g_pipe.dev);
+  for (int s = 0; s < 2; ++s) {
+    if (g_pipe.ready[s]) cudaEventDestroy(g_pipe.ready[s]);
+    if (g_pipe.done[s]) cudaEventDestroy(g_pipe.done[s]);
+    if (g_pipe.freed[s]) cudaEventDestroy(g_pipe.freed[s]);
+  }
+  if (g_pipe.h2d) cudaStreamDestroy(g_pipe.h2d);
+  if (g_pipe.run) cudaStreamDestroy(g_pipe.run);
+  if (g_pipe.d2h) cudaStreamDestroy(g_pipe.d2h);
+  g_pipe = PipeCache();
+}
+}  // namespace ifd

@@ -70,12 +70,15 @@ __device__ __forceinline__ V3Geom v3_geom(float px, float py, float pz, int R, f
 }
 // the tap offsets / weights of tapset() (decode_v2.cuh) rebuilt from the packed axes -- same expressions, same bits
 struct V3Taps {
-  int off[3][4];
+  uint32_t off[3][4];
   float w[3][4];
   float f[3], near_w[3];
   int has1[3];
 };
-__device__ __forceinline__ void v3_taps(const int (&pk)[3], const float (&f)[3], int R, V3Taps& t) {
+// off[pl][t] is a 32-bit index in float4 units into the whole [3][B][R][R][32] plane array (cloud, plane, texel and the
+// lane's 4-channel slice folded in), so every tap load is one base + 16 * index address computation.
+__device__ __forceinline__ void v3_taps(const int (&pk)[3], const float (&f)[3], int R, uint32_t cloud4, uint32_t plane4,
+                                        V3Taps& t) {
   int i0[3];
 #pragma unroll
   for (int ax = 0; ax < 3; ++ax) {
@@ -89,8 +92,9 @@ __device__ __forceinline__ void v3_taps(const int (&pk)[3], const float (&f)[3],
     const int aw = plane_axis_w(pl), ah = plane_axis_h(pl);
     const int w0 = i0[aw], w1 = t.has1[aw] ? i0[aw] + 1 : i0[aw];
     const int h0 = i0[ah], h1 = t.has1[ah] ? i0[ah] + 1 : i0[ah];
-    t.off[pl][0] = (h0 * R + w0) * 32; t.off[pl][1] = (h0 * R + w1) * 32;
-    t.off[pl][2] = (h1 * R + w0) * 32; t.off[pl][3] = (h1 * R + w1) * 32;
+    const uint32_t o = cloud4 + (uint32_t)pl * plane4;
+    t.off[pl][0] = o + (uint32_t)(h0 * R + w0) * 8u; t.off[pl][1] = o + (uint32_t)(h0 * R + w1) * 8u;
+    t.off[pl][2] = o + (uint32_t)(h1 * R + w0) * 8u; t.off[pl][3] = o + (uint32_t)(h1 * R + w1) * 8u;
     const float fw = t.has1[aw] ? t.f[aw] : 0.0f, fh = t.has1[ah] ? t.f[ah] : 0.0f;
     t.w[pl][0] = t.near_w[ah] * t.near_w[aw]; t.w[pl][1] = t.near_w[ah] * fw;
     t.w[pl][2] = fh * t.near_w[aw];           t.w[pl][3] = fh * fw;
@@ -168,7 +172,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int group = warp >> 2;                                              // tile of this thread
   const int grp = lane >> 3, j4 = lane & 7;
-  const size_t plane_sz = (size_t)a.R * a.R * 32;
+  const float4* __restrict__ planes4 = reinterpret_cast<const float4*>(a.planes);
+  const uint32_t plane4 = (uint32_t)(a.R * a.R * 8);              // one plane of one cloud, in float4 units
 
   if (warp == 0) umma::tmem_alloc(tmem_slot, kV3TmemCols);
   if (threadIdx.x == 32) {
@@ -208,15 +213,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
     }
     const int b = __shfl_sync(0xffffffffu, geo.b, src);
     V3Taps ts;
-    v3_taps(pk, fr, a.R, ts);
+    v3_taps(pk, fr, a.R, (uint32_t)b * plane4 + (uint32_t)j4, (uint32_t)a.B * plane4, ts);
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      const float* base = a.planes + ((size_t)pl * a.B + b) * plane_sz + j4 * 4;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + ts.off[pl][t]));
+        const float4 v = __ldg(planes4 + ts.off[pl][t]);
         s.x = fmaf(v.x, ts.w[pl][t], s.x);
         s.y = fmaf(v.y, ts.w[pl][t], s.y);
         s.z = fmaf(v.z, ts.w[pl][t], s.z);
@@ -382,22 +386,19 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
     }
     const int b = __shfl_sync(0xffffffffu, geo2.b, src);
     V3Taps ts;
-    v3_taps(pk, fr, a.R, ts);
+    v3_taps(pk, fr, a.R, (uint32_t)b * plane4 + (uint32_t)j4, (uint32_t)a.B * plane4, ts);
     const float4 gc = make_float4(feat[(j4 * 4 + 0) * kV3Stride + gslot], feat[(j4 * 4 + 1) * kV3Stride + gslot],
                                   feat[(j4 * 4 + 2) * kV3Stride + gslot], feat[(j4 * 4 + 3) * kV3Stride + gslot]);
+    // d c / d (ix, iy) is linear in the four texel . g_c dot products, so each lane combines its 4-channel partial
+    // dots into partial axis gradients first and only THREE values cross the 8 lanes (instead of twelve)
     float gi[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      const float* base = a.planes + ((size_t)pl * a.B + b) * plane_sz + j4 * 4;
       float qv[4];
 #pragma unroll
       for (int t4 = 0; t4 < 4; ++t4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(base + ts.off[pl][t4]));
-        float s = (v.x * gc.x + v.y * gc.y) + (v.z * gc.z + v.w * gc.w);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        qv[t4] = s;
+        const float4 v = __ldg(planes4 + ts.off[pl][t4]);
+        qv[t4] = (v.x * gc.x + v.y * gc.y) + (v.z * gc.z + v.w * gc.w);
       }
       const int aw = plane_axis_w(pl), ah = plane_axis_h(pl);
       const float q_ne = ts.has1[aw] ? qv[1] : 0.0f;
@@ -405,6 +406,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
       const float q_se = (ts.has1[aw] && ts.has1[ah]) ? qv[3] : 0.0f;
       gi[aw] += (q_ne - qv[0]) * (1.0f - ts.f[ah]) + (q_se - q_sw) * ts.f[ah];
       gi[ah] += (q_sw - qv[0]) * (1.0f - ts.f[aw]) + (q_se - q_ne) * ts.f[aw];
+    }
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      gi[ax] += __shfl_xor_sync(0xffffffffu, gi[ax], 1);
+      gi[ax] += __shfl_xor_sync(0xffffffffu, gi[ax], 2);
+      gi[ax] += __shfl_xor_sync(0xffffffffu, gi[ax], 4);
     }
     if (j4 == 0 && pi_raw < a.n) {
       const float4 gp = gpart[gslot];

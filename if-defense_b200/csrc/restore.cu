@@ -418,6 +418,7 @@ static int launch_decode_v3(const DecodeArgs& a, const float* wimg, cudaStream_t
   v.denom = a.denom; v.target = a.target; v.ginv = a.ginv;
   const size_t smem = DecodeV3Smem::bytes(a.n_blocks);
   if (smem > 227 * 1024) return fail(IFD_ERR_UNSUPPORTED, "decode v3 supports n_blocks <= 6");
+  if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v3: plane array too large for 32-bit texel indices");
   IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   convonet_decode_v3_kernel<<<(v.n + kV3Pts - 1) / kV3Pts, kV3Threads, smem, st>>>(v);
   IFD_LAUNCH_CHECK("convonet_decode_v3_kernel");

@@ -13,7 +13,7 @@ import os
 import numpy as np
 import torch
 
-from . import convonet
+from . import convonet, shard
 from .defense import SORDefense
 
 
@@ -31,6 +31,8 @@ class Args:
     sor_alpha = 1.1
     threshold = 0.2       # cfg['test']['threshold']
     input_npoint = 600    # cfg['data']['pointcloud_n'] (300 for ONet)
+    encoder_chunk = 1     # sharded path only: clouds per encoder call.  1 makes the (torch/cuDNN) encoder see the same
+                          # shapes however the job is split, so the result does not depend on the number of ranks
 
     def __init__(self, **over):
         for k, v in over.items():
@@ -89,10 +91,8 @@ class Defender:
             out += [o.detach().cpu().numpy().astype(np.float32) for o in sor(x)]
         return out
 
-    def defend_point_cloud(self, pc, rng=None, gen=None, printing=False, clouds_slice=None):
-        """opt_defense.py:255-314.  pc: [N,K,3] array.  Returns float32 [N,sample_npoint,3].
-        clouds_slice=(lo, hi): restore only clouds lo..hi-1 of every reference batch position range (used by
-        the multi-GPU sharder; B_ref stays the reference batch size so results do not depend on the split)."""
+    def defend_point_cloud(self, pc, rng=None, gen=None, printing=False):
+        """opt_defense.py:255-314.  pc: [N,K,3] array.  Returns float32 [N,sample_npoint,3]."""
         a = self.args
         pcs = self.sor_process(pc) if a.sor else [np.asarray(p, dtype=np.float32) for p in pc]
         out = np.zeros((len(pcs), a.sample_npoint, 3), dtype=np.float32)
@@ -106,6 +106,35 @@ class Defender:
             out[lo:lo + a.batch_size] = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight,
                                                                       iterations=a.iterations, printing=printing)
         return out
+
+    def restore_slice(self, pc, lo, hi, B_ref, seed):
+        """Clouds lo..hi-1 of a reference batch of B_ref clouds, every random draw taken from a per-cloud stream
+        (seed, cloud index) so that the result does not depend on how the job is cut into slices."""
+        a = self.args
+        raw = np.asarray(pc[lo:hi])[..., :3]
+        pcs = self.sor_process(raw) if a.sor else [np.asarray(p, dtype=np.float32) for p in raw]
+        proc, pts = [], []
+        for j, p in enumerate(pcs):
+            i = lo + j
+            allp, sel = preprocess_pc(p, num_points=a.input_npoint, padding_scale=a.padding_scale,
+                                      rng=np.random.default_rng([int(seed), i]))
+            proc.append(sel)
+            g = torch.Generator().manual_seed((int(seed) * 1000003 + i) % (2 ** 63 - 1))
+            pts.append(init_points([allp], a.sample_npoint, a.init_sigma, a.padding_scale, g)[0])
+        sel = torch.from_numpy(np.stack(proc)).float().to(self.device)
+        step = a.encoder_chunk or len(proc)
+        with torch.no_grad():
+            parts = [self.model.encode_inputs(sel[i:i + step]) for i in range(0, len(proc), step)]
+        c = {k: torch.cat([q[k] for q in parts]) for k in parts[0]}
+        return self.restorer.optimize_points(torch.stack(pts), None, c, rep_weight=a.rep_weight, iterations=a.iterations,
+                                             B_ref=B_ref)
+
+    def defend_point_cloud_sharded(self, pc, seed=0, rank=None, world=None):
+        """defend_point_cloud across the ranks of torch.distributed (one process per GPU): every reference batch is
+        cut into `world` contiguous slices (shard.plan), each rank restores its slices with the batch's B_ref, one
+        all_gather returns all N restored clouds in input order on every rank."""
+        return shard.restore_sharded(lambda lo, hi, n: self.restore_slice(pc, lo, hi, n, seed), len(pc), self.args.batch_size,
+                                     rank=rank, world=world, device=self.device)
 
 
 def get_save_name(path, tag="convonet_opt-", folder="ConvONet-Opt"):

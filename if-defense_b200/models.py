@@ -130,6 +130,22 @@ class LocalPoolPointnet(nn.Module):
         return out.permute(0, 2, 1)
 
     def forward(self, p):
+        """fp32 throughout (the reference runs fp32: TF32 convolutions -- torch's CUDA default -- would move the planes
+        by ~1e-3 relative) and with torch's deterministic scatter_add, so the planes are reproducible run to run."""
+        if not p.is_cuda:
+            return self._forward(p)
+        tf32_c, tf32_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        det, warn = torch.are_deterministic_algorithms_enabled(), torch.is_deterministic_algorithms_warn_only_enabled()
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.use_deterministic_algorithms(True, warn_only=True)
+        try:
+            return self._forward(p)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_c, tf32_m
+            torch.use_deterministic_algorithms(det, warn_only=warn)
+
+    def _forward(self, p):
         index = {pl: coordinate2index(normalize_coordinate(p, self.padding, pl), self.reso_plane) for pl in self.plane_type}
         net = self.blocks[0](self.fc_pos(p))
         for block in self.blocks[1:]:

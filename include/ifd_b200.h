@@ -191,6 +191,14 @@ int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const float* g_o
 int ifd_convonet_opt_host(const float* planes_nchw_host, const float* dec_weights_host, float* xyz_host,
                           int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* params,
                           double* stats_out_host);
+/* The same for a sequence of batches -- the loop of defend_point_cloud over batches (ConvONet/opt_defense.py:272-312):
+ * planes_nchw_host[j] / xyz_host[j] are the HOST buffers of batch j (all batches B clouds; pinned memory makes the
+ * copies asynchronous).  Batch j+1 is uploaded and converted, and batch j-1 is downloaded, while batch j runs
+ * (three streams, two device buffer slots); every batch still pays its own H2D and D2H.  Synchronises before
+ * returning.  Results are bit-identical to n_batches calls of ifd_convonet_opt_host. */
+int ifd_convonet_opt_host_batches(int n_batches, const float* const* planes_nchw_host, const float* dec_weights_host,
+                                  float* const* xyz_host, int B, int K, int R, int C, int H, int n_blocks,
+                                  const ifd_opt_params* params);
 void ifd_release_cache(void);
 
 /* ------------------------------------------------------------------------------------------------

@@ -223,6 +223,8 @@ def test_reference_signature_and_host_seam(conv, dec, conv_planes):
     assert rest.last_stats.shape == (1, 4)
     host = rest.optimize_points_host(conv["p0"], conv["planes_nchw"], rep_weight=500., iterations=19)
     assert np.array_equal(host, out)
+    many = rest.optimize_points_host_many([conv["p0"]] * 3, [conv["planes_nchw"]] * 3, rep_weight=500., iterations=19)
+    assert len(many) == 3 and all(np.array_equal(m, host) for m in many)      # pipelined batch loop: same bits
     out0 = rest.optimize_points(dev(conv["p0"]), None, c, rep_weight=0., iterations=19)     # rep_weight == 0 branch
     assert np.isfinite(out0).all() and not np.array_equal(out0, out)
 
