@@ -35,6 +35,22 @@ ALG_BYTES_PER_PT_STEP = 1560                   # 3 planes x 4 te
 ALG_FLOP_PER_PT_STEP = 61952                   # decoder fwd + dgrad
 
 
+def ncu_traffic(kernel="convonet_decode_v3_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full summary
+    (profiles/, cold-cache replay), or None."""
+    try:
+        txt = open(os.path.join(ROOT, "profiles", "r01_v4_ncu_full_summary.txt")).read()
+        sec = txt.split("==== " + kernel, 1)[1].split("====", 1)[0]
+        unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = sec.split(key, 1)[1].split()[:2]
+            tot += float(v) * unit[u]
+        return tot
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -219,13 +235,16 @@ def main():
         achieved = alg_bytes / (dec_ms * 1e-3) / 1e9
         total_k = sum(kms)
         roof = {"bound": "hbm", "kernel": "convonet_decode_v3_kernel (plane gather + tcgen05 ResNet-MLP fwd/dgrad)", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "traffic_source": "profiles/r01_v4_ncu_full_summary.txt (ncu --set full, bytes per launch, cold-cache replay)",
                 "ms_per_launch": dec_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp32_tflops_achieved": ALG_FLOP_PER_PT_STEP * B * K / (dec_ms * 1e-3) / 1e12,
-                "kernel_time_share": {"decode": kms[0] / total_k, "knn_repulsion": kms[1] / total_k, "adam": kms[2] / total_k},
-                "note": "planes (100 MB) are L2-resident after the first Adam step, so DRAM traffic is far below the algorithmic "
-                        "gather bytes; the kernel is bound by epilogue issue slots and tcgen05/TMEM round-trip latency "
-                        "(profiles/), not by HBM: fp32_tflops_achieved counts the decoder's algorithmic FLOPs"}
+                "kernel_time_share": {"decode": kms[0] / total_k, "knn_repulsion_adam (cloud_step)": kms[1] / total_k,
+                                      "adam (separate, legacy tail only)": kms[2] / total_k},
+                "note": "planes (100 MB) are L2-resident after the first Adam step and the points of a cloud share texels, so DRAM "
+                        "traffic is far below the algorithmic gather bytes; the kernel is bound by L2->SM gather latency (texels "
+                        "fetched for fwd and bwd) and the tcgen05/TMEM round trip of the 30-layer chain (profiles/), not by "
+                        "HBM: fp32_tflops_achieved counts the decoder's algorithmic FLOPs"}
 
         # ---- e2e: host buffers through the reference-facing host call (pinned inputs, H2D + D2H timed)
         rest = convonet.Restorer(dec, threshold=0.2, lr=1e-3, decode_kernel=args.decode_kernel)
