@@ -44,6 +44,9 @@ SIGNATURES = {
     "ifd_convonet_decode_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
     "ifd_convonet_decode_bce_grad": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _c_d, _c_int,
                                               _c_int, _vp, _vp, _c_sz, _vp]),
+    "ifd_plane_bins": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
+    "ifd_scatter_max_gather": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "ifd_scatter_mean_cl": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "ifd_opt_params_default": (None, [ctypes.POINTER(OptParams)]),
     "ifd_convonet_opt_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "ifd_convonet_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -24,6 +24,10 @@ def planes_to_channels_last(c):
     if isinstance(c, torch.Tensor):          # already converted
         return c
     capi.require_gpu()
+    if all(c[k].dim() == 4 and c[k].dtype == torch.float32 and c[k].is_contiguous(memory_format=torch.channels_last)
+           and not c[k].is_contiguous() for k in PLANES):
+        # the encoder already produced channels_last memory (models.LocalPoolPointnet on CUDA): that IS the kernel layout
+        return torch.stack([c[k].detach().permute(0, 2, 3, 1) for k in PLANES]).contiguous()
     x = torch.stack([c[k].detach().float() for k in PLANES]).contiguous()     # [3,B,C,R,R]
     _, B, C, R, R2 = x.shape
     if R != R2:

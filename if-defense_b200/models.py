@@ -146,6 +146,8 @@ class LocalPoolPointnet(nn.Module):
             torch.use_deterministic_algorithms(det, warn_only=warn)
 
     def _forward(self, p):
+        if p.is_cuda:
+            return self._forward_cuda(p)
         index = {pl: coordinate2index(normalize_coordinate(p, self.padding, pl), self.reso_plane) for pl in self.plane_type}
         net = self.blocks[0](self.fc_pos(p))
         for block in self.blocks[1:]:
@@ -158,6 +160,37 @@ class LocalPoolPointnet(nn.Module):
             plane = src.new_zeros(p.size(0), self.c_dim, self.reso_plane ** 2).scatter_add_(-1, idx, src)
             cnt = torch.zeros_like(plane).scatter_add_(-1, idx, torch.ones_like(src))
             plane = (plane / cnt.clamp_(min=1)).reshape(p.size(0), self.c_dim, self.reso_plane, self.reso_plane)
+            fea[pl] = self.unet(plane) if self.unet is not None else plane
+        return fea
+
+    def _forward_cuda(self, p):
+        """The same forward on the GPU: bins, scatter_max + gather and scatter_mean are the library's kernels
+        (ifd_plane_bins, ifd_scatter_max_gather, ifd_scatter_mean_cl: deterministic, channels-last planes); the Linear
+        layers and the U-Net stay torch / cuDNN."""
+        from . import capi
+        capi.require_gpu()
+        if list(self.plane_type) != ["xz", "xy", "yz"]:
+            raise RuntimeError("the CUDA encoder path is built for plane_type ['xz', 'xy', 'yz']")
+        L, st = capi.lib(), capi.stream()
+        x = p.detach().float().contiguous()
+        B, T, _ = x.shape
+        R, nb = self.reso_plane, self.reso_plane ** 2
+        bins = torch.empty((3, B, T), dtype=torch.int32, device=x.device)
+        capi.check(L.ifd_plane_bins(capi.ptr(x), B, T, R, float(self.padding), capi.ptr(bins), st), "ifd_plane_bins")
+        net = self.blocks[0](self.fc_pos(x))
+        for block in self.blocks[1:]:
+            src = net.contiguous()
+            pooled = torch.empty_like(src)
+            capi.check(L.ifd_scatter_max_gather(capi.ptr(src), capi.ptr(bins), 3, B, T, src.shape[2], nb, capi.ptr(pooled), st),
+                       "ifd_scatter_max_gather")
+            net = block(torch.cat([src, pooled], dim=2))
+        c = self.fc_c(net).contiguous()
+        fea = {}
+        for i, pl in enumerate(self.plane_type):
+            out = torch.empty((B, nb, self.c_dim), dtype=torch.float32, device=x.device)
+            capi.check(L.ifd_scatter_mean_cl(capi.ptr(c), capi.ptr(bins[i]), B, T, self.c_dim, nb, capi.ptr(out), st),
+                       "ifd_scatter_mean_cl")
+            plane = out.view(B, R, R, self.c_dim).permute(0, 3, 1, 2)        # [B,C,R,R], channels_last memory
             fea[pl] = self.unet(plane) if self.unet is not None else plane
         return fea
 

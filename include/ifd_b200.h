@@ -129,6 +129,28 @@ int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weight
                                  ifd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * ConvONet encoder operators (LocalPoolPointnet; run once per batch, before the loop)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* coordinate2index(normalize_coordinate(p, plane), R) for the three planes (ConvONet/src/common.py:235-258,300-315;
+ * called at ConvONet/src/encoder/pointnet.py:131-143): bins_out [3][B][T] int32 in the order xz, xy, yz,
+ * bin = floor(u0 * R) + R * floor(u1 * R). */
+int ifd_plane_bins(const float* xyz, int B, int T, int R, double padding, int32_t* bins_out, ifd_stream_t stream);
+
+/* pool_local (ConvONet/src/encoder/pointnet.py:104-122): for each of the P planes torch_scatter.scatter_max into the
+ * bins, gather back to the points, summed over the planes in order.  src, out: [B][T][C] point-major (the reference
+ * permutes to [B,C,T] around the call); bins [P][B][T]. */
+int ifd_scatter_max_gather(const float* src, const int32_t* bins, int P, int B, int T, int C, int nbins, float* out,
+                           ifd_stream_t stream);
+
+/* generate_plane_features up to the U-Net (ConvONet/src/encoder/pointnet.py:68-80): torch_scatter.scatter_mean of the
+ * point features into the R^2 bins of one plane, empty bins 0.  src [B][T][C]; bins [B][T]; plane_out [B][nbins][C]
+ * channels-last (the memory of a [B,C,R,R] torch tensor in channels_last format).  Members of a bin are summed in
+ * ascending point order: reproducible, and equal to a sequential scatter_add (the reference's CUDA atomics are not). */
+int ifd_scatter_mean_cl(const float* src, const int32_t* bins, int B, int T, int C, int nbins, float* plane_out,
+                        ifd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The restoration loop
  * ---------------------------------------------------------------------------------------------- */
 
