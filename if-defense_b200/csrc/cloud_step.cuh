@@ -63,6 +63,7 @@ struct CloudStepSmem {
   uint16_t sorted[kCsMaxK];                  // point indices in cell order
   float gmv[3][3 * kCsMaxK];                 // g_occ, m, v of the cloud, flat [K][3] (coalesced in, coalesced out)
   uint16_t cid[kCsMaxK];                     // cell of every point (ownership: cell < split -> CTA 0)
+  uint16_t hcnt[kCsMaxK];                    // candidates found by the helper thread of each query slot
   double hubsum[kCsMaxHub][3];               // in-edge sums of hubs (points whose inbox overflowed)
   uint16_t hub[kCsMaxHub];
   float red[8][32];
@@ -257,8 +258,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
   // ---- from here on thread t owns the t-th point in CELL order: the lanes of a warp are spatial neighbours, so
   //      their range queries walk (nearly) the same rows and candidates -- coherent loops, broadcast loads
   const int rank0 = half == 0 ? 0 : S.split_rank, rank1 = half == 0 ? S.split_rank : K;
-  live = rank0 + i < rank1;
-  const int p = live ? (int)S.sorted[rank0 + i] : (int)S.sorted[0];
+  const int n_own = rank1 - rank0;
+  live = i < n_own;
+  // Two threads per query wherever the CTA has threads to spare (the split is at the median, so about half of them
+  // are): thread n_own + q walks the odd rows of query q's box, thread q the even ones -- the idle half of the CTA
+  // halves the length of the divergent candidate walk.
+  const int n_help = min(kCsThreads - n_own, n_own);           // queries [0, n_help) have a helper
+  const bool helper = i >= n_own && i - n_own < n_help;
+  const int qi = helper ? i - n_own : i;                       // query slot this thread works for
+  const bool helped = qi < n_help;                             // this thread's query is shared by two threads
+  const bool scan = live || helper;
+  const int p = scan ? (int)S.sorted[rank0 + qi] : (int)S.sorted[0];
   const float4 me = S.pos[p];
 
   // ---- kNN
@@ -268,8 +278,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
     // the scan threshold and the scan itself use one expression: -2 * dot(a, b) == dot(-2 a, b) bit for bit (scaling
     // by a power of two commutes with rounding), folded into the query once; the ranking keys are knn_key proper
     const float mx = -2.0f * me.x, my = -2.0f * me.y, mz = -2.0f * me.z;
-    float tau = live ? INFINITY : -INFINITY;                   // idle lanes accept nothing
-    if (live && a.warm) {
+    float tau = scan ? INFINITY : -INFINITY;                   // idle lanes accept nothing
+    if (scan && a.warm) {
       const uint4 pr = *reinterpret_cast<const uint4*>(&S.nbr[p][0]);
       const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w};
       tau = -INFINITY;
@@ -287,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
     // for max-over-lanes (rows + candidates) iterations instead of the product of the per-row maxima that nested
     // loops cost (measured: 2400 instructions per warp for ~300 useful per lane).
     int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1, bz0 = 0, bz1 = -1;
-    if (live) {
+    if (scan) {
       if (tau < INFINITY) {
         const float r = sqrtf(fmaxf(tau, 0.0f) + key_margin) * 1.0001f + 1e-7f;
         bx0 = cs_cell(me.x - r, lox, ihx); bx1 = cs_cell(me.x + r, lox, ihx);
@@ -303,13 +313,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
     uint16_t* col = &S.inbox[0][0] + i;                        // element c at col[c * kCsThreads]
     int cnt = 0;
     {
-      int cz = bz0, cy = by0 - 1, t = 0, t1 = 0;
-      bool more = live;
+      const int ny = by1 - by0 + 1, stride = (scan && helped) ? 2 : 1;
+      int cz = bz0, cy = by0 + (helper ? 1 : 0) - stride, t = 0, t1 = 0;    // rows in (cz, cy) order, every stride-th one
+      bool more = scan && ny > 0;
       while (__any_sync(0xffffffffu, more)) {
         if (more) {
           if (t >= t1) {                                       // next row of the box
-            if (++cy > by1) {
-              cy = by0;
+            cy += stride;
+            while (cy > by1) {
+              cy -= ny;
               ++cz;
             }
             if (cz > bz1) {
@@ -331,7 +343,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
         }
       }
     }
+    int cnt2 = 0;
+    if (helper) S.hcnt[qi] = (uint16_t)min(cnt, 0xffff);       // hand the helper's column over
+    __syncthreads();
+    if (live && helped) cnt2 = S.hcnt[i];
+    if (live && cnt2 > kCsInbox) cnt = kCsInbox + 1;           // either column overflowed: rescan below, nothing offered yet
     if (live && cnt <= kCsInbox) {
+      const uint16_t* col2 = col + n_own;                      // the helper's column
+      for (int c0 = 0; c0 < cnt2; ++c0) {
+        const int j = col2[c0 * kCsThreads];
+        const float4 c = S.pos[j];
+        top.offer_lex(knn_key(me.w, c.w, dot3_chain(me.x, me.y, me.z, c.x, c.y, c.z)), j);
+      }
       for (int c0 = 0; c0 < cnt; ++c0) {
         const int j = col[c0 * kCsThreads];
         const float4 c = S.pos[j];
