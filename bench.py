@@ -180,12 +180,12 @@ def main():
     gathered = [torch.empty_like(x) for _ in range(world)] if world > 1 else None
     stream = torch.cuda.current_stream()
 
-    def step(j):
+    def step(j, gather=True):
         _, planes_cl, p0 = batches[j % NB]
         x.copy_(p0)
         capi.check(L.ifd_convonet_opt(capi.ptr(planes_cl), capi.ptr(dec.blob), capi.ptr(x), None, None, B, K, R, C, H, nb,
                                       ctypes.byref(P), None, capi.ptr(ws), ws_bytes, stream.cuda_stream), "ifd_convonet_opt")
-        if world > 1:
+        if world > 1 and gather:              # the one collective of the path: restored clouds of all ranks
             dist.all_gather(gathered, x)
 
     def barrier():
@@ -216,15 +216,48 @@ def main():
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---- per-kernel device time for the roofline (separate pass; events bracket every launch)
     roof = None
     e2e = None
     cpu = None
+    # ---- e2e on EVERY rank: host buffers through the reference-facing host call (pinned inputs; H2D, layout conversion,
+    #      loop and D2H of every batch inside the timed region), whole-job clouds/s over the slowest rank
+    rest = convonet.Restorer(dec, threshold=0.2, lr=1e-3, decode_kernel=args.decode_kernel)
+    host = []
+    for case, _, _ in batches:
+        pl = torch.stack([case.c[k] for k in ("xz", "xy", "yz")]).contiguous().pin_memory()
+        host.append((pl.numpy(), case.p0.clone().pin_memory().numpy()))
+    n_e2e = max(4, min(args.steps, 12))
+    seq = [host[j % NB] for j in range(n_e2e)]
+    rest.optimize_points_host_many([h[1] for h in seq[:3]], [h[0] for h in seq[:3]], rep_weight=500., iterations=ITERS, B_ref=B)
+    barrier()
+    t0 = time.perf_counter()
+    outs = rest.optimize_points_host_many([h[1] for h in seq], [h[0] for h in seq], rep_weight=500., iterations=ITERS, B_ref=B)
+    if world > 1:                                  # the final gather of the restored clouds of the last batch
+        dist.all_gather(gathered, torch.from_numpy(outs[-1]).cuda())
+        torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    if rank == 0:
+        t1 = time.perf_counter()                   # the same batches one blocking call at a time (no overlap), for reference
+        for h in seq[:4]:
+            rest.optimize_points_host(h[1], h[0], rep_weight=500., iterations=ITERS, B_ref=B)
+        t_serial = (time.perf_counter() - t1) / 4
+        h2d = int(host[0][0].nbytes + host[0][1].nbytes)
+        e2e = {"value": world * B * n_e2e / t_e2e, "unit": "clouds/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(outs[-1].nbytes), "steps": n_e2e, "ms_per_step": t_e2e / n_e2e * 1e3,
+               "ms_per_step_unpipelined_rank0": t_serial * 1e3,
+               "api": "Restorer.optimize_points_host_many -> ifd_convonet_opt_host_batches on every rank: pinned host buffers in "
+                      "and out, H2D of batch j+1 and D2H of batch j-1 overlap the loop of batch j; max over ranks"}
+
+    # ---- rank 0: per-kernel device time for the roofline (separate pass; events bracket every launch), CPU baseline
     if rank == 0:
         L.ifd_profile_enable(1)
         n_prof = max(2, min(args.steps, 5))
         for j in range(n_prof):
-            step(W + j)
+            step(W + j, gather=False)          # rank 0 alone runs this pass: no collective in it
         kms = (ctypes.c_double * 4)()
         kn = (ctypes.c_longlong * 4)()
         L.ifd_profile_read(kms, kn)
@@ -245,31 +278,6 @@ def main():
                         "traffic is far below the algorithmic gather bytes; the kernel is bound by L2->SM gather latency (texels "
                         "fetched for fwd and bwd) and the tcgen05/TMEM round trip of the 30-layer chain (profiles/), not by "
                         "HBM: fp32_tflops_achieved counts the decoder's algorithmic FLOPs"}
-
-        # ---- e2e: host buffers through the reference-facing host call (pinned inputs, H2D + D2H timed)
-        rest = convonet.Restorer(dec, threshold=0.2, lr=1e-3, decode_kernel=args.decode_kernel)
-        host = []
-        for case, _, _ in batches:
-            pl = torch.stack([case.c[k] for k in ("xz", "xy", "yz")]).contiguous().pin_memory()
-            host.append((pl.numpy(), case.p0.clone().pin_memory().numpy()))
-        n_e2e = max(4, min(args.steps, 12))
-        seq = [host[j % NB] for j in range(n_e2e)]
-        rest.optimize_points_host_many([h[1] for h in seq[:3]], [h[0] for h in seq[:3]], rep_weight=500., iterations=ITERS, B_ref=B)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        outs = rest.optimize_points_host_many([h[1] for h in seq], [h[0] for h in seq], rep_weight=500., iterations=ITERS, B_ref=B)
-        t_e2e = time.perf_counter() - t0
-        out = outs[-1]
-        # the same batches one blocking call at a time (no overlap), for reference
-        t1 = time.perf_counter()
-        for h in seq[:4]:
-            rest.optimize_points_host(h[1], h[0], rep_weight=500., iterations=ITERS, B_ref=B)
-        t_serial = (time.perf_counter() - t1) / 4
-        h2d = int(host[0][0].nbytes + host[0][1].nbytes)
-        e2e = {"value": B * n_e2e / t_e2e, "unit": "clouds/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(out.nbytes),
-               "steps": n_e2e, "ms_per_step": t_e2e / n_e2e * 1e3, "ms_per_step_unpipelined": t_serial * 1e3,
-               "api": "Restorer.optimize_points_host_many -> ifd_convonet_opt_host_batches: pinned host buffers in and out, "
-                      "H2D of batch j+1 and D2H of batch j-1 overlap the loop of batch j (1 GPU, rank 0)"}
 
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
