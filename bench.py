@@ -39,7 +39,7 @@ def ncu_traffic(kernel="convonet_decode_v3_kernel"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full summary
     (profiles/, cold-cache replay), or None."""
     try:
-        txt = open(os.path.join(ROOT, "profiles", "r01_v4_ncu_full_summary.txt")).read()
+        txt = open(os.path.join(ROOT, "profiles", "r01_final_ncu_full_summary.txt")).read()
         sec = txt.split("==== " + kernel, 1)[1].split("====", 1)[0]
         unit = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
         tot = 0.0
@@ -269,7 +269,7 @@ def main():
         total_k = sum(kms)
         roof = {"bound": "hbm", "kernel": "convonet_decode_v3_kernel (plane gather + tcgen05 ResNet-MLP fwd/dgrad)", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                "traffic_source": "profiles/r01_v4_ncu_full_summary.txt (ncu --set full, bytes per launch, cold-cache replay)",
+                "traffic_source": "profiles/r01_final_ncu_full_summary.txt (ncu --set full, bytes per launch, cold-cache replay)",
                 "ms_per_launch": dec_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "fp32_tflops_achieved": ALG_FLOP_PER_PT_STEP * B * K / (dec_ms * 1e-3) / 1e12,
                 "kernel_time_share": {"decode": kms[0] / total_k, "knn_repulsion_adam (cloud_step)": kms[1] / total_k,

@@ -106,14 +106,22 @@ def default_params(**over):
     return p
 
 
+_cc_ok = set()
+
+
 def require_gpu():
-    """Fail loudly unless a CUDA device of compute capability 10.x is current."""
+    """Fail loudly unless a CUDA device of compute capability 10.x is current (checked once per device: the
+    property query behind ifd_device_cc costs milliseconds)."""
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("ifdefense_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device()
+    if dev in _cc_ok:
+        return
     cc = lib().ifd_device_cc()
     if cc // 10 != 10:
         raise RuntimeError("ifdefense_b200 kernels are built for sm_100a only (device reports cc %d)" % cc)
+    _cc_ok.add(dev)
 
 
 def ptr(t):

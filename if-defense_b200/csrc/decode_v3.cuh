@@ -180,10 +180,12 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
     for (int g = 0; g < 4; ++g) umma::mbar_init(&bars[g], 1);
     umma::fence_mbar_init();
   }
-  {  // forward weight images -> smem
+  {  // forward weight images -> smem with cp.async (no register staging): the copy runs under the forward gather
     const float4* src = reinterpret_cast<const float4*>(a.Wimg);
-    float4* dst = reinterpret_cast<float4*>(wimg);
-    for (int i = threadIdx.x; i < n_layers * kV3ImgFloats / 4; i += kV3Threads) dst[i] = src[i];
+    const uint32_t dst = umma::smem_u32(wimg);
+    for (int i = threadIdx.x; i < n_layers * kV3ImgFloats / 4; i += kV3Threads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   for (int i = threadIdx.x; i < (n_layers + 6) * 32; i += kV3Threads) {
     const int row = i >> 5, c = i & 31;
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) convonet_decode_v3_kernel(const
     feat[(j4 * 4 + 2) * kV3Stride + gslot] = c.z;
     feat[(j4 * 4 + 3) * kV3Stride + gslot] = c.w;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   umma::fence_proxy_async();          // weight images were written through the generic proxy
   umma::fence_before_sync();
   __syncthreads();
