@@ -104,15 +104,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
     umma::mbar_init(&bars[1], 1);
     umma::fence_mbar_init();
   }
-  {  // weight chunk 0
-    const float4* src = reinterpret_cast<const float4*>(a.img);
-    float4* dst = reinterpret_cast<float4*>(bbuf);
-    for (int i = threadIdx.x; i < kChunkImgFloats / 4; i += kGemmThreads) dst[i] = src[i];
-  }
-  umma::fence_proxy_async();
-  umma::fence_before_sync();
-  __syncthreads();
-  umma::fence_after_sync();
+  auto load_b = [&](int kc, int buf) {      // weight chunk kc -> slot buf, cp.async (no register staging)
+    const float4* src = reinterpret_cast<const float4*>(a.img + (size_t)kc * kChunkImgFloats);
+    const uint32_t dst = umma::smem_u32(bbuf + (size_t)buf * kChunkImgFloats);
+    for (int i = threadIdx.x; i < kChunkImgFloats / 4; i += kGemmThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_b(0, 0);
+  __syncthreads();                          // barriers / TMEM slot visible
   const uint32_t tmem = *tmem_slot;
   const uint32_t lane_t = tmem + ((uint32_t)(warp * 32) << 16);
   const int row = blockIdx.x * kGemmThreads + threadIdx.x;
@@ -123,17 +123,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
   uint32_t parity[2] = {0u, 0u};
   constexpr uint32_t idesc = umma::idesc_tf32(128, kOH);
 
+  float4 nx[8];                             // next chunk of this thread's row, loaded one iteration ahead
+#pragma unroll
+  for (int q = 0; q < 8; ++q) nx[q] = __ldg(reinterpret_cast<const float4*>(arow) + q);
+
 #pragma unroll 1
   for (int kc = 0; kc < kOH / kChunk; ++kc) {
     const int buf = kc & 1;
     float x[32];
-    {
-      const float4* p4 = reinterpret_cast<const float4*>(arow + kc * kChunk);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = __ldg(p4 + q);
-        x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-      }
+    for (int q = 0; q < 8; ++q) {
+      x[4 * q + 0] = nx[q].x; x[4 * q + 1] = nx[q].y; x[4 * q + 2] = nx[q].z; x[4 * q + 3] = nx[q].w;
+    }
+    if (kc + 1 < kOH / kChunk) {
+      const float4* p4 = reinterpret_cast<const float4*>(arow + (kc + 1) * kChunk);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) nx[q] = __ldg(p4 + q);
     }
     if (a.pro_s) {
       const float4* s4 = reinterpret_cast<const float4*>(a.pro_s + (size_t)b * kOH + kc * kChunk);
@@ -147,27 +152,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
         x[4 * q + 3] = fmaxf(fmaf(s.w, x[4 * q + 3], t.w), 0.0f);
       }
     }
-    if (kc >= 1) {
-      if (kc >= 2) {                      // MMA kc-2 read A/B slot `buf`: it must have completed
-        umma::mbar_wait(&bars[buf], parity[buf]);
-        parity[buf] ^= 1;
+    if (kc + 1 < kOH / kChunk) {            // prefetch the next weight chunk into the other slot
+      if (kc >= 1) {                        // MMA kc-1 read that slot (and its A columns): it must have completed
+        umma::mbar_wait(&bars[buf ^ 1], parity[buf ^ 1]);
+        parity[buf ^ 1] ^= 1;
         umma::fence_after_sync();
       }
-      const float4* src = reinterpret_cast<const float4*>(a.img + (size_t)kc * kChunkImgFloats);
-      float4* dst = reinterpret_cast<float4*>(bbuf + (size_t)buf * kChunkImgFloats);
-      for (int i = threadIdx.x; i < kChunkImgFloats / 4; i += kGemmThreads) dst[i] = __ldg(src + i);
-      umma::fence_proxy_async();
+      load_b(kc + 1, buf ^ 1);
     }
     uint32_t u[32];
     const uint32_t a_hi = lane_t + 256 + buf * 64, a_lo = a_hi + 32;
 #pragma unroll
     for (int k = 0; k < 32; ++k) u[k] = umma::tf32_hi_fast(x[k]);
     umma::tmem_st32(a_hi, u);
-    umma::tmem_wait_st();
 #pragma unroll
-    for (int k = 0; k < 32; ++k) u[k] = umma::tf32_lo_fast(x[k], u[k]);
+    for (int k = 0; k < 32; ++k) u[k] = __float_as_uint(x[k] - __uint_as_float(u[k]));   // exact residual, top 11 bits used
     umma::tmem_st32(a_lo, u);
     umma::tmem_wait_st();
+    // this chunk's weights (all but the group just committed) have landed
+    if (kc + 1 < kOH / kChunk) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     if (leader) {

@@ -1,7 +1,7 @@
 """Per-kernel accuracy probe: decode+BCE gradient of kernels 1/2/3 against a float64 evaluation of the oracle."""
 import os, sys
 import numpy as np, torch, torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from ifdefense_b200 import capi, convonet, synth
 from oracle import torch_port as tp
 torch.set_num_threads(8)

@@ -247,6 +247,33 @@ def test_full_size_properties():
     assert np.abs(raw - case.p0.numpy()).max() < 0.25                  # |step| <= ~lr per iteration
 
 
+def test_reference_default_batch_192_and_ragged_last_batch():
+    """The reference's default --batch_size=192 (opt_defense.py:40) and its ragged last batch of 164 (2468 = 12 x 192 +
+    164): more CTAs than SMs for both kernels; restoring the batch in one call == in three slices with B_ref."""
+    for Bfull in (192, 164):
+        case = synth.make_case(Bfull, K=1024, seed=3, device="cuda")
+        d = convonet.ConvONetDecoder(case.sd)
+        pl = convonet.planes_to_channels_last({k: v.cuda() for k, v in case.c.items()})
+        full, _ = run_opt(d, pl, case.p0, 8, normalize=1)
+        assert full.shape == (Bfull, 1024, 3) and np.isfinite(full).all()
+        cuts = [0, Bfull // 3, 2 * Bfull // 3 + 1, Bfull]
+        parts = [run_opt(d, pl[:, a:b].contiguous(), case.p0[a:b], 8, B_ref=Bfull, normalize=1)[0] for a, b in zip(cuts, cuts[1:])]
+        assert np.array_equal(np.concatenate(parts), full)
+
+
+def test_large_clouds_take_the_first_generation_tail_and_edge_step_counts(dec, planes, conv):
+    """K > 1024 points per cloud: the fused tail does not apply, the loop switches to the brute-force kNN + separate Adam
+    kernels by itself (same result as asking for them); n_steps = 0 leaves the points untouched."""
+    case = synth.make_case(2, K=1536, seed=4, device="cuda")
+    d = convonet.ConvONetDecoder(case.sd)
+    pl = convonet.planes_to_channels_last({k: v.cuda() for k, v in case.c.items()})
+    a, _ = run_opt(d, pl, case.p0, 6)
+    b, _ = run_opt(d, pl, case.p0, 6, tail_kernel=1)
+    assert a.shape == (2, 1536, 3) and np.isfinite(a).all() and np.array_equal(a, b)
+    x0, _ = run_opt(dec, planes, conv["p0"], 0)
+    assert np.array_equal(x0, conv["p0"])
+
+
 def test_errors(dec, planes, conv):
     x = dev(conv["p0"])
     L = capi.lib()
