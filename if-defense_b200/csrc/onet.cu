@@ -28,6 +28,9 @@ constexpr int kGemmThreads = 128;
 constexpr int kChunk = 32;                              // K columns per pipeline step
 constexpr int kChunkImgFloats = 2 * kOH * kChunk;       // hi + lo of a [256 x 32] chunk
 constexpr int kLayerImgFloats = (kOH / kChunk) * kChunkImgFloats;   // 131072 floats = 512 KB
+constexpr int kNH = kOH / 2;                            // output columns per CTA: the N range is split over blockIdx.y so that
+                                                        // two CTAs (256 TMEM columns each) share an SM
+constexpr int kHalfImgFloats = 2 * kNH * kChunk;        // hi + lo of a [128 x 32] half chunk = 32 KB
 
 // ---------------------------------------------------------------------------------------------- packing
 // One layer's weight W[n][k] (row-major [256][256]) -> chunked K-major UMMA images, hi then lo per chunk.
@@ -92,23 +95,30 @@ struct GemmArgs {
   int M, K;              // rows, points per cloud
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__(kGemmThreads, 2) onet_gemm_kernel(const GemmArgs a) {
   extern __shared__ float4 smem4[];
-  float* bbuf = reinterpret_cast<float*>(smem4);                    // [2][kChunkImgFloats]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + 2 * kChunkImgFloats);
+  float* bbuf = reinterpret_cast<float*>(smem4);                    // [2][kHalfImgFloats]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + 2 * kHalfImgFloats);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int warp = threadIdx.x >> 5;
-  if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
+  const int nh = blockIdx.y;                                        // which half of the 256 output columns
+  if (warp == 0) umma::tmem_alloc(tmem_slot, 256);                  // D: columns 0..127, A chunks: 128..255
   if (threadIdx.x == 32) {
     umma::mbar_init(&bars[0], 1);
     umma::mbar_init(&bars[1], 1);
     umma::fence_mbar_init();
   }
-  auto load_b = [&](int kc, int buf) {      // weight chunk kc -> slot buf, cp.async (no register staging)
+  // Weight chunk kc, rows [128 nh, 128 nh + 128) -> slot buf with cp.async (no register staging).  In the packed
+  // K-major image of the full [256 x 32] chunk every 4-wide k group holds its 32 n-groups contiguously (4 KB), so
+  // the half is 16 pieces of 2 KB (8 k groups x {hi, lo}), stored back to back: LBO = 2048 in shared memory.
+  auto load_b = [&](int kc, int buf) {
     const float4* src = reinterpret_cast<const float4*>(a.img + (size_t)kc * kChunkImgFloats);
-    const uint32_t dst = umma::smem_u32(bbuf + (size_t)buf * kChunkImgFloats);
-    for (int i = threadIdx.x; i < kChunkImgFloats / 4; i += kGemmThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + i) : "memory");
+    const uint32_t dst = umma::smem_u32(bbuf + (size_t)buf * kHalfImgFloats);
+    for (int i = threadIdx.x; i < kHalfImgFloats / 4; i += kGemmThreads) {
+      const int piece = i >> 7, within = i & 127;                   // 128 float4 = 2 KB per piece
+      const int sidx = (piece < 8 ? piece * 256 : 2048 + (piece - 8) * 256) + nh * 128 + within;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + sidx) : "memory");
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   load_b(0, 0);
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
   const float* arow = a.A + (size_t)rowc * kOH;
   const bool leader = threadIdx.x == 0;
   uint32_t parity[2] = {0u, 0u};
-  constexpr uint32_t idesc = umma::idesc_tf32(128, kOH);
+  constexpr uint32_t idesc = umma::idesc_tf32(128, kNH);
 
   float4 nx[8];                             // next chunk of this thread's row, loaded one iteration ahead
 #pragma unroll
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
       load_b(kc + 1, buf ^ 1);
     }
     uint32_t u[32];
-    const uint32_t a_hi = lane_t + 256 + buf * 64, a_lo = a_hi + 32;
+    const uint32_t a_hi = lane_t + kNH + buf * 64, a_lo = a_hi + 32;
 #pragma unroll
     for (int k = 0; k < 32; ++k) u[k] = umma::tf32_hi_fast(x[k]);
     umma::tmem_st32(a_hi, u);
@@ -177,15 +187,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
     __syncthreads();
     if (leader) {
       umma::fence_after_sync();
-      const uint32_t ta_hi = tmem + 256 + buf * 64, ta_lo = ta_hi + 32;
-      const uint32_t sb = umma::smem_u32(bbuf + (size_t)buf * kChunkImgFloats);
+      const uint32_t ta_hi = tmem + kNH + buf * 64, ta_lo = ta_hi + 32;
+      const uint32_t sb = umma::smem_u32(bbuf + (size_t)buf * kHalfImgFloats);
 #pragma unroll
       for (int part = 0; part < 3; ++part) {        // lo.hi, hi.lo, hi.hi
         const uint32_t ta = part == 0 ? ta_lo : ta_hi;
-        const uint32_t bs = sb + (part == 1 ? (uint32_t)(kOH * kChunk * 4) : 0u);
+        const uint32_t bs = sb + (part == 1 ? (uint32_t)(kNH * kChunk * 4) : 0u);
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-          umma::mma_tf32_ts(tmem, ta + s * 8, umma::smem_desc_kmajor(bs + s * 2 * (kOH / 8) * 128, (kOH / 8) * 128, 128), idesc,
+          umma::mma_tf32_ts(tmem, ta + s * 8, umma::smem_desc_kmajor(bs + s * 2 * (kNH / 8) * 128, (kNH / 8) * 128, 128), idesc,
                             (kc | part | s) ? 1u : 0u);
       }
       umma::commit(&bars[buf]);
@@ -199,9 +209,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
   float* orow = a.out + (size_t)rowc * kOH;
   const bool live = row < a.M;
 #pragma unroll 1
-  for (int cg = 0; cg < kOH / 32; ++cg) {
+  for (int cl = 0; cl < kNH / 32; ++cl) {
+    const int cg = nh * (kNH / 32) + cl;            // 32-column group of the full row
     uint32_t d[32];
-    umma::tmem_ld32(lane_t + cg * 32, d);
+    umma::tmem_ld32(lane_t + cl * 32, d);
     float y[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(d[k]);
@@ -242,7 +253,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) onet_gemm_kernel(const GemmAr
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 // ---------------------------------------------------------------------------------------------- thin layers
@@ -382,9 +393,9 @@ OnetWs carve_onet(void* base, int B, int K) {
   return w;
 }
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)2 * kChunkImgFloats * 4 + 64;
+  const size_t smem = (size_t)2 * kHalfImgFloats * 4 + 64;
   IFD_CUDA_TRY(cudaFuncSetAttribute(onet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  onet_gemm_kernel<<<(a.M + kGemmThreads - 1) / kGemmThreads, kGemmThreads, smem, st>>>(a);
+  onet_gemm_kernel<<<dim3((a.M + kGemmThreads - 1) / kGemmThreads, 2), kGemmThreads, smem, st>>>(a);
   IFD_LAUNCH_CHECK("onet_gemm_kernel");
   return IFD_OK;
 }
