@@ -45,13 +45,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns): the warp sleeps
-        "selp.u32 %0, 1, 0, p;\n\t"                                        // in hardware instead of burning issue slots
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(20000u)
+        : "r"(addr), "r"(parity)
         : "memory");
-    if (!done && ++spins > (1 << 20)) __trap();   // a lost tcgen05.commit must fail the launch, not hang the GPU
+    if (!done && ++spins > (1 << 22)) __trap();   // a lost tcgen05.commit must fail the launch, not hang the GPU
   } while (!done);
 }
 // arrive on `bar` once every previously issued tcgen05.mma of this thread has completed
