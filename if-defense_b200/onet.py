@@ -74,6 +74,46 @@ class ONetDecoder:
     def decode(self, p, z, c, **kwargs):
         return dist.Bernoulli(logits=_DecodeFn.apply(p, c, self))
 
+    def _logits_nograd(self, x, cc):
+        """x [1,K,3] cuda, cc [1,512] cuda -> logits [K] cuda (forward only, nothing saved)."""
+        K = x.shape[1]
+        L = capi.lib()
+        ws = self.ws.get(1, K, x.device)
+        capi.check(L.ifd_onet_prepare(capi.ptr(self.blob), capi.ptr(cc), 1, K, capi.ptr(ws), ws.numel(), capi.stream()), "ifd_onet_prepare")
+        logits = torch.empty((1, K), dtype=torch.float32, device=x.device)
+        capi.check(L.ifd_onet_decode_fwd(capi.ptr(self.blob), capi.ptr(x), 1, K, capi.ptr(logits), capi.ptr(ws), ws.numel(),
+                                         capi.stream()), "ifd_onet_decode_fwd")
+        return logits[0]
+
+    def eval_points(self, p, z=None, c=None, points_batch_size=100000):
+        """Generator3D.eval_points (ONet/im2mesh/onet/generation.py:138-158): occupancy logits of N points for ONE shape,
+        in chunks of points_batch_size (the reference's default, configs/default.yaml), returned on the CPU."""
+        capi.require_gpu()
+        p = torch.as_tensor(p).detach().float()
+        cc = torch.as_tensor(c).detach().float().reshape(1, -1).cuda().contiguous()
+        out = torch.empty(p.shape[0], dtype=torch.float32)
+        for lo in range(0, p.shape[0], points_batch_size):
+            x = p[lo:lo + points_batch_size].cuda().contiguous().view(1, -1, 3)
+            out[lo:lo + x.shape[1]] = self._logits_nograd(x, cc).cpu()
+        return out
+
+    def eval_dense_grid(self, c, resolution=128, padding=0.1, points_batch_size=100000):
+        """The occupancy field generate_from_latent needs (ONet/im2mesh/onet/generation.py:101-130), evaluated densely
+        on the (resolution + 1)^3 lattice MISE would refine to (resolution0 = 32, two upsampling steps -> 128):
+        p = box_size * (index / resolution - 0.5), box_size = 1 + padding.  Returns a float32 cuda tensor
+        [R+1, R+1, R+1] indexed [x, y, z] like MISE.to_dense(); every value is an evaluated one (MISE fills the
+        cells it skips by propagation)."""
+        capi.require_gpu()
+        n = resolution + 1
+        cc = torch.as_tensor(c).detach().float().reshape(1, -1).cuda().contiguous()
+        ax = (1.0 + padding) * (torch.arange(n, dtype=torch.float32, device="cuda") / resolution - 0.5)
+        out = torch.empty(n * n * n, dtype=torch.float32, device="cuda")
+        for lo in range(0, n * n * n, points_batch_size):
+            idx = torch.arange(lo, min(lo + points_batch_size, n * n * n), device="cuda")
+            x = torch.stack([ax[idx // (n * n)], ax[(idx // n) % n], ax[idx % n]], dim=1).contiguous().view(1, -1, 3)
+            out[lo:lo + x.shape[1]] = self._logits_nograd(x, cc)
+        return out.view(n, n, n)
+
 
 class ONetRestorer:
     def __init__(self, decoder, threshold=0.2, lr=1e-3):

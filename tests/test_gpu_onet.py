@@ -68,3 +68,23 @@ def test_full_size_onet_opt_properties():
     assert out.shape == (16, 1024, 3) and np.isfinite(out).all() and np.abs(out.mean(1)).max() < 1e-5
     small = rest.optimize_points(case.p0[:3, :1000].cuda().contiguous(), None, case.c[:3].cuda(), rep_weight=500., iterations=3)
     assert small.shape == (3, 1000, 3) and np.isfinite(small).all()
+
+
+def test_eval_points_and_dense_grid_vs_oracle(dec):
+    """The occupancy evaluation of ONet-Mesh (Generator3D.eval_points, generation.py:138-158): chunked forward decode for
+    one shape, and the dense (R+1)^3 lattice in the reference's coordinates, against the oracle decoder on the CPU."""
+    from oracle import torch_port as tp
+    sd = models.synthetic_state_dict("onet", 0)
+    case = synth.make_onet_case(1, K=64, seed=2)
+    c = case.c[:1]
+    p = (torch.rand(2500, 3, generator=torch.Generator().manual_seed(0)) - 0.5) * 1.1
+    got = dec.eval_points(p, None, c, points_batch_size=1000)                   # 3 chunks, the last one ragged
+    want = tp.onet_decode(sd, p[None], c)[0]
+    assert got.shape == (2500,) and got.device.type == "cpu"
+    assert (got - want).abs().max().item() < 2e-5
+    grid = dec.eval_dense_grid(c, resolution=16, points_batch_size=2000)
+    assert grid.shape == (17, 17, 17)
+    ax = 1.1 * (torch.arange(17, dtype=torch.float32) / 16 - 0.5)
+    pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).view(1, -1, 3)
+    want = tp.onet_decode(sd, pts, c)[0].view(17, 17, 17)
+    assert (grid.cpu() - want).abs().max().item() < 2e-5
