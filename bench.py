@@ -193,8 +193,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for j in range(W):
-        step(j)
+    # ---- the timed path: K steps (batches) through ifd_convonet_opt_batches -- the loops of two consecutive batches run
+    #      side by side on two streams (one launch fills 128 of the 148 SMs); every step still restores its own batch
+    n_max = max(args.steps, W)
+    xs = [torch.empty_like(x) for _ in range(n_max)]
+    ws2_bytes = 2 * ((ws_bytes + 255) // 256 * 256)
+    ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device="cuda")
+
+    def run_steps(j0, n):
+        for j in range(n):
+            xs[j].copy_(batches[(j0 + j) % NB][2])
+        pp = (ctypes.c_void_p * n)(*[batches[(j0 + j) % NB][1].data_ptr() for j in range(n)])
+        xp = (ctypes.c_void_p * n)(*[xs[j].data_ptr() for j in range(n)])
+        capi.check(L.ifd_convonet_opt_batches(n, pp, capi.ptr(dec.blob), xp, B, K, R, C, H, nb, ctypes.byref(P), capi.ptr(ws2),
+                                              ws2_bytes, stream.cuda_stream), "ifd_convonet_opt_batches")
+        if world > 1:                          # the one collective of the path: restored clouds of all ranks, per step
+            for j in range(n):
+                dist.all_gather(gathered, xs[j])
+
+    run_steps(0, W)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -203,8 +220,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for j in range(args.steps):
-        step(W + j)
+    run_steps(W, args.steps)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -302,6 +318,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clouds_per_gpu_per_step": B, "B_ref": B,
                        "l2": "inputs rotate over %d distinct batches per rank (%.0f MB of planes) > 126 MB L2" % (NB, NB * 100.7),
+                       "concurrency": "loops of two consecutive steps run side by side on two streams (ifd_convonet_opt_batches)",
                        "parallelism": "clouds sharded over %d GPU(s), all_gather of restored clouds per step" % world},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }))

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ifd_convonet_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                   ctypes.POINTER(OptParams), _vp, _vp, _c_sz, _vp]),
     "ifd_opt_tail_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, ctypes.POINTER(OptParams), _c_int, _vp, _vp, _vp]),
+    "ifd_convonet_opt_batches": (_c_int, [_c_int, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                          ctypes.POINTER(OptParams), _vp, _c_sz, _vp]),
     "ifd_convonet_opt_host": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                        ctypes.POINTER(OptParams), _vp]),
     "ifd_convonet_opt_host_batches": (_c_int, [_c_int, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -152,20 +152,22 @@ extern "C" int ifd_convonet_opt_host(const float* planes_nchw_host, const float*
 
 // ---------------------------------------------------------------------------------------------------------------
 // Many batches, pipelined: what defend_point_cloud (ConvONet/opt_defense.py:272-312) does batch after batch, with the
-// host<->device copies of batch j+1 / j-1 overlapped with the loop of batch j (three streams, two buffer slots).
+// host<->device copies overlapped with the loops, and the loops of two consecutive batches running side by side (two
+// run streams, two buffer slots, copy streams for H2D and D2H).
 // Every batch still pays its own H2D of planes + init points and D2H of the restored cloud.
 namespace ifd {
 struct PipeCache {
   void* dev = nullptr;
   size_t bytes = 0;
-  cudaStream_t h2d = nullptr, run = nullptr, d2h = nullptr;
+  cudaStream_t h2d = nullptr, run[2] = {nullptr, nullptr}, d2h = nullptr;
   cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
 };
 static thread_local PipeCache g_pipe;
 static int ensure_pipe(size_t dev_bytes) {
   if (!g_pipe.h2d) {
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.h2d, cudaStreamNonBlocking));
-    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run, cudaStreamNonBlocking));
+    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[0], cudaStreamNonBlocking));
+    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[1], cudaStreamNonBlocking));
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.d2h, cudaStreamNonBlocking));
     for (int s = 0; s < 2; ++s) {
       IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.ready[s], cudaEventDisableTiming));
@@ -199,12 +201,14 @@ extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* 
   const size_t xyz_al = align_up(xyz_bytes, 256);
   const size_t w_bytes = align_up(nw * sizeof(float), 256);
   const size_t ws_bytes = align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
-  const size_t total = w_bytes + ws_bytes + 2 * (2 * plane_bytes + xyz_al);
+  const size_t total = w_bytes + 2 * ws_bytes + 2 * (2 * plane_bytes + xyz_al);
   int rc = ensure_pipe(total);
   if (rc) return rc;
   char* base = (char*)g_pipe.dev;
   float* d_w = (float*)base; base += w_bytes;
-  void* d_ws = base; base += ws_bytes;
+  void* d_ws[2];                            // one workspace per slot: the loops of two batches run side by side
+  d_ws[0] = base; base += ws_bytes;
+  d_ws[1] = base; base += ws_bytes;
   float *d_nchw[2], *d_cl[2], *d_xyz[2];
   for (int s = 0; s < 2; ++s) {
     d_nchw[s] = (float*)base; base += plane_bytes;
@@ -220,17 +224,20 @@ extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* 
     IFD_CUDA_TRY(cudaMemcpyAsync(d_xyz[s], xyz_host[j], xyz_bytes, cudaMemcpyHostToDevice, g_pipe.h2d));
     if ((rc = ifd_planes_nchw_to_cl(d_nchw[s], d_cl[s], 3 * B, C, R, g_pipe.h2d))) return rc;
     IFD_CUDA_TRY(cudaEventRecord(g_pipe.ready[s], g_pipe.h2d));
-    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.run, g_pipe.ready[s], 0));
-    if ((rc = ifd_convonet_opt(d_cl[s], d_w, d_xyz[s], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr, d_ws, ws_bytes,
-                               g_pipe.run)))
+    // two run streams: a decode or tail launch occupies 128 of the 148 SMs (one CTA per SM), the other batch's
+    // launches fill the rest and every gap between dependent launches
+    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.run[s], g_pipe.ready[s], 0));
+    if ((rc = ifd_convonet_opt(d_cl[s], d_w, d_xyz[s], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr, d_ws[s], ws_bytes,
+                               g_pipe.run[s])))
       return rc;
-    IFD_CUDA_TRY(cudaEventRecord(g_pipe.done[s], g_pipe.run));
+    IFD_CUDA_TRY(cudaEventRecord(g_pipe.done[s], g_pipe.run[s]));
     IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.done[s], 0));
     IFD_CUDA_TRY(cudaMemcpyAsync(xyz_host[j], d_xyz[s], xyz_bytes, cudaMemcpyDeviceToHost, g_pipe.d2h));
     IFD_CUDA_TRY(cudaEventRecord(g_pipe.freed[s], g_pipe.d2h));
   }
   IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.d2h));
-  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.run));
+  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.run[0]));
+  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.run[1]));
   IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.h2d));
   return IFD_OK;
 }
@@ -244,7 +251,8 @@ void release_pipe() {
     if (g_pipe.freed[s]) cudaEventDestroy(g_pipe.freed[s]);
   }
   if (g_pipe.h2d) cudaStreamDestroy(g_pipe.h2d);
-  if (g_pipe.run) cudaStreamDestroy(g_pipe.run);
+  if (g_pipe.run[0]) cudaStreamDestroy(g_pipe.run[0]);
+  if (g_pipe.run[1]) cudaStreamDestroy(g_pipe.run[1]);
   if (g_pipe.d2h) cudaStreamDestroy(g_pipe.d2h);
   g_pipe = PipeCache();
 }

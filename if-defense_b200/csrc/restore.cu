@@ -724,6 +724,51 @@ extern "C" int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const
   return IFD_OK;
 }
 
+// A sequence of batches on device buffers, two at a time: one decode or tail launch occupies 128 of the 148 SMs (one CTA
+// per SM, B = 64), so the loops of two batches side by side keep the remaining SMs -- and every gap between dependent
+// launches -- busy.  Forks from `stream` into two internal streams and joins back into it.
+namespace {
+struct PairStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+};
+thread_local PairStreams g_pair;
+int ensure_pair() {
+  if (g_pair.fork) return IFD_OK;
+  for (int i = 0; i < 2; ++i) {
+    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pair.s[i], cudaStreamNonBlocking));
+    IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pair.join[i], cudaEventDisableTiming));
+  }
+  IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pair.fork, cudaEventDisableTiming));
+  return IFD_OK;
+}
+}  // namespace
+
+extern "C" int ifd_convonet_opt_batches(int n_batches, const float* const* planes_cl, const float* dec_weights, float* const* xyz,
+                                        int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* P, void* workspace,
+                                        size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_REQUIRE(n_batches >= 0 && planes_cl && dec_weights && xyz && P && workspace && B > 0 && K > 0, "ifd_convonet_opt_batches: bad arguments");
+  const size_t one = align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
+  if (workspace_bytes < 2 * one) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_opt_batches: workspace must hold 2 x ifd_convonet_opt_workspace_bytes (256-byte aligned)");
+  int rc = ensure_pair();
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  IFD_CUDA_TRY(cudaEventRecord(g_pair.fork, st));
+  for (int i = 0; i < 2; ++i) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pair.s[i], g_pair.fork, 0));
+  for (int j = 0; j < n_batches; ++j) {
+    const int s = j & 1;
+    IFD_REQUIRE(planes_cl[j] && xyz[j], "ifd_convonet_opt_batches: null batch pointer");
+    if ((rc = ifd_convonet_opt(planes_cl[j], dec_weights, xyz[j], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr,
+                               (char*)workspace + (size_t)s * one, one, g_pair.s[s])))
+      return rc;
+  }
+  for (int i = 0; i < 2; ++i) {
+    IFD_CUDA_TRY(cudaEventRecord(g_pair.join[i], g_pair.s[i]));
+    IFD_CUDA_TRY(cudaStreamWaitEvent(st, g_pair.join[i], 0));
+  }
+  return IFD_OK;
+}
+
 extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,
                                             int R, int C, int H, int n_blocks, double padding, double occ_target, int B_ref,
                                             int decode_kernel, float* grad_xyz_out, void* workspace, size_t workspace_bytes,

@@ -207,6 +207,16 @@ int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const float* g_o
                       int K, const ifd_opt_params* params, int step_index, float* loss_sum_out, float* rep_grad_out,
                       ifd_stream_t stream);
 
+/* The same for a sequence of batches on DEVICE buffers (the loop of defend_point_cloud over batches, opt_defense.py:
+ * 272-312, with the encoder outputs already in kernel layout): batch j uses planes_cl[j] / xyz[j] (in place), all of B
+ * clouds.  The loops of two consecutive batches run side by side on two internal streams forked from and joined back
+ * into `stream` -- one launch of the loop fills 128 of the 148 SMs at B = 64.  workspace: 2 x
+ * ifd_convonet_opt_workspace_bytes(B, K), each rounded up to 256 bytes.  Results are bit-identical to n_batches calls of
+ * ifd_convonet_opt. */
+int ifd_convonet_opt_batches(int n_batches, const float* const* planes_cl, const float* dec_weights, float* const* xyz,
+                             int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* params,
+                             void* workspace, size_t workspace_bytes, ifd_stream_t stream);
+
 /* Host-buffer convenience call (the end-to-end seam): planes in the reference's NCHW layout
  * [3][B][C][R][R], weights, xyz are HOST pointers; does H2D, layout conversion, the loop, D2H of xyz and
  * synchronises.  Device scratch is cached per thread between calls and released by ifd_release_cache(). */
@@ -215,8 +225,9 @@ int ifd_convonet_opt_host(const float* planes_nchw_host, const float* dec_weight
                           double* stats_out_host);
 /* The same for a sequence of batches -- the loop of defend_point_cloud over batches (ConvONet/opt_defense.py:272-312):
  * planes_nchw_host[j] / xyz_host[j] are the HOST buffers of batch j (all batches B clouds; pinned memory makes the
- * copies asynchronous).  Batch j+1 is uploaded and converted, and batch j-1 is downloaded, while batch j runs
- * (three streams, two device buffer slots); every batch still pays its own H2D and D2H.  Synchronises before
+ * copies asynchronous).  Two device buffer slots and two run streams: uploads, layout conversions and downloads
+ * overlap the loops, and the loops of two consecutive batches run side by side (one launch fills 128 of the 148 SMs);
+ * every batch still pays its own H2D and D2H.  Synchronises before
  * returning.  Results are bit-identical to n_batches calls of ifd_convonet_opt_host. */
 int ifd_convonet_opt_host_batches(int n_batches, const float* const* planes_nchw_host, const float* dec_weights_host,
                                   float* const* xyz_host, int B, int K, int R, int C, int H, int n_blocks,

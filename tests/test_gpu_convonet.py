@@ -229,6 +229,27 @@ def test_reference_signature_and_host_seam(conv, dec, conv_planes):
     assert np.isfinite(out0).all() and not np.array_equal(out0, out)
 
 
+def test_device_batches_equal_single_calls(conv, dec, planes):
+    """ifd_convonet_opt_batches (two loops side by side on two streams) gives the bits of one call per batch."""
+    L = capi.lib()
+    want, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1)
+    xs = [dev(conv["p0"]).clone() for _ in range(3)]
+    B, K, _ = xs[0].shape
+    one = (L.ifd_convonet_opt_workspace_bytes(B, K) + 255) // 256 * 256
+    ws = torch.empty(2 * one, dtype=torch.uint8, device="cuda")
+    P = capi.default_params(n_steps=20, B_ref=B, normalize_out=1)
+    pp = (ctypes.c_void_p * 3)(*[planes.data_ptr()] * 3)
+    xp = (ctypes.c_void_p * 3)(*[x.data_ptr() for x in xs])
+    capi.check(L.ifd_convonet_opt_batches(3, pp, capi.ptr(dec.blob), xp, B, K, 64, 32, 32, 5, ctypes.byref(P), capi.ptr(ws),
+                                          ws.numel(), capi.stream()), "ifd_convonet_opt_batches")
+    torch.cuda.synchronize()
+    for x in xs:
+        assert np.array_equal(x.cpu().numpy(), want)
+    with pytest.raises(RuntimeError, match="workspace must hold 2 x"):
+        capi.check(L.ifd_convonet_opt_batches(3, pp, capi.ptr(dec.blob), xp, B, K, 64, 32, 32, 5, ctypes.byref(P), capi.ptr(ws),
+                                              one, capi.stream()))
+
+
 def test_full_size_properties():
     """BASELINE.json config 2: B=64 x 1024 points, 201 steps.  Size-independent invariants of the output:
     centred, unit max-norm, finite, loss decreased, surface constraint approached."""
