@@ -5,13 +5,15 @@
 
 One "step" = one pass of the hot path over one batch: optimize_points on B=64 clouds x 1024 points,
 201 Adam steps (--iterations=200), synthetic ModelNet40-shaped clouds, random-init weights with the
-reference's parameter names (no checkpoint or data ships with the reference).  Under torchrun every rank
-restores its own batch (weak scaling; clouds are independent) and the restored clouds are all-gathered over
-NCCL at the end of each step -- the only collective on the path.
+reference's parameter names (no checkpoint or data ships with the reference).  The K timed steps go through
+ifd_convonet_opt_batches, which runs the loops of two consecutive batches side by side on two streams (one
+launch of the loop fills 128 of the 148 SMs at B=64).  Under torchrun every rank restores its own batches (weak
+scaling; clouds are independent) and the restored clouds of every step are all-gathered over NCCL -- the only
+collective on the path.
 
 Printed JSON (rank 0, one line): value = whole-job clouds/s with inputs resident in HBM (CUDA events, max
-over ranks); e2e = the same through the host-buffer C-ABI call (H2D + layout conversion + loop + D2H inside
-the timed region); roofline for the dominant kernel; cpu_baseline = the oracle port timed on this box's host
+over ranks); e2e = the same through the host-buffer C-ABI call (ifd_convonet_opt_host_batches: H2D + layout
+conversion + loop + D2H of every batch inside the timed region, on every rank); roofline for the dominant kernel; cpu_baseline = the oracle port timed on this box's host
 cores on a bounded sample.  --impl reference times only that CPU port (the reference's op sequence on stock
 PyTorch CPU; /root/reference itself does not exist on the GPU box).
 """
