@@ -4,7 +4,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 
 #include "../../include/ifd_b200.h"
 
@@ -50,6 +53,23 @@ struct ProfileScope {
   cudaStream_t st_;
   cudaEvent_t e0_ = nullptr;
 };
+
+// Raise a kernel's dynamic shared-memory limit once per (kernel, device): the setting is sticky, and the runtime call
+// takes the context lock -- made before every one of the ~400 launches of a restoration it made the host the
+// bottleneck of the end-to-end path (worse with NCCL's threads contending for the same lock).
+inline cudaError_t set_max_dyn_smem(const void* kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> g(mu);
+  size_t& cur = done[std::make_pair(kernel, dev)];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 
 inline cudaStream_t as_stream(ifd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -119,7 +119,7 @@ extern "C" int ifd_scatter_max_gather(const float* src, const int32_t* bins, int
   size_t smem;
   int rc = enc_smem_bytes(T, nbins, &smem);
   if (rc) return rc;
-  IFD_CUDA_TRY(cudaFuncSetAttribute(scatter_max_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)scatter_max_gather_kernel, smem));
   scatter_max_gather_kernel<<<B, kEncThreads, smem, as_stream(stream)>>>(src, bins, P, B, T, C, nbins, out);
   IFD_LAUNCH_CHECK("scatter_max_gather_kernel");
   return IFD_OK;
@@ -131,7 +131,7 @@ extern "C" int ifd_scatter_mean_cl(const float* src, const int32_t* bins, int B,
   size_t smem;
   int rc = enc_smem_bytes(T, nbins, &smem);
   if (rc) return rc;
-  IFD_CUDA_TRY(cudaFuncSetAttribute(scatter_mean_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)scatter_mean_cl_kernel, smem));
   scatter_mean_cl_kernel<<<B, kEncThreads, smem, as_stream(stream)>>>(src, bins, T, C, nbins, plane_out);
   IFD_LAUNCH_CHECK("scatter_mean_cl_kernel");
   return IFD_OK;

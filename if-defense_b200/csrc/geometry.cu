@@ -153,7 +153,7 @@ static int launch_knn(const float* x, int B, int N, int C, int k, int drop, int3
   } else {
     const size_t smem = ((size_t)(C / 4) * kKnnThreads + (size_t)kKnnCTile * (C / 4)) * sizeof(float4) +
                         kKnnCTile * sizeof(float);
-    IFD_CUDA_TRY(cudaFuncSetAttribute(knnc_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)knnc_kernel<KK>, smem));
     knnc_kernel<KK><<<grid, kKnnThreads, smem, st>>>(x, N, C, k, drop, idx_out, key_out);
     IFD_LAUNCH_CHECK("knnc_kernel");
   }
@@ -402,10 +402,10 @@ extern "C" int ifd_sor(const float* xyz, int B, int K, int k, double alpha, uint
   if (smem > 200 * 1024) return fail(IFD_ERR_UNSUPPORTED, "ifd_sor: K must be <= 5120");
   cudaStream_t st = as_stream(stream);
   if (k <= 3) {
-    IFD_CUDA_TRY(cudaFuncSetAttribute(sor_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)sor_kernel<4>, smem));
     sor_kernel<4><<<B, kSorThreads, smem, st>>>(xyz, K, k, alpha, keep_out, value_out);
   } else {
-    IFD_CUDA_TRY(cudaFuncSetAttribute(sor_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)sor_kernel<8>, smem));
     sor_kernel<8><<<B, kSorThreads, smem, st>>>(xyz, K, k, alpha, keep_out, value_out);
   }
   IFD_LAUNCH_CHECK("sor_kernel");

@@ -394,7 +394,7 @@ OnetWs carve_onet(void* base, int B, int K) {
 }
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)2 * kHalfImgFloats * 4 + 64;
-  IFD_CUDA_TRY(cudaFuncSetAttribute(onet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)onet_gemm_kernel, smem));
   onet_gemm_kernel<<<dim3((a.M + kGemmThreads - 1) / kGemmThreads, 2), kGemmThreads, smem, st>>>(a);
   IFD_LAUNCH_CHECK("onet_gemm_kernel");
   return IFD_OK;

@@ -385,13 +385,13 @@ static int launch_decode(int mode, DecodeArgs a, cudaStream_t st) {
   const int n = a.B * a.K;
   const int grid = (n + kDecThreads - 1) / kDecThreads;
   if (mode == kFwdOnly) {
-    IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_kernel<kFwdOnly>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_kernel<kFwdOnly>, smem));
     convonet_decode_kernel<kFwdOnly><<<grid, kDecThreads, smem, st>>>(a);
   } else if (mode == kBwdGiven) {
-    IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_kernel<kBwdGiven>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_kernel<kBwdGiven>, smem));
     convonet_decode_kernel<kBwdGiven><<<grid, kDecThreads, smem, st>>>(a);
   } else {
-    IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_kernel<kBce>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_kernel<kBce>, smem));
     convonet_decode_kernel<kBce><<<grid, kDecThreads, smem, st>>>(a);
   }
   IFD_LAUNCH_CHECK("convonet_decode_kernel");
@@ -405,7 +405,7 @@ static int launch_decode_v2(const DecodeArgs& a, cudaStream_t st) {
   v.wtotal4 = (ConvDecLayout<H32>::total(a.n_blocks) + 3) / 4;
   v.denom = a.denom; v.target = a.target; v.ginv = a.ginv;
   const size_t smem = DecodeV2Smem::bytes(v.wtotal4);
-  IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v2_kernel, smem));
   convonet_decode_v2_kernel<<<(v.n + kV2Pts - 1) / kV2Pts, kV2Threads, smem, st>>>(v);
   IFD_LAUNCH_CHECK("convonet_decode_v2_kernel");
   return IFD_OK;
@@ -419,7 +419,7 @@ static int launch_decode_v3(const DecodeArgs& a, const float* wimg, cudaStream_t
   const size_t smem = DecodeV3Smem::bytes(a.n_blocks);
   if (smem > 227 * 1024) return fail(IFD_ERR_UNSUPPORTED, "decode v3 supports n_blocks <= 6");
   if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v3: plane array too large for 32-bit texel indices");
-  IFD_CUDA_TRY(cudaFuncSetAttribute(convonet_decode_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v3_kernel, smem));
   convonet_decode_v3_kernel<<<(v.n + kV3Pts - 1) / kV3Pts, kV3Threads, smem, st>>>(v);
   IFD_LAUNCH_CHECK("convonet_decode_v3_kernel");
   return IFD_OK;
@@ -434,10 +434,10 @@ static int launch_knn_repulsion(const float* xyz, int B, int K, int k, float rad
   if (smem > 200 * 1024) return fail(IFD_ERR_UNSUPPORTED, "K must be <= 12000 points per cloud");
   dim3 grid((K + kRepThreads - 1) / kRepThreads, B);
   if (warm) {
-    IFD_CUDA_TRY(cudaFuncSetAttribute(knn_repulsion_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)knn_repulsion_kernel<8, true>, smem));
     knn_repulsion_kernel<8, true><<<grid, kRepThreads, smem, st>>>(xyz, K, k, radius, h, eps, idx_out, loss_part, acc, nbr);
   } else {
-    IFD_CUDA_TRY(cudaFuncSetAttribute(knn_repulsion_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)knn_repulsion_kernel<8, false>, smem));
     knn_repulsion_kernel<8, false><<<grid, kRepThreads, smem, st>>>(xyz, K, k, radius, h, eps, idx_out, loss_part, acc, nbr);
   }
   IFD_LAUNCH_CHECK("knn_repulsion_kernel");
@@ -528,7 +528,7 @@ int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int
     c.omb1 = omb1; c.b2 = (float)P->beta2; c.omb2 = omb2; c.adam_eps = (float)P->adam_eps; c.sc = sc;
     {
       ProfileScope ps(1, st);
-      IFD_CUDA_TRY(cudaFuncSetAttribute(cloud_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CloudStepSmem)));
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
       cloud_step_kernel<<<2 * B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
       IFD_LAUNCH_CHECK("cloud_step_kernel");
     }
@@ -718,7 +718,7 @@ extern "C" int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const
   c.omb1 = (float)(1.0 - P->beta1); c.b2 = (float)P->beta2; c.omb2 = (float)(1.0 - P->beta2); c.adam_eps = (float)P->adam_eps;
   c.sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
   c.sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
-  IFD_CUDA_TRY(cudaFuncSetAttribute(cloud_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CloudStepSmem)));
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
   cloud_step_kernel<<<2 * B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
   IFD_LAUNCH_CHECK("cloud_step_kernel");
   return IFD_OK;
