@@ -160,7 +160,7 @@ struct PipeCache {
   void* dev = nullptr;
   size_t bytes = 0;
   cudaStream_t h2d = nullptr, run[2] = {nullptr, nullptr}, d2h = nullptr;
-  cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  cudaEvent_t ready[3] = {nullptr, nullptr, nullptr}, done[3] = {nullptr, nullptr, nullptr}, freed[3] = {nullptr, nullptr, nullptr};
 };
 static thread_local PipeCache g_pipe;
 static int ensure_pipe(size_t dev_bytes) {
@@ -169,7 +169,7 @@ static int ensure_pipe(size_t dev_bytes) {
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[0], cudaStreamNonBlocking));
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[1], cudaStreamNonBlocking));
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.d2h, cudaStreamNonBlocking));
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.ready[s], cudaEventDisableTiming));
       IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.done[s], cudaEventDisableTiming));
       IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.freed[s], cudaEventDisableTiming));
@@ -201,7 +201,7 @@ extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* 
   const size_t xyz_al = align_up(xyz_bytes, 256);
   const size_t w_bytes = align_up(nw * sizeof(float), 256);
   const size_t ws_bytes = align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
-  const size_t total = w_bytes + 2 * ws_bytes + 2 * (2 * plane_bytes + xyz_al);
+  const size_t total = w_bytes + 2 * ws_bytes + 3 * (2 * plane_bytes + xyz_al);
   int rc = ensure_pipe(total);
   if (rc) return rc;
   char* base = (char*)g_pipe.dev;
@@ -209,16 +209,16 @@ extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* 
   void* d_ws[2];                            // one workspace per slot: the loops of two batches run side by side
   d_ws[0] = base; base += ws_bytes;
   d_ws[1] = base; base += ws_bytes;
-  float *d_nchw[2], *d_cl[2], *d_xyz[2];
-  for (int s = 0; s < 2; ++s) {
+  float *d_nchw[3], *d_cl[3], *d_xyz[3];    // three buffer slots: two batches run while the third is uploaded / downloaded
+  for (int s = 0; s < 3; ++s) {
     d_nchw[s] = (float*)base; base += plane_bytes;
     d_cl[s] = (float*)base; base += plane_bytes;
     d_xyz[s] = (float*)base; base += xyz_al;
   }
   IFD_CUDA_TRY(cudaMemcpyAsync(d_w, dec_weights_host, nw * sizeof(float), cudaMemcpyHostToDevice, g_pipe.h2d));
   for (int j = 0; j < n_batches; ++j) {
-    const int s = j & 1;
-    if (j >= 2) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.freed[s], 0));       // slot s drained (loop + D2H of j-2)
+    const int s = j % 3, r = j & 1;           // buffer slot, run stream
+    if (j >= 3) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.freed[s], 0));       // slot s drained (loop + D2H of j-3)
     IFD_CUDA_TRY(cudaMemcpyAsync(d_nchw[s], planes_nchw_host[j], (size_t)3 * B * C * R * R * sizeof(float), cudaMemcpyHostToDevice,
                                  g_pipe.h2d));
     IFD_CUDA_TRY(cudaMemcpyAsync(d_xyz[s], xyz_host[j], xyz_bytes, cudaMemcpyHostToDevice, g_pipe.h2d));
@@ -226,11 +226,11 @@ extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* 
     IFD_CUDA_TRY(cudaEventRecord(g_pipe.ready[s], g_pipe.h2d));
     // two run streams: a decode or tail launch occupies 128 of the 148 SMs (one CTA per SM), the other batch's
     // launches fill the rest and every gap between dependent launches
-    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.run[s], g_pipe.ready[s], 0));
-    if ((rc = ifd_convonet_opt(d_cl[s], d_w, d_xyz[s], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr, d_ws[s], ws_bytes,
-                               g_pipe.run[s])))
+    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.run[r], g_pipe.ready[s], 0));
+    if ((rc = ifd_convonet_opt(d_cl[s], d_w, d_xyz[s], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr, d_ws[r], ws_bytes,
+                               g_pipe.run[r])))
       return rc;
-    IFD_CUDA_TRY(cudaEventRecord(g_pipe.done[s], g_pipe.run[s]));
+    IFD_CUDA_TRY(cudaEventRecord(g_pipe.done[s], g_pipe.run[r]));
     IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.done[s], 0));
     IFD_CUDA_TRY(cudaMemcpyAsync(xyz_host[j], d_xyz[s], xyz_bytes, cudaMemcpyDeviceToHost, g_pipe.d2h));
     IFD_CUDA_TRY(cudaEventRecord(g_pipe.freed[s], g_pipe.d2h));
@@ -245,7 +245,7 @@ extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* 
 namespace ifd {
 void release_pipe() {
   if (g_pipe.dev) cudaFree(g_pipe.dev);
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < 3; ++s) {
     if (g_pipe.ready[s]) cudaEventDestroy(g_pipe.ready[s]);
     if (g_pipe.done[s]) cudaEventDestroy(g_pipe.done[s]);
     if (g_pipe.freed[s]) cudaEventDestroy(g_pipe.freed[s]);

@@ -225,7 +225,7 @@ int ifd_convonet_opt_host(const float* planes_nchw_host, const float* dec_weight
                           double* stats_out_host);
 /* The same for a sequence of batches -- the loop of defend_point_cloud over batches (ConvONet/opt_defense.py:272-312):
  * planes_nchw_host[j] / xyz_host[j] are the HOST buffers of batch j (all batches B clouds; pinned memory makes the
- * copies asynchronous).  Two device buffer slots and two run streams: uploads, layout conversions and downloads
+ * copies asynchronous).  Three device buffer slots and two run streams: uploads, layout conversions and downloads
  * overlap the loops, and the loops of two consecutive batches run side by side (one launch fills 128 of the 148 SMs);
  * every batch still pays its own H2D and D2H.  Synchronises before
  * returning.  Results are bit-identical to n_batches calls of ifd_convonet_opt_host. */
