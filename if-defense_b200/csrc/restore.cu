@@ -15,6 +15,7 @@
 #include "decode_v2.cuh"
 #include "cloud_step.cuh"
 #include "decode_v3.cuh"
+#include "decode_v4.cuh"
 #include "topk.cuh"
 
 namespace ifd {
@@ -425,6 +426,19 @@ static int launch_decode_v3(const DecodeArgs& a, const float* wimg, cudaStream_t
   return IFD_OK;
 }
 
+static int launch_decode_v4(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
+  DecodeV3Args v{};
+  v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
+  v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
+  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv;
+  const size_t smem = DecodeV4Smem::bytes(a.n_blocks);
+  if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v4: plane array too large for 32-bit texel indices");
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v4_kernel, smem));
+  convonet_decode_v4_kernel<<<(v.n + kV4Pts - 1) / kV4Pts, kV4Threads, smem, st>>>(v);
+  IFD_LAUNCH_CHECK("convonet_decode_v4_kernel");
+  return IFD_OK;
+}
+
 static int launch_knn_repulsion(const float* xyz, int B, int K, int k, float radius, float h, float eps,
                                 int32_t* idx_out, float* loss_part, long long* acc, int32_t* nbr, bool warm,
                                 cudaStream_t st) {
@@ -679,10 +693,11 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   a.target = (float)P->occ_target;
   // d/dlogit of (mean over B_ref*K) * K: autograd multiplies K, then divides by the element count
   a.ginv = (float)K / (float)((long long)P->B_ref * K);
-  const int dk = P->decode_kernel == 0 ? 3 : P->decode_kernel;
-  if (dk < 1 || dk > 3) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0..3");
-  const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads : (B * K + kV2Pts - 1) / kV2Pts;   // v2, v3: 512-point tiles
-  if (dk == 3) {
+  const int dk = P->decode_kernel == 0 ? 4 : P->decode_kernel;
+  if (dk < 1 || dk > 4) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0..4");
+  const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads          // CTAs of the decode kernel (stat partials)
+                    : dk == 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
+  if (dk >= 3) {
     const int nl = 3 * n_blocks;
     convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg);
     IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
@@ -692,7 +707,8 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
     a.stat_part = stat ? w.dec_part : nullptr;
     {
       ProfileScope ps(0, st);
-      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
+                   : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
       if (rc) return rc;
     }
     if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1, st))) return rc;
@@ -779,8 +795,8 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
   IFD_REQUIRE(workspace, "ifd_convonet_decode_bce_grad: workspace is required");
   if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_decode_bce_grad: workspace too small");
-  const int dk = decode_kernel == 0 ? 3 : decode_kernel;
-  if (dk < 1 || dk > 3) return fail(IFD_ERR_INVALID, "decode_kernel must be 0..3");
+  const int dk = decode_kernel == 0 ? 4 : decode_kernel;
+  if (dk < 1 || dk > 4) return fail(IFD_ERR_INVALID, "decode_kernel must be 0..4");
   cudaStream_t st = as_stream(stream);
   OptWorkspace w = carve_opt_ws(workspace, B, K);
   DecodeArgs a{};
@@ -788,12 +804,13 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(padding);
   a.target = (float)occ_target;
   a.ginv = (float)K / (float)((long long)B_ref * K);
-  if (dk == 3) {
+  if (dk >= 3) {
     const int nl = 3 * n_blocks;
     convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg);
     IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
   }
-  return dk == 1 ? launch_decode(kBce, a, st) : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+  return dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
+                 : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
 }
 
 extern "C" void ifd_test_hook(int key, int value) {

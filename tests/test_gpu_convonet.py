@@ -131,12 +131,14 @@ def test_bce_grad_seam_all_kernels(conv, conv_sd, conv_planes, dec, planes):
     want = p.grad.numpy()
     scale = np.abs(want).max()
     errs = {}
-    for kernel in (1, 2, 3):
-        g = bce_grad(dec, planes, conv["p0"], kernel)
+    grads = {}
+    for kernel in (1, 2, 3, 4):
+        g = grads[kernel] = bce_grad(dec, planes, conv["p0"], kernel)
         errs[kernel] = np.abs(g - want).max() / scale
     print("bce-grad max error / max|grad| per kernel:", errs)
     assert errs[1] < 2e-6 and errs[2] < 2e-6
     assert errs[3] < 2e-5          # 3xTF32 tensor-core path: fp32-class, ~2^-21 per product term
+    assert np.array_equal(grads[3], grads[4])      # v4 = v3's arithmetic in 256-point CTAs, two per SM: the same bits
 
 
 def test_tensor_core_decode_kernel(conv, dec, planes):
