@@ -37,7 +37,7 @@ ALG_BYTES_PER_PT_STEP = 1560                   # 3 planes x 4 te
 ALG_FLOP_PER_PT_STEP = 61952                   # decoder fwd + dgrad
 
 
-def ncu_traffic(kernel="convonet_decode_v3_kernel"):
+def ncu_traffic(kernel="convonet_decode_v4_kernel"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full summary
     (profiles/, cold-cache replay), or None."""
     try:
@@ -246,10 +246,14 @@ def main():
         host.append((pl.numpy(), case.p0.clone().pin_memory().numpy()))
     n_e2e = max(4, min(args.steps, 12))
     seq = [host[j % NB] for j in range(n_e2e)]
-    rest.optimize_points_host_many([h[1] for h in seq[:3]], [h[0] for h in seq[:3]], rep_weight=500., iterations=ITERS, B_ref=B)
+    out_pinned = [torch.empty((B, K, 3), dtype=torch.float32).pin_memory() for _ in range(n_e2e)]     # result buffers (host)
+    out_np = [t.numpy() for t in out_pinned]
+    rest.optimize_points_host_many([h[1] for h in seq[:3]], [h[0] for h in seq[:3]], rep_weight=500., iterations=ITERS, B_ref=B,
+                                   out=out_np[:3])
     barrier()
     t0 = time.perf_counter()
-    outs = rest.optimize_points_host_many([h[1] for h in seq], [h[0] for h in seq], rep_weight=500., iterations=ITERS, B_ref=B)
+    outs = rest.optimize_points_host_many([h[1] for h in seq], [h[0] for h in seq], rep_weight=500., iterations=ITERS, B_ref=B,
+                                          out=out_np)
     if world > 1:                                  # the final gather of the restored clouds of the last batch
         dist.all_gather(gathered, torch.from_numpy(outs[-1]).cuda())
         torch.cuda.synchronize()
@@ -285,7 +289,7 @@ def main():
         alg_bytes = ALG_BYTES_PER_PT_STEP * B * K                     # per decode launch (one Adam step)
         achieved = alg_bytes / (dec_ms * 1e-3) / 1e9
         total_k = sum(kms)
-        roof = {"bound": "hbm", "kernel": "convonet_decode_v3_kernel (plane gather + tcgen05 ResNet-MLP fwd/dgrad)", "achieved": achieved,
+        roof = {"bound": "hbm", "kernel": "convonet_decode_v4_kernel (plane gather + tcgen05 ResNet-MLP fwd/dgrad)", "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                 "traffic_source": "profiles/r01_final_ncu_full_summary.txt (ncu --set full, bytes per launch, cold-cache replay)",
                 "ms_per_launch": dec_ms, "algorithmic_bytes_per_launch": alg_bytes,

@@ -153,11 +153,13 @@ class Restorer:
                                                     C, H, nb, ctypes.byref(P), None), "ifd_convonet_opt_host")
         return x
 
-    def optimize_points_host_many(self, opt_points_list, planes_nchw_list, rep_weight=500., iterations=200, B_ref=None):
+    def optimize_points_host_many(self, opt_points_list, planes_nchw_list, rep_weight=500., iterations=200, B_ref=None,
+                                  out=None):
         """The batch loop of defend_point_cloud (opt_defense.py:272-312) through one pipelined C call
         (ifd_convonet_opt_host_batches): lists of HOST arrays in ([B,K,3] init points, [3,B,C,R,R] planes per batch,
         all batches the same shape; pinned memory -- e.g. torch.Tensor.pin_memory().numpy() -- makes the copies
-        overlap the previous batch's loop), list of restored [B,K,3] arrays out."""
+        overlap the previous batch's loop), list of restored [B,K,3] arrays out.  `out` (optional): a list of float32
+        [B,K,3] arrays in pinned memory to restore into (saves the pinned allocations of this call)."""
         capi.require_gpu()
         if len(opt_points_list) != len(planes_nchw_list):
             raise RuntimeError("need one planes array per batch")
@@ -165,8 +167,17 @@ class Restorer:
             return []
         # in/out point buffers in pinned memory (torch's caching host allocator): a D2H into pageable memory would
         # block the host inside the batch loop and serialise the pipeline
-        keep = [torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).clone().pin_memory() for p in opt_points_list]
-        outs = [t.numpy() for t in keep]
+        if out is None:
+            keep = [torch.from_numpy(np.ascontiguousarray(p, dtype=np.float32)).clone().pin_memory() for p in opt_points_list]
+            outs = [t.numpy() for t in keep]
+        else:
+            if len(out) != len(opt_points_list):
+                raise RuntimeError("need one output array per batch")
+            outs = list(out)
+            for o, p in zip(outs, opt_points_list):
+                if o.dtype != np.float32 or not o.flags["C_CONTIGUOUS"] or o.shape != np.shape(p):
+                    raise RuntimeError("output arrays must be C-contiguous float32 of the input shape")
+                np.copyto(o, p)
         pls = [np.ascontiguousarray(p, dtype=np.float32) for p in planes_nchw_list]
         B, K, _ = outs[0].shape
         _, _, C, R, _ = pls[0].shape
