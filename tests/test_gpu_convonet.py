@@ -227,6 +227,11 @@ def test_reference_signature_and_host_seam(conv, dec, conv_planes):
     assert np.array_equal(host, out)
     many = rest.optimize_points_host_many([conv["p0"]] * 3, [conv["planes_nchw"]] * 3, rep_weight=500., iterations=19)
     assert len(many) == 3 and all(np.array_equal(m, host) for m in many)      # pipelined batch loop: same bits
+    pinned = [torch.empty(conv["p0"].shape, dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
+    into = rest.optimize_points_host_many([conv["p0"]] * 2, [conv["planes_nchw"]] * 2, rep_weight=500., iterations=19, out=pinned)
+    assert all(a is b for a, b in zip(into, pinned)) and all(np.array_equal(m, host) for m in pinned)
+    with pytest.raises(RuntimeError, match="one output array per batch"):
+        rest.optimize_points_host_many([conv["p0"]] * 2, [conv["planes_nchw"]] * 2, out=pinned[:1])
     out0 = rest.optimize_points(dev(conv["p0"]), None, c, rep_weight=0., iterations=19)     # rep_weight == 0 branch
     assert np.isfinite(out0).all() and not np.array_equal(out0, out)
 
