@@ -47,6 +47,12 @@ SIGNATURES = {
     "ifd_plane_bins": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
     "ifd_scatter_max_gather": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "ifd_scatter_mean_cl": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "ifd_mc_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
+    "ifd_mc_count": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _c_d, _vp, _c_sz,
+                              ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), _vp]),
+    "ifd_mc_emit": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _c_d, _c_int, _c_d, _vp, _c_sz, _vp, _vp, _vp]),
+    "ifd_sample_surface_workspace_bytes": (_c_sz, [ctypes.c_longlong]),
+    "ifd_sample_surface": (_c_int, [_vp, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp, _c_int, _vp, _vp, _vp, _c_sz, _vp]),
     "ifd_opt_params_default": (None, [ctypes.POINTER(OptParams)]),
     "ifd_convonet_opt_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "ifd_convonet_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

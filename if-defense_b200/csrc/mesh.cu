@@ -1,0 +1,531 @@
+// mesh.cu -- the ONet-Mesh tail on the device: marching cubes over the occupancy lattice and area-weighted surface
+// sampling.
+//
+// Reference: ONet/im2mesh/onet/generation.py:165-186 (extract_mesh: pad with -1e6, libmcubes.marching_cubes, undo the
+// half-cell shift and the padding, scale to the box), ONet/im2mesh/utils/libmcubes/marchingcubes.h:23-189 (the
+// sequential algorithm and its vertex sharing), marchingcubes.cpp:288-326 (vertex placement),
+// ONet/remesh_defense.py:151-158 (trimesh.sample.sample_surface of the mesh).
+//
+// The reference walks the cells in (i, j, k) order, appends a vertex the first time an edge is met and remembers the
+// indices of the three edges at a cell's far corner for its neighbours.  The same numbering falls out of a prefix sum:
+// a cell "creates" the vertices of its far-corner edges 6, 5, 10 (and, on the i/j/k == 0 faces, of the edges nobody
+// before it could have created -- duplicates included, as in the reference), so
+//     index(vertex) = (# vertices created by earlier cells) + (position inside the cell's creation order)
+// and a neighbour's index is a lookup of that neighbour's prefix.  Output order and every bit of the coordinates
+// (fp64, the reference's association, no FMA contraction) equal the sequential code; HBM-bound streaming passes.
+#include "common.cuh"
+
+namespace ifd {
+
+#include "mc_tables.inc"
+__device__ const unsigned long long kMcTri[256] = {IFD_MC_TRI_WORDS};
+__device__ const unsigned short kMcEdges[256] = {IFD_MC_EDGE_MASKS};
+
+constexpr int kMcBlock = 1024;  // cells per scan block
+
+struct McGrid {
+  const void* vol;
+  int is_f64;
+  int nx, ny, nz;       // dimensions of the array that is handed in
+  int pad;              // 1: a one-voxel border of pad_value is added around it (np.pad(..., 1, 'constant'))
+  double pad_value, iso;
+  int px, py, pz;       // dimensions after padding
+  int cx, cy, cz;       // cells
+  long long ncells;
+};
+
+__device__ __forceinline__ double mc_value(const McGrid& g, int x, int y, int z) {
+  x -= g.pad;
+  y -= g.pad;
+  z -= g.pad;
+  if (x < 0 || y < 0 || z < 0 || x >= g.nx || y >= g.ny || z >= g.nz) return g.pad_value;
+  const size_t o = ((size_t)x * g.ny + y) * g.nz + z;
+  return g.is_f64 ? static_cast<const double*>(g.vol)[o] : (double)static_cast<const float*>(g.vol)[o];
+}
+
+__device__ __forceinline__ void mc_corners(const McGrid& g, int i, int j, int k, double v[8]) {
+  v[0] = mc_value(g, i, j, k);
+  v[1] = mc_value(g, i + 1, j, k);
+  v[2] = mc_value(g, i + 1, j + 1, k);
+  v[3] = mc_value(g, i, j + 1, k);
+  v[4] = mc_value(g, i, j, k + 1);
+  v[5] = mc_value(g, i + 1, j, k + 1);
+  v[6] = mc_value(g, i + 1, j + 1, k + 1);
+  v[7] = mc_value(g, i, j + 1, k + 1);
+}
+
+// edges whose vertex THIS cell appends (marchingcubes.h:69-178): always 6, 5, 10; the others only on the low faces
+__device__ __forceinline__ unsigned mc_created_mask(int i, int j, int k) {
+  unsigned m = 0x040u | 0x020u | 0x400u;
+  if (j == 0 || k == 0) m |= 0x001u;
+  if (k == 0) m |= 0x002u | 0x004u;
+  if (i == 0 || k == 0) m |= 0x008u;
+  if (j == 0) m |= 0x010u | 0x200u;
+  if (i == 0) m |= 0x080u | 0x800u;
+  if (i == 0 || j == 0) m |= 0x100u;
+  return m;
+}
+
+__device__ __forceinline__ int mc_tri_count(unsigned long long w) {
+  int n = 0;
+#pragma unroll
+  for (int s = 0; s < 15; ++s) n += ((w >> (4 * s)) & 0xF) != 0xF;      // entries are contiguous from nibble 0
+  return n;
+}
+
+// pass 1: case index and counts per cell, sums per block of kMcBlock cells (low 32 bits vertices, high 32 indices)
+__global__ void __launch_bounds__(kMcBlock) mc_classify_kernel(McGrid g, uint8_t* __restrict__ cases,
+                                                               uint8_t* __restrict__ counts,
+                                                               unsigned long long* __restrict__ block_sums) {
+  __shared__ unsigned long long warp_sums[kMcBlock / 32];
+  const long long c = (long long)blockIdx.x * kMcBlock + threadIdx.x;
+  unsigned long long mine = 0;
+  if (c < g.ncells) {
+    const int k = (int)(c % g.cz), j = (int)((c / g.cz) % g.cy), i = (int)(c / ((long long)g.cz * g.cy));
+    double v[8];
+    mc_corners(g, i, j, k, v);
+    unsigned ci = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) ci |= (v[m] <= g.iso ? 1u : 0u) << m;
+    const int nv = __popc((unsigned)kMcEdges[ci] & mc_created_mask(i, j, k));
+    const int ni = mc_tri_count(kMcTri[ci]);
+    cases[c] = (uint8_t)ci;
+    counts[c] = (uint8_t)(nv | (ni << 4));
+    mine = (unsigned long long)nv | ((unsigned long long)ni << 32);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = mine;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long s = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+  }
+}
+
+// pass 2: exclusive scan of the block sums in place (one CTA; a few thousand entries), totals to totals[0]
+__global__ void __launch_bounds__(1024) mc_scan_blocks_kernel(unsigned long long* __restrict__ block_sums, int n,
+                                                              unsigned long long* __restrict__ totals) {
+  __shared__ unsigned long long warp_sums[32];
+  __shared__ unsigned long long carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int e = base + threadIdx.x;
+    const unsigned long long x = e < n ? block_sums[e] : 0;
+    unsigned long long inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned long long w = warp_sums[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      warp_sums[threadIdx.x] = w;     // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned long long before = carry_s + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0);
+    if (e < n) block_sums[e] = before + inc - x;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = before + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) totals[0] = carry_s;
+}
+
+// pass 3: per-cell bases (vertices created / indices emitted by all earlier cells)
+__global__ void __launch_bounds__(kMcBlock) mc_bases_kernel(long long ncells, const uint8_t* __restrict__ counts,
+                                                            const unsigned long long* __restrict__ block_sums,
+                                                            uint32_t* __restrict__ vbase, uint32_t* __restrict__ ibase) {
+  __shared__ unsigned long long warp_sums[kMcBlock / 32];
+  const long long c = (long long)blockIdx.x * kMcBlock + threadIdx.x;
+  const unsigned cnt = c < ncells ? counts[c] : 0;
+  const unsigned long long x = (unsigned long long)(cnt & 15) | ((unsigned long long)(cnt >> 4) << 32);
+  unsigned long long inc = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long w = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+      if (threadIdx.x >= o) w += y;
+    }
+    warp_sums[threadIdx.x] = w;
+  }
+  __syncthreads();
+  const unsigned long long ex = block_sums[blockIdx.x] + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0) + inc - x;
+  if (c < ncells) {
+    vbase[c] = (uint32_t)(ex & 0xffffffffull);
+    ibase[c] = (uint32_t)(ex >> 32);
+  }
+}
+
+// marchingcubes.cpp:288-295: (x2 - x1) * (iso - f1) / (f2 - f1) + x1, midpoint when f1 == f2; every operation rounded
+__device__ __forceinline__ double mc_interp(double iso, double f1, double f2, double x1, double x2) {
+  if (f2 == f1) return __ddiv_rn(__dadd_rn(x2, x1), 2.0);
+  return __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(x2, x1), __dsub_rn(iso, f1)), __dsub_rn(f2, f1)), x1);
+}
+
+struct McXform {   // generation.py:177-183: v -= 0.5; v -= 1; v /= (n - 1); v = box * (v - 0.5)   (numpy fp64, one op each)
+  int on;
+  double dx, dy, dz, box;
+};
+
+__device__ __forceinline__ double mc_xform1(double v, double d, double box) {
+  v = __dsub_rn(v, 0.5);
+  v = __dsub_rn(v, 1.0);
+  v = __ddiv_rn(v, d);
+  return __dmul_rn(box, __dsub_rn(v, 0.5));
+}
+
+// pass 4: vertices and triangle indices
+__global__ void __launch_bounds__(256) mc_emit_kernel(McGrid g, McXform xf, const uint8_t* __restrict__ cases,
+                                                      const uint32_t* __restrict__ vbase, const uint32_t* __restrict__ ibase,
+                                                      double* __restrict__ verts, long long* __restrict__ indices) {
+  const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (c >= g.ncells) return;
+  const unsigned ci = cases[c];
+  const unsigned edges = kMcEdges[ci];
+  if (edges == 0) return;
+  const int k = (int)(c % g.cz), j = (int)((c / g.cz) % g.cy), i = (int)(c / ((long long)g.cz * g.cy));
+  double v[8];
+  mc_corners(g, i, j, k, v);
+  // marchingcubes.h:40-55 with lower = 0, upper = n - 1: dx = 1, x = 0 + 1 * i + 1 / 2
+  const double x = (double)i + 0.5, xd = (double)(i + 1) + 0.5;
+  const double y = (double)j + 0.5, yd = (double)(j + 1) + 0.5;
+  const double z = (double)k + 0.5, zd = (double)(k + 1) + 0.5;
+  const unsigned created = edges & mc_created_mask(i, j, k);
+  long long idx[12];
+  uint32_t next = vbase[c];
+  const long long sz = 1, sy = g.cz, sx = (long long)g.cz * g.cy;   // cell strides
+  // index of slot s (0: edge 6, 1: edge 5, 2: edge 10) of the cell at linear index n
+  auto shared_slot = [&](long long n, int s) -> long long {
+    const unsigned en = kMcEdges[cases[n]];
+    const unsigned before = s == 0 ? 0u : (s == 1 ? (en & 0x040u) : (en & 0x060u));
+    return (long long)vbase[n] + __popc(before);
+  };
+  auto put = [&](int e, double px, double py, double pz) {
+    idx[e] = next;
+    double* o = verts + (size_t)next * 3;
+    if (xf.on) {
+      px = mc_xform1(px, xf.dx, xf.box);
+      py = mc_xform1(py, xf.dy, xf.box);
+      pz = mc_xform1(pz, xf.dz, xf.box);
+    }
+    o[0] = px;
+    o[1] = py;
+    o[2] = pz;
+    ++next;
+  };
+  // creation order of marchingcubes.h: 6, 5, 10, then 0, 1, 2, 3, 4, 7, 8, 9, 11
+  if (edges & 0x040u) put(6, mc_interp(g.iso, v[6], v[7], xd, x), yd, zd);
+  if (edges & 0x020u) put(5, xd, mc_interp(g.iso, v[5], v[6], y, yd), zd);
+  if (edges & 0x400u) put(10, xd, __dadd_rn(y, 1.0), mc_interp(g.iso, v[2], v[6], z, zd));     // "y + dx" (:89)
+  if (edges & 0x001u) {
+    if (created & 0x001u) put(0, mc_interp(g.iso, v[0], v[1], x, xd), y, z);
+    else idx[0] = shared_slot(c - sy - sz, 0);
+  }
+  if (edges & 0x002u) {
+    if (created & 0x002u) put(1, xd, mc_interp(g.iso, v[1], v[2], y, yd), z);
+    else idx[1] = shared_slot(c - sz, 1);
+  }
+  if (edges & 0x004u) {
+    if (created & 0x004u) put(2, mc_interp(g.iso, v[2], v[3], xd, x), yd, z);
+    else idx[2] = shared_slot(c - sz, 0);
+  }
+  if (edges & 0x008u) {
+    if (created & 0x008u) put(3, x, mc_interp(g.iso, v[3], v[0], yd, y), z);
+    else idx[3] = shared_slot(c - sx - sz, 1);
+  }
+  if (edges & 0x010u) {
+    if (created & 0x010u) put(4, mc_interp(g.iso, v[4], v[5], x, xd), y, zd);
+    else idx[4] = shared_slot(c - sy, 0);
+  }
+  if (edges & 0x080u) {
+    if (created & 0x080u) put(7, x, mc_interp(g.iso, v[7], v[4], yd, y), zd);
+    else idx[7] = shared_slot(c - sx, 1);
+  }
+  if (edges & 0x100u) {
+    if (created & 0x100u) put(8, x, y, mc_interp(g.iso, v[0], v[4], z, zd));
+    else idx[8] = shared_slot(c - sx - sy, 2);
+  }
+  if (edges & 0x200u) {
+    if (created & 0x200u) put(9, xd, y, mc_interp(g.iso, v[1], v[5], z, zd));
+    else idx[9] = shared_slot(c - sy, 2);
+  }
+  if (edges & 0x800u) {
+    if (created & 0x800u) put(11, x, yd, mc_interp(g.iso, v[3], v[7], z, zd));
+    else idx[11] = shared_slot(c - sx, 2);
+  }
+  const unsigned long long w = kMcTri[ci];
+  long long* o = indices + ibase[c];
+#pragma unroll
+  for (int s = 0; s < 15; ++s) {
+    const int e = (int)((w >> (4 * s)) & 0xF);
+    if (e == 0xF) break;
+    long long val = 0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+      if (q == e) val = idx[q];       // keeps idx[] in registers
+    o[s] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// area-weighted surface sampling (trimesh 3.7.7 sample.sample_surface; the uniform numbers are the caller's)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tri_corner(const double* __restrict__ verts, long long v, double p[3]) {
+  p[0] = verts[v * 3 + 0];
+  p[1] = verts[v * 3 + 1];
+  p[2] = verts[v * 3 + 2];
+}
+
+// area = |cross(b - a, c - a)| / 2, chunk sums for the scan
+constexpr int kAreaBlock = 1024;
+__global__ void __launch_bounds__(kAreaBlock) face_area_kernel(const double* __restrict__ verts, const long long* __restrict__ faces,
+                                                               long long nf, double* __restrict__ area,
+                                                               double* __restrict__ block_sums) {
+  __shared__ double warp_sums[kAreaBlock / 32];
+  const long long f = (long long)blockIdx.x * kAreaBlock + threadIdx.x;
+  double a = 0.0;
+  if (f < nf) {
+    double p0[3], p1[3], p2[3];
+    tri_corner(verts, faces[f * 3 + 0], p0);
+    tri_corner(verts, faces[f * 3 + 1], p1);
+    tri_corner(verts, faces[f * 3 + 2], p2);
+    const double ux = p1[0] - p0[0], uy = p1[1] - p0[1], uz = p1[2] - p0[2];
+    const double vx = p2[0] - p0[0], vy = p2[1] - p0[1], vz = p2[2] - p0[2];
+    const double cx = __dsub_rn(__dmul_rn(uy, vz), __dmul_rn(uz, vy));
+    const double cy = __dsub_rn(__dmul_rn(uz, vx), __dmul_rn(ux, vz));
+    const double cz = __dsub_rn(__dmul_rn(ux, vy), __dmul_rn(uy, vx));
+    a = __dmul_rn(sqrt(__dadd_rn(__dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy)), __dmul_rn(cz, cz))), 0.5);
+    area[f] = a;
+  }
+  // block-inclusive scan kept in `area`, block totals out
+  double inc = a;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double w = warp_sums[threadIdx.x];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double y = __shfl_up_sync(0xffffffffu, w, o);
+      if (threadIdx.x >= o) w += y;
+    }
+    warp_sums[threadIdx.x] = w;
+  }
+  __syncthreads();
+  inc += threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0.0;
+  if (f < nf) area[f] = inc;
+  if (threadIdx.x == kAreaBlock - 1) block_sums[blockIdx.x] = inc;
+}
+
+// exclusive scan of the block totals in place by one thread per 32 ... the list is short (nf / 1024): sequential
+__global__ void area_scan_blocks_kernel(double* __restrict__ block_sums, int n, double* __restrict__ total) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double run = 0.0;
+  for (int b = 0; b < n; ++b) {
+    const double x = block_sums[b];
+    block_sums[b] = run;
+    run += x;
+  }
+  *total = run;
+}
+
+__global__ void area_add_base_kernel(double* __restrict__ area_cum, long long nf, const double* __restrict__ block_sums) {
+  const long long f = (long long)blockIdx.x * kAreaBlock + threadIdx.x;
+  if (f < nf) area_cum[f] += block_sums[blockIdx.x];
+}
+
+// one sample per thread: face = searchsorted(cum, u0 * total) (left), point = origin + l0 * e0 + l1 * e1 with the pair
+// (l0, l1) folded back into the triangle when l0 + l1 > 1
+__global__ void sample_surface_kernel(const double* __restrict__ verts, const long long* __restrict__ faces, long long nf,
+                                      const double* __restrict__ cum, const double* __restrict__ total,
+                                      const double* __restrict__ u, int count, double* __restrict__ out,
+                                      long long* __restrict__ face_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= count) return;
+  const double pick = __dmul_rn(u[(size_t)s * 3 + 0], *total);
+  long long lo = 0, hi = nf;               // first f with cum[f] >= pick
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (cum[mid] < pick) lo = mid + 1;
+    else hi = mid;
+  }
+  const long long f = lo < nf ? lo : nf - 1;
+  double p0[3], p1[3], p2[3];
+  tri_corner(verts, faces[f * 3 + 0], p0);
+  tri_corner(verts, faces[f * 3 + 1], p1);
+  tri_corner(verts, faces[f * 3 + 2], p2);
+  double l0 = u[(size_t)s * 3 + 1], l1 = u[(size_t)s * 3 + 2];
+  if (__dadd_rn(l0, l1) > 1.0) {
+    l0 = __dsub_rn(l0, 1.0);
+    l1 = __dsub_rn(l1, 1.0);
+  }
+  l0 = fabs(l0);
+  l1 = fabs(l1);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double e0 = __dsub_rn(p1[d], p0[d]), e1 = __dsub_rn(p2[d], p0[d]);
+    out[(size_t)s * 3 + d] = __dadd_rn(__dadd_rn(__dmul_rn(e0, l0), __dmul_rn(e1, l1)), p0[d]);
+  }
+  if (face_out) face_out[s] = f;
+}
+
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
+struct McWorkspace {
+  uint8_t *cases, *counts;
+  uint32_t *vbase, *ibase;
+  unsigned long long *block_sums, *totals;
+  int nblocks;
+  size_t bytes;
+};
+
+static McWorkspace mc_carve(void* base, long long ncells) {
+  McWorkspace w;
+  w.nblocks = (int)((ncells + kMcBlock - 1) / kMcBlock);
+  size_t off = 0;
+  auto take = [&](size_t b) {
+    char* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align256(b);
+    return p;
+  };
+  w.cases = reinterpret_cast<uint8_t*>(take((size_t)ncells));
+  w.counts = reinterpret_cast<uint8_t*>(take((size_t)ncells));
+  w.vbase = reinterpret_cast<uint32_t*>(take((size_t)ncells * 4));
+  w.ibase = reinterpret_cast<uint32_t*>(take((size_t)ncells * 4));
+  w.block_sums = reinterpret_cast<unsigned long long*>(take((size_t)w.nblocks * 8));
+  w.totals = reinterpret_cast<unsigned long long*>(take(8));
+  w.bytes = off;
+  return w;
+}
+
+static int mc_grid(McGrid* g, const void* vol, int dtype, int nx, int ny, int nz, int pad, double pad_value, double iso) {
+  IFD_REQUIRE(nx >= 1 && ny >= 1 && nz >= 1 && (pad == 0 || pad == 1) && (dtype == 0 || dtype == 1), "marching cubes: bad arguments");
+  g->vol = vol;
+  g->is_f64 = dtype;
+  g->nx = nx;
+  g->ny = ny;
+  g->nz = nz;
+  g->pad = pad;
+  g->pad_value = pad_value;
+  g->iso = iso;
+  g->px = nx + 2 * pad;
+  g->py = ny + 2 * pad;
+  g->pz = nz + 2 * pad;
+  g->cx = g->px - 1;
+  g->cy = g->py - 1;
+  g->cz = g->pz - 1;
+  g->ncells = (long long)g->cx * g->cy * g->cz;
+  IFD_REQUIRE(g->ncells < (1ll << 31), "marching cubes: lattice too large (2^31 cells)");
+  return IFD_OK;
+}
+
+}  // namespace ifd
+
+using namespace ifd;
+
+extern "C" size_t ifd_mc_workspace_bytes(int nx, int ny, int nz, int pad) {
+  McGrid g;
+  if (mc_grid(&g, nullptr, 0, nx, ny, nz, pad, 0.0, 0.0) != IFD_OK) return 0;
+  return mc_carve(nullptr, g.ncells > 0 ? g.ncells : 1).bytes;
+}
+
+extern "C" int ifd_mc_count(const void* volume, int dtype, int nx, int ny, int nz, int pad, double pad_value, double isovalue,
+                            void* workspace, size_t workspace_bytes, long long* n_verts, long long* n_faces, ifd_stream_t stream) {
+  IFD_REQUIRE(volume && workspace && n_verts && n_faces, "ifd_mc_count: null argument");
+  McGrid g;
+  int rc = mc_grid(&g, volume, dtype, nx, ny, nz, pad, pad_value, isovalue);
+  if (rc) return rc;
+  *n_verts = *n_faces = 0;
+  if (g.ncells <= 0) return IFD_OK;
+  McWorkspace w = mc_carve(workspace, g.ncells);
+  IFD_REQUIRE(workspace_bytes >= w.bytes, "ifd_mc_count: workspace too small (ifd_mc_workspace_bytes)");
+  cudaStream_t s = as_stream(stream);
+  mc_classify_kernel<<<w.nblocks, kMcBlock, 0, s>>>(g, w.cases, w.counts, w.block_sums);
+  IFD_LAUNCH_CHECK("mc_classify_kernel");
+  mc_scan_blocks_kernel<<<1, 1024, 0, s>>>(w.block_sums, w.nblocks, w.totals);
+  IFD_LAUNCH_CHECK("mc_scan_blocks_kernel");
+  mc_bases_kernel<<<w.nblocks, kMcBlock, 0, s>>>(g.ncells, w.counts, w.block_sums, w.vbase, w.ibase);
+  IFD_LAUNCH_CHECK("mc_bases_kernel");
+  unsigned long long tot = 0;
+  IFD_CUDA_TRY(cudaMemcpyAsync(&tot, w.totals, 8, cudaMemcpyDeviceToHost, s));
+  IFD_CUDA_TRY(cudaStreamSynchronize(s));
+  *n_verts = (long long)(tot & 0xffffffffull);
+  *n_faces = (long long)(tot >> 32) / 3;
+  return IFD_OK;
+}
+
+extern "C" int ifd_mc_emit(const void* volume, int dtype, int nx, int ny, int nz, int pad, double pad_value, double isovalue,
+                           int to_box, double box_size, const void* workspace, size_t workspace_bytes, double* verts_out,
+                           long long* faces_out, ifd_stream_t stream) {
+  IFD_REQUIRE(volume && workspace && verts_out && faces_out, "ifd_mc_emit: null argument");
+  McGrid g;
+  int rc = mc_grid(&g, volume, dtype, nx, ny, nz, pad, pad_value, isovalue);
+  if (rc) return rc;
+  if (g.ncells <= 0) return IFD_OK;
+  McWorkspace w = mc_carve(const_cast<void*>(workspace), g.ncells);
+  IFD_REQUIRE(workspace_bytes >= w.bytes, "ifd_mc_emit: workspace too small (ifd_mc_workspace_bytes)");
+  McXform xf;
+  xf.on = to_box ? 1 : 0;
+  // generation.py:181: divide by (n - 1) of the UNPADDED lattice
+  xf.dx = (double)(g.px - 2 - 1);
+  xf.dy = (double)(g.py - 2 - 1);
+  xf.dz = (double)(g.pz - 2 - 1);
+  xf.box = box_size;
+  IFD_REQUIRE(!to_box || (xf.dx > 0 && xf.dy > 0 && xf.dz > 0), "ifd_mc_emit: to_box needs an unpadded lattice of >= 2 points per axis");
+  const int blocks = (int)((g.ncells + 255) / 256);
+  mc_emit_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, xf, w.cases, w.vbase, w.ibase, verts_out, faces_out);
+  IFD_LAUNCH_CHECK("mc_emit_kernel");
+  return IFD_OK;
+}
+
+extern "C" size_t ifd_sample_surface_workspace_bytes(long long n_faces) {
+  const long long nb = (n_faces + kAreaBlock - 1) / kAreaBlock;
+  return align256((size_t)(n_faces > 0 ? n_faces : 1) * 8) + align256((size_t)(nb > 0 ? nb : 1) * 8) + 256;
+}
+
+extern "C" int ifd_sample_surface(const double* verts, long long n_verts, const long long* faces, long long n_faces,
+                                  const double* uniforms, int count, double* xyz_out, long long* face_out, void* workspace,
+                                  size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_REQUIRE(verts && faces && uniforms && xyz_out && workspace && count > 0 && n_verts > 0, "ifd_sample_surface: bad arguments");
+  // the reference's sample_surface raises IndexError on a mesh without faces (remesh_defense.py:160-171 catches it)
+  if (n_faces <= 0) return fail(IFD_ERR_INVALID, "ifd_sample_surface: the mesh has no faces");
+  IFD_REQUIRE(workspace_bytes >= ifd_sample_surface_workspace_bytes(n_faces), "ifd_sample_surface: workspace too small");
+  const int nb = (int)((n_faces + kAreaBlock - 1) / kAreaBlock);
+  char* base = static_cast<char*>(workspace);
+  double* cum = reinterpret_cast<double*>(base);
+  double* bsum = reinterpret_cast<double*>(base + align256((size_t)n_faces * 8));
+  double* total = reinterpret_cast<double*>(base + align256((size_t)n_faces * 8) + align256((size_t)nb * 8));
+  cudaStream_t s = as_stream(stream);
+  face_area_kernel<<<nb, kAreaBlock, 0, s>>>(verts, faces, n_faces, cum, bsum);
+  IFD_LAUNCH_CHECK("face_area_kernel");
+  area_scan_blocks_kernel<<<1, 32, 0, s>>>(bsum, nb, total);
+  IFD_LAUNCH_CHECK("area_scan_blocks_kernel");
+  area_add_base_kernel<<<nb, kAreaBlock, 0, s>>>(cum, n_faces, bsum);
+  IFD_LAUNCH_CHECK("area_add_base_kernel");
+  sample_surface_kernel<<<(count + 127) / 128, 128, 0, s>>>(verts, faces, n_faces, cum, total, uniforms, count, xyz_out, face_out);
+  IFD_LAUNCH_CHECK("sample_surface_kernel");
+  return IFD_OK;
+}

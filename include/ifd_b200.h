@@ -270,6 +270,37 @@ int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz, float* ad
                  const ifd_opt_params* params, double* stats_out, void* workspace, size_t workspace_bytes,
                  ifd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ONet-Mesh tail: marching cubes over the occupancy lattice, surface sampling
+ * ---------------------------------------------------------------------------------------------- */
+
+/* libmcubes.marching_cubes(volume, isovalue) (ONet/im2mesh/utils/libmcubes/mcubes.pyx:20-25 -> pywrapper.cpp:90-127 ->
+ * marchingcubes.h:23-189) on the device, in two calls because the output sizes are data dependent.
+ * volume: device array [nx][ny][nz], dtype 0 = float32, 1 = float64 (the reference hands float64 in; float32 values
+ * are widened exactly).  pad = 1 adds the one-voxel border of pad_value that Generator3D.extract_mesh adds with np.pad
+ * (ONet/im2mesh/onet/generation.py:172-173: -1e6) without materialising it.  Vertices [V][3] float64 and faces [F][3]
+ * int64 come out in the reference's order with the reference's bits.
+ * ifd_mc_count fills the workspace (ifd_mc_workspace_bytes) and synchronises `stream` to return the counts to the
+ * host; ifd_mc_emit then needs the same arguments and the untouched workspace.  to_box != 0 applies
+ * generation.py:177-183 to the vertices (-0.5, -1, / (n - 1) of the unpadded lattice, box_size * (v - 0.5)). */
+size_t ifd_mc_workspace_bytes(int nx, int ny, int nz, int pad);
+int ifd_mc_count(const void* volume, int dtype, int nx, int ny, int nz, int pad, double pad_value, double isovalue,
+                 void* workspace, size_t workspace_bytes, long long* n_verts_host, long long* n_faces_host,
+                 ifd_stream_t stream);
+int ifd_mc_emit(const void* volume, int dtype, int nx, int ny, int nz, int pad, double pad_value, double isovalue,
+                int to_box, double box_size, const void* workspace, size_t workspace_bytes, double* verts_out,
+                long long* faces_out, ifd_stream_t stream);
+
+/* trimesh.sample.sample_surface(mesh, count) (un-vendored trimesh 3.7.7; call site ONet/remesh_defense.py:157) with
+ * the random numbers handed in (the library never draws any): uniforms [count][3] in [0, 1): column 0 picks the face
+ * by cumulative area (searchsorted, left), columns 1-2 are the two edge lengths, reflected into the triangle when their
+ * sum exceeds 1.  verts [V][3] float64, faces [F][3] int64 (device); xyz_out [count][3] float64; face_out [count] or
+ * null.  A mesh without faces is IFD_ERR_INVALID (the reference's IndexError, remesh_defense.py:160). */
+size_t ifd_sample_surface_workspace_bytes(long long n_faces);
+int ifd_sample_surface(const double* verts, long long n_verts, const long long* faces, long long n_faces,
+                       const double* uniforms, int count, double* xyz_out, long long* face_out, void* workspace,
+                       size_t workspace_bytes, ifd_stream_t stream);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 long long ifd_launch_count(int reset);
 

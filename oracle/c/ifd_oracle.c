@@ -161,3 +161,85 @@ void ifdo_sor(const float* xyz, int B, int K, int k, double alpha, uint8_t* keep
   }
   free(row); free(xx); free(val);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Marching cubes as libmcubes.marching_cubes(volume, isovalue) runs it
+ * (ONet/im2mesh/utils/libmcubes/marchingcubes.h:23-189, marchingcubes.cpp:288-326, pywrapper.cpp:90-107):
+ * cells in (i, j, k) order; a vertex sits at cell-centre-shifted coordinates (i + 0.5, ...), is appended the first
+ * time its edge is met and is found again through the cell that owns it (the cell whose far corner the edge touches);
+ * on the i/j/k == 0 faces that owner does not exist and the vertex is appended again.  Restated data-driven: one
+ * descriptor per cube edge.  Case tables: derived from the reference's behaviour (tools/gen_mc_tables.py).
+ * Call with verts == NULL to count.  Returns the number of vertices; *n_idx = number of triangle indices.
+ * ------------------------------------------------------------------------------------------------ */
+#include "../../if-defense_b200/csrc/mc_tables.inc"
+static const unsigned long long mc_tri_words[256] = {IFD_MC_TRI_WORDS};
+static const unsigned short mc_edge_masks[256] = {IFD_MC_EDGE_MASKS};
+
+typedef struct {
+  int edge, ca, cb;      /* cube edge; corners of f1 and f2 in the interpolation */
+  int oi, oj, ok, slot;  /* owning neighbour (offset, <= 0) and which of its three far-corner edges; slot < 0: own edge */
+} mc_edge_t;
+
+static const int mc_corner[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+/* in the order the reference appends vertices inside one cell */
+static const mc_edge_t mc_edges[12] = {
+    {6, 6, 7, 0, 0, 0, -1},  {5, 5, 6, 0, 0, 0, -2},   {10, 2, 6, 0, 0, 0, -3}, {0, 0, 1, 0, -1, -1, 0},
+    {1, 1, 2, 0, 0, -1, 1},  {2, 2, 3, 0, 0, -1, 0},   {3, 3, 0, -1, 0, -1, 1}, {4, 4, 5, 0, -1, 0, 0},
+    {7, 7, 4, -1, 0, 0, 1},  {8, 0, 4, -1, -1, 0, 2},  {9, 1, 5, 0, -1, 0, 2},  {11, 3, 7, -1, 0, 0, 2}};
+
+long long ifdo_marching_cubes(const double* vol, int nx, int ny, int nz, double iso, double* verts, long long* idx,
+                              long long* n_idx) {
+  const int cx = nx - 1, cy = ny - 1, cz = nz - 1;
+  long long nv = 0, ni = 0;
+  if (cx <= 0 || cy <= 0 || cz <= 0) { *n_idx = 0; return 0; }
+  long long* own = (long long*)malloc((size_t)cx * cy * cz * 3 * sizeof(long long));
+  for (int i = 0; i < cx; ++i)
+    for (int j = 0; j < cy; ++j)
+      for (int k = 0; k < cz; ++k) {
+        double v[8];
+        unsigned c = 0;
+        for (int m = 0; m < 8; ++m) {
+          v[m] = vol[((size_t)(i + mc_corner[m][0]) * ny + (j + mc_corner[m][1])) * nz + (k + mc_corner[m][2])];
+          if (v[m] <= iso) c |= 1u << m;
+        }
+        const unsigned mask = mc_edge_masks[c];
+        long long at[12];
+        for (int d = 0; d < 12; ++d) {
+          const mc_edge_t* e = &mc_edges[d];
+          if (!(mask >> e->edge & 1)) continue;
+          const int oi = i + e->oi, oj = j + e->oj, ok = k + e->ok;
+          if (e->slot >= 0 && oi >= 0 && oj >= 0 && ok >= 0) {
+            at[e->edge] = own[(((size_t)oi * cy + oj) * cz + ok) * 3 + e->slot];
+            continue;
+          }
+          at[e->edge] = nv;
+          if (e->slot < 0) own[(((size_t)i * cy + j) * cz + k) * 3 + (-e->slot - 1)] = nv;
+          if (verts) {
+            const int ijk[3] = {i, j, k};
+            double p[3];
+            int axis = 0;
+            for (int a = 0; a < 3; ++a) {
+              p[a] = (double)(ijk[a] + mc_corner[e->ca][a]) + 0.5;
+              if (mc_corner[e->ca][a] != mc_corner[e->cb][a]) axis = a;
+            }
+            const double x1 = p[axis], x2 = (double)(ijk[axis] + mc_corner[e->cb][axis]) + 0.5;
+            const double f1 = v[e->ca], f2 = v[e->cb];
+            p[axis] = f2 == f1 ? (x2 + x1) / 2 : (x2 - x1) * (iso - f1) / (f2 - f1) + x1;
+            verts[nv * 3 + 0] = p[0];
+            verts[nv * 3 + 1] = p[1];
+            verts[nv * 3 + 2] = p[2];
+          }
+          ++nv;
+        }
+        const unsigned long long w = mc_tri_words[c];
+        for (int s = 0; s < 15; ++s) {
+          const int e = (int)(w >> (4 * s) & 0xF);
+          if (e == 0xF) break;
+          if (idx) idx[ni] = at[e];
+          ++ni;
+        }
+      }
+  free(own);
+  *n_idx = ni;
+  return nv;
+}

@@ -62,3 +62,52 @@ def sor(xyz, k=2, alpha=1.1):
     val = np.empty((B, K), dtype=np.float64)
     lib().ifdo_sor(_p(xyz), B, K, k, ctypes.c_double(alpha), _p(keep), _p(val))
     return keep.astype(bool), val
+
+
+def marching_cubes(volume, isovalue):
+    """-> (verts [V,3] f64, faces [F,3] int64), the restatement of libmcubes.marching_cubes (ifd_oracle.c)."""
+    v = np.ascontiguousarray(volume, dtype=np.float64)
+    nx, ny, nz = v.shape
+    L = lib()
+    L.ifdo_marching_cubes.restype = ctypes.c_longlong
+    L.ifdo_marching_cubes.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+    ni = ctypes.c_longlong()
+    nv = L.ifdo_marching_cubes(_p(v), nx, ny, nz, float(isovalue), None, None, ctypes.byref(ni))
+    verts = np.empty((nv, 3), dtype=np.float64)
+    idx = np.empty(ni.value, dtype=np.int64)
+    L.ifdo_marching_cubes(_p(v), nx, ny, nz, float(isovalue), _p(verts), _p(idx), ctypes.byref(ni))
+    return verts, idx.reshape(-1, 3)
+
+
+def extract_mesh(occ_hat, threshold=0.2, padding=0.1):
+    """ONet/im2mesh/onet/generation.py:165-186 up to the Trimesh constructor: (verts [V,3] f64 in box coordinates, faces)."""
+    occ_hat = np.asarray(occ_hat)
+    n_x, n_y, n_z = occ_hat.shape
+    box_size = 1 + padding
+    thr = np.log(threshold) - np.log(1. - threshold)
+    padded = np.pad(occ_hat, 1, "constant", constant_values=-1e6)
+    vertices, triangles = marching_cubes(padded, thr)
+    vertices -= 0.5
+    vertices -= 1
+    vertices /= np.array([n_x - 1, n_y - 1, n_z - 1])
+    vertices = box_size * (vertices - 0.5)
+    return vertices, triangles
+
+
+def sample_surface(verts, faces, u):
+    """trimesh 3.7.7 sample.sample_surface (un-vendored dependency; call site ONet/remesh_defense.py:157) with the
+    uniform numbers handed in: u[:, 0] picks the face, u[:, 1:3] are the two edge lengths.  Parity unpinned."""
+    tri = verts[faces]                                   # [F, 3, 3]
+    cross = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    area = np.sqrt((cross ** 2).sum(axis=1)) / 2
+    cum = np.cumsum(area)
+    pick = u[:, 0] * cum[-1]
+    f = np.minimum(np.searchsorted(cum, pick), len(faces) - 1)
+    origins = tri[f, 0]
+    vectors = tri[f, 1:] - origins[:, None, :]
+    lengths = u[:, 1:3].copy()[:, :, None]
+    flip = lengths.sum(axis=1).reshape(-1) > 1.0
+    lengths[flip] -= 1.0
+    lengths = np.abs(lengths)
+    return (vectors * lengths).sum(axis=1) + origins, f
