@@ -529,3 +529,231 @@ extern "C" int ifd_sample_surface(const double* verts, long long n_verts, const 
   IFD_LAUNCH_CHECK("sample_surface_kernel");
   return IFD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// MISE -- multiresolution iso-surface extraction (ONet/im2mesh/utils/libmise/mise.pyx:33-369): the octree controller
+// that decides which lattice points generate_from_latent evaluates (generation.py:113-130).
+//
+// The reference keeps vectors of voxels and grid points and a hash map; every decision it takes is a set decision, so
+// the state here is dense and the passes are data parallel:
+//   exists[n^3], known[n^3]   lattice points that were created / whose value was set        (n = (resolution_0 << depth) + 1)
+//   sub[L][(r0 << L)^3]       voxel of level L was subdivided; a voxel exists when L == 0 or its parent was subdivided
+// A leaf voxel below the last level is subdivided when the known points on its closure (corners, and points that finer
+// neighbours put on its faces and edges -- subdivide_voxels visits the 8 unit cells around every known point,
+// mise.pyx:195-219) hold both a value >= threshold and a value <= threshold; subdividing creates the 27 points of the
+// half-size lattice (:247-282).  Levels are processed finest first so that children created in this round are not
+// examined in it (the reference fixes the flags of the existing voxels before it subdivides, :221-237).
+// ------------------------------------------------------------------------------------------------
+namespace ifd {
+
+struct MiseState {
+  int r0, depth, res, n;
+  long long npts;
+  double* val;
+  uint8_t *exists, *known;
+  uint8_t* sub[8];
+  unsigned long long* counter;   // [0] query cursor, [1] error flag
+  size_t bytes;
+};
+
+static int mise_carve(MiseState* m, void* base, int r0, int depth) {
+  IFD_REQUIRE(r0 >= 1 && depth >= 0 && depth <= 7 && ((long long)r0 << depth) <= 1024, "MISE: resolution_0 << depth must be <= 1024, depth <= 7");
+  m->r0 = r0;
+  m->depth = depth;
+  m->res = r0 << depth;
+  m->n = m->res + 1;
+  m->npts = (long long)m->n * m->n * m->n;
+  size_t off = 0;
+  auto take = [&](size_t b) {
+    char* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align256(b);
+    return p;
+  };
+  m->val = reinterpret_cast<double*>(take((size_t)m->npts * 8));
+  m->exists = reinterpret_cast<uint8_t*>(take((size_t)m->npts));
+  m->known = reinterpret_cast<uint8_t*>(take((size_t)m->npts));
+  for (int L = 0; L < 8; ++L) m->sub[L] = nullptr;
+  for (int L = 0; L < depth; ++L) {
+    const size_t r = (size_t)r0 << L;
+    m->sub[L] = reinterpret_cast<uint8_t*>(take(r * r * r));
+  }
+  m->counter = reinterpret_cast<unsigned long long*>(take(16));
+  m->bytes = off;
+  return IFD_OK;
+}
+
+__global__ void mise_init_kernel(MiseState m) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m.npts) return;
+  const int z = (int)(p % m.n), y = (int)((p / m.n) % m.n), x = (int)(p / ((long long)m.n * m.n));
+  const int s = 1 << m.depth;
+  m.exists[p] = (x % s == 0 && y % s == 0 && z % s == 0) ? 1 : 0;
+  m.known[p] = 0;
+  m.val[p] = __longlong_as_double(0x7ff8000000000000ll);       // np.nan (to_dense, mise.pyx:130)
+}
+
+// unknown points that exist: count only (out == nullptr) or append (x, y, z)
+__global__ void mise_query_kernel(MiseState m, long long* __restrict__ out, long long cap) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool want = p < m.npts && m.exists[p] && !m.known[p];
+  const unsigned ballot = __ballot_sync(0xffffffffu, want);
+  if (ballot == 0) return;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(m.counter, (unsigned long long)__popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (want && out) {
+    const long long at = (long long)base + __popc(ballot & ((1u << lane) - 1));
+    if (at < cap) {
+      out[at * 3 + 0] = p / ((long long)m.n * m.n);
+      out[at * 3 + 1] = (p / m.n) % m.n;
+      out[at * 3 + 2] = p % m.n;
+    }
+  }
+}
+
+__global__ void mise_update_kernel(MiseState m, const long long* __restrict__ pts, const double* __restrict__ values, long long count) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  const long long x = pts[e * 3 + 0], y = pts[e * 3 + 1], z = pts[e * 3 + 2];
+  if (x < 0 || y < 0 || z < 0 || x >= m.n || y >= m.n || z >= m.n || !m.exists[(x * m.n + y) * m.n + z]) {
+    m.counter[1] = 1;                                           // ValueError('Point not in grid!'), mise.pyx:101-102
+    return;
+  }
+  const long long p = (x * m.n + y) * m.n + z;
+  m.val[p] = values[e];
+  m.known[p] = 1;
+}
+
+// one thread per voxel of level L
+__global__ void mise_subdivide_kernel(MiseState m, int L, double thr) {
+  const int r = m.r0 << L;
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= (long long)r * r * r) return;
+  const int k = (int)(v % r), j = (int)((v / r) % r), i = (int)(v / ((long long)r * r));
+  if (L > 0) {
+    const int rp = r >> 1;
+    if (!m.sub[L - 1][((long long)(i >> 1) * rp + (j >> 1)) * rp + (k >> 1)]) return;      // the voxel does not exist
+  }
+  if (m.sub[L][v]) return;                                                               // not a leaf
+  const int s = 1 << (m.depth - L);                                                      // voxel size on the fine lattice
+  const int x0 = i * s, y0 = j * s, z0 = k * s;
+  bool pos = false, neg = false;
+  for (int a = 0; a <= s; ++a)
+    for (int b = 0; b <= s; ++b)
+      for (int c = 0; c <= s; ++c) {
+        const long long p = ((long long)(x0 + a) * m.n + (y0 + b)) * m.n + (z0 + c);
+        if (!m.known[p]) continue;
+        const double f = m.val[p];
+        pos = pos || f >= thr;
+        neg = neg || f <= thr;
+      }
+  if (!(pos && neg)) return;
+  m.sub[L][v] = 1;
+  const int h = s >> 1;
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b)
+      for (int c = 0; c < 3; ++c) m.exists[((long long)(x0 + a * h) * m.n + (y0 + b * h)) * m.n + (z0 + c * h)] = 1;
+}
+
+// to_dense (mise.pyx:128-163): NaN where nothing was evaluated, then completed along x, then y, then z
+__global__ void mise_fill_kernel(const MiseState m, double* __restrict__ out, int axis) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= m.n * m.n) return;
+  const int a = t / m.n, b = t % m.n;
+  const long long n = m.n;
+  long long start, stride;
+  if (axis == 0) { start = a * n + b; stride = n * n; }              // (j, k) lines along i
+  else if (axis == 1) { start = a * n * n + b; stride = n; }         // (i, k) lines along j
+  else { start = (a * n + b) * n; stride = 1; }                      // (i, j) lines along k
+  double prev = out[start];
+  for (int q = 1; q < m.n; ++q) {
+    const long long p = start + q * stride;
+    const double f = out[p];
+    if (f != f) out[p] = prev;
+    else prev = f;
+  }
+}
+
+}  // namespace ifd
+
+extern "C" size_t ifd_mise_workspace_bytes(int resolution0, int depth) {
+  MiseState m;
+  if (mise_carve(&m, nullptr, resolution0, depth) != IFD_OK) return 0;
+  return m.bytes;
+}
+
+#define IFD_MISE_STATE(m)                                                                           \
+  MiseState m;                                                                                      \
+  {                                                                                                 \
+    IFD_REQUIRE(workspace, "MISE: null workspace");                                                 \
+    int rc_ = mise_carve(&m, workspace, resolution0, depth);                                        \
+    if (rc_) return rc_;                                                                            \
+    IFD_REQUIRE(workspace_bytes >= m.bytes, "MISE: workspace too small (ifd_mise_workspace_bytes)"); \
+  }
+
+extern "C" int ifd_mise_init(int resolution0, int depth, void* workspace, size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_MISE_STATE(m);
+  cudaStream_t s = as_stream(stream);
+  for (int L = 0; L < depth; ++L) {
+    const size_t r = (size_t)resolution0 << L;
+    IFD_CUDA_TRY(cudaMemsetAsync(m.sub[L], 0, r * r * r, s));
+  }
+  IFD_CUDA_TRY(cudaMemsetAsync(m.counter, 0, 16, s));
+  mise_init_kernel<<<(unsigned)((m.npts + 255) / 256), 256, 0, s>>>(m);
+  IFD_LAUNCH_CHECK("mise_init_kernel");
+  return IFD_OK;
+}
+
+extern "C" int ifd_mise_query(int resolution0, int depth, void* workspace, size_t workspace_bytes, long long* points_out,
+                              long long capacity, long long* count_host, ifd_stream_t stream) {
+  IFD_MISE_STATE(m);
+  IFD_REQUIRE(count_host, "ifd_mise_query: null count");
+  cudaStream_t s = as_stream(stream);
+  IFD_CUDA_TRY(cudaMemsetAsync(m.counter, 0, 8, s));
+  mise_query_kernel<<<(unsigned)((m.npts + 255) / 256), 256, 0, s>>>(m, points_out, points_out ? capacity : 0);
+  IFD_LAUNCH_CHECK("mise_query_kernel");
+  unsigned long long cnt = 0;
+  IFD_CUDA_TRY(cudaMemcpyAsync(&cnt, m.counter, 8, cudaMemcpyDeviceToHost, s));
+  IFD_CUDA_TRY(cudaStreamSynchronize(s));
+  *count_host = (long long)cnt;
+  IFD_REQUIRE(!points_out || (long long)cnt <= capacity, "ifd_mise_query: capacity smaller than the number of unknown points");
+  return IFD_OK;
+}
+
+extern "C" int ifd_mise_update(int resolution0, int depth, double threshold, void* workspace, size_t workspace_bytes,
+                               const long long* points, const double* values, long long count, ifd_stream_t stream) {
+  IFD_MISE_STATE(m);
+  IFD_REQUIRE(count == 0 || (points && values), "ifd_mise_update: null argument");
+  cudaStream_t s = as_stream(stream);
+  if (count > 0) {
+    mise_update_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(m, points, values, count);
+    IFD_LAUNCH_CHECK("mise_update_kernel");
+    unsigned long long bad = 0;
+    IFD_CUDA_TRY(cudaMemcpyAsync(&bad, m.counter + 1, 8, cudaMemcpyDeviceToHost, s));
+    IFD_CUDA_TRY(cudaStreamSynchronize(s));
+    if (bad) {
+      IFD_CUDA_TRY(cudaMemsetAsync(m.counter + 1, 0, 8, s));
+      return fail(IFD_ERR_INVALID, "Point not in grid!");
+    }
+  }
+  for (int L = depth - 1; L >= 0; --L) {
+    const long long r = (long long)resolution0 << L;
+    mise_subdivide_kernel<<<(unsigned)((r * r * r + 127) / 128), 128, 0, s>>>(m, L, threshold);
+    IFD_LAUNCH_CHECK("mise_subdivide_kernel");
+  }
+  return IFD_OK;
+}
+
+extern "C" int ifd_mise_to_dense(int resolution0, int depth, void* workspace, size_t workspace_bytes, double* dense_out,
+                                 ifd_stream_t stream) {
+  IFD_MISE_STATE(m);
+  IFD_REQUIRE(dense_out, "ifd_mise_to_dense: null output");
+  cudaStream_t s = as_stream(stream);
+  IFD_CUDA_TRY(cudaMemcpyAsync(dense_out, m.val, (size_t)m.npts * 8, cudaMemcpyDeviceToDevice, s));
+  for (int axis = 0; axis < 3; ++axis) {
+    mise_fill_kernel<<<(m.n * m.n + 127) / 128, 128, 0, s>>>(m, dense_out, axis);
+    IFD_LAUNCH_CHECK("mise_fill_kernel");
+  }
+  return IFD_OK;
+}

@@ -5,10 +5,10 @@ Mirrors, with the reference's names and argument meaning:
   Generator3D.generate_from_latent / extract_mesh     ONet/im2mesh/onet/generation.py:88-221
   trimesh.sample.sample_surface(mesh, count)          call site ONet/remesh_defense.py:157
   reconstruct_mesh / resample_points                  ONet/remesh_defense.py:126-171
+  libmise.MISE                                        ONet/im2mesh/utils/libmise/mise.pyx:33-369
 
-Differences: the occupancy lattice is evaluated densely on the (resolution0 * 2^steps + 1)^3 lattice MISE refines to
-(every value is a real evaluation; MISE's skipped cells carry propagated coarse values) and stays on the device; a mesh
-is a pair of cuda tensors (vertices [V,3] float64, faces [F,3] int64) instead of a trimesh.Trimesh; random numbers take
+Differences: the octree state and the occupancy lattice stay on the device (Generator3D(dense=True) evaluates the whole
+(resolution0 * 2^steps + 1)^3 lattice instead of refining); a mesh is a pair of cuda tensors (vertices [V,3] float64, faces [F,3] int64) instead of a trimesh.Trimesh; random numbers take
 an explicit numpy Generator.  There is no CPU fallback.
 """
 import ctypes
@@ -92,12 +92,63 @@ def sample_surface_device(verts, faces, count, rng=None, uniforms=None, return_i
     return (out, fidx) if return_index else out
 
 
+class MISE:
+    """libmise.MISE (ONet/im2mesh/utils/libmise/mise.pyx) with its state on the device; points and values are cuda tensors."""
+
+    def __init__(self, resolution_0, depth, threshold):
+        capi.require_gpu()
+        self.resolution_0, self.depth, self.threshold = int(resolution_0), int(depth), float(threshold)
+        self.resolution = self.resolution_0 << self.depth
+        L = capi.lib()
+        nb = int(L.ifd_mise_workspace_bytes(self.resolution_0, self.depth))
+        if nb == 0:
+            raise RuntimeError("MISE: unsupported resolution_0 / depth")
+        self._ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        capi.check(L.ifd_mise_init(self.resolution_0, self.depth, capi.ptr(self._ws), nb, capi.stream()), "ifd_mise_init")
+
+    def query(self):
+        """-> int64 cuda [N, 3]: the points to evaluate next (empty when the extraction is complete)."""
+        L = capi.lib()
+        n = ctypes.c_longlong()
+        capi.check(L.ifd_mise_query(self.resolution_0, self.depth, capi.ptr(self._ws), self._ws.numel(), None, 0, ctypes.byref(n),
+                                    capi.stream()), "ifd_mise_query")
+        pts = torch.empty((n.value, 3), dtype=torch.int64, device="cuda")
+        if n.value:
+            capi.check(L.ifd_mise_query(self.resolution_0, self.depth, capi.ptr(self._ws), self._ws.numel(), capi.ptr(pts), n.value,
+                                        ctypes.byref(n), capi.stream()), "ifd_mise_query")
+        return pts
+
+    def update(self, points, values):
+        points = torch.as_tensor(points).to("cuda", torch.int64).contiguous()
+        values = torch.as_tensor(values).to("cuda", torch.float64).contiguous()
+        assert points.shape[0] == values.shape[0] and points.shape[1] == 3            # mise.pyx:85-86
+        L = capi.lib()
+        rc = L.ifd_mise_update(self.resolution_0, self.depth, self.threshold, capi.ptr(self._ws), self._ws.numel(),
+                               capi.ptr(points) if points.shape[0] else None, capi.ptr(values) if points.shape[0] else None,
+                               points.shape[0], capi.stream())
+        if rc != 0:
+            msg = (L.ifd_last_error() or b"").decode()
+            if "Point not in grid" in msg:
+                raise ValueError("Point not in grid!")                                  # mise.pyx:102
+            capi.check(rc, "ifd_mise_update")
+
+    def to_dense(self):
+        n = self.resolution + 1
+        out = torch.empty((n, n, n), dtype=torch.float64, device="cuda")
+        capi.check(capi.lib().ifd_mise_to_dense(self.resolution_0, self.depth, capi.ptr(self._ws), self._ws.numel(), capi.ptr(out),
+                                                capi.stream()), "ifd_mise_to_dense")
+        return out
+
+
 class Generator3D:
     """The part of im2mesh.onet.generation.Generator3D that remesh_defense.py uses (generate_from_latent with z of
     width 0).  `decoder` is an onet.ONetDecoder."""
 
-    def __init__(self, decoder, threshold=0.2, resolution0=32, upsampling_steps=2, padding=0.1, points_batch_size=100000):
+    def __init__(self, decoder, threshold=0.2, resolution0=32, upsampling_steps=2, padding=0.1, points_batch_size=100000,
+                 dense=False):
         self.decoder = decoder
+        self.dense = dense            # True: evaluate the whole fine lattice instead of refining with MISE
+        self.points_evaluated = 0
         self.threshold = threshold
         self.resolution0 = resolution0
         self.upsampling_steps = upsampling_steps
@@ -110,7 +161,24 @@ class Generator3D:
             # generation.py:105-111: make_3d_grid((-0.5,)*3, (0.5,)*3, (nx,)*3): nx points from -0.5 to 0.5 per axis,
             # i.e. the lattice of resolution nx - 1
             return self.decoder.eval_dense_grid(c, self.resolution0 - 1, self.padding, self.points_batch_size)
-        return self.decoder.eval_dense_grid(c, self.resolution0 * 2 ** self.upsampling_steps, self.padding, self.points_batch_size)
+        if self.dense:
+            return self.decoder.eval_dense_grid(c, self.resolution0 * 2 ** self.upsampling_steps, self.padding, self.points_batch_size)
+        threshold = np.log(self.threshold) - np.log(1. - self.threshold)
+        box_size = 1 + self.padding
+        cc = torch.as_tensor(c).detach().float().reshape(1, -1).cuda().contiguous()
+        extractor = MISE(self.resolution0, self.upsampling_steps, threshold)            # generation.py:113-130
+        self.points_evaluated = 0
+        points = extractor.query()
+        while points.shape[0] != 0:
+            pointsf = box_size * (points.float() / extractor.resolution - 0.5)
+            values = torch.empty(points.shape[0], dtype=torch.float32, device="cuda")
+            for lo in range(0, points.shape[0], self.points_batch_size):
+                x = pointsf[lo:lo + self.points_batch_size].contiguous().view(1, -1, 3)
+                values[lo:lo + x.shape[1]] = self.decoder._logits_nograd(x, cc)
+            self.points_evaluated += int(points.shape[0])
+            extractor.update(points, values)
+            points = extractor.query()
+        return extractor.to_dense()
 
     def generate_from_latent(self, z, c=None):
         return extract_mesh(self.value_grid(c), self.threshold, self.padding)

@@ -72,3 +72,17 @@ def make_onet_case(B, K=1024, seed=0, T=300, device="cpu", sd=None):
     gen = torch.Generator().manual_seed(3000 + seed)
     p0 = driver.init_points([p for p, _ in proc], npoint=K, sigma=0.01, padding_scale=0.9, gen=gen)
     return types.SimpleNamespace(sd=sd, raw=raw, sel=sel, c=c, p0=p0, B=B, K=K)
+
+
+def onet_with_surface(sd, c, occupied=0.25, resolution=16):
+    """Random-init ONet weights put the whole box on one side of the threshold, which makes mesh extraction trivial.  Returns a
+    copy of `sd` whose `decoder.fc_out.bias` is shifted so that the logit(0.2) level set encloses about `occupied` of the box
+    for the latent code c (a wiggly closed surface: a harder case than a real shape for MISE and marching cubes)."""
+    from . import onet as onet_mod
+    dec = onet_mod.ONetDecoder(sd)
+    g = dec.eval_dense_grid(c, resolution=resolution).flatten().float().cpu()
+    thr = float(np.log(0.2) - np.log(0.8))
+    shift = thr - float(torch.quantile(g, 1.0 - occupied))
+    out = {k: v.clone() for k, v in sd.items()}
+    out["decoder.fc_out.bias"] = out["decoder.fc_out.bias"] + shift
+    return out

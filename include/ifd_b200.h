@@ -301,6 +301,26 @@ int ifd_sample_surface(const double* verts, long long n_verts, const long long* 
                        const double* uniforms, int count, double* xyz_out, long long* face_out, void* workspace,
                        size_t workspace_bytes, ifd_stream_t stream);
 
+/* MISE, the octree controller of Generator3D.generate_from_latent (ONet/im2mesh/utils/libmise/mise.pyx:33-369; driven by
+ * ONet/im2mesh/onet/generation.py:113-130), with its state in a caller-provided device workspace:
+ *   ifd_mise_init       MISE(resolution_0, depth, threshold).__cinit__: the (resolution_0 + 1)^3 coarse points exist
+ *   ifd_mise_query      .query(): the lattice points (x, y, z int64, on the (resolution_0 << depth) + 1 lattice) that exist
+ *                       and have no value yet.  points_out == NULL only counts; synchronises `stream` for the count
+ *   ifd_mise_update     .update(points, values): sets the values, then subdivides every leaf voxel whose known points hold
+ *                       a value >= threshold and a value <= threshold.  A point that is not in the grid is
+ *                       IFD_ERR_INVALID "Point not in grid!" (the reference's ValueError); synchronises for that check
+ *   ifd_mise_to_dense   .to_dense(): [n][n][n] float64, unevaluated points completed along x, then y, then z
+ * The result equals the reference's for the same evaluation function (set semantics; the order of the queried points
+ * is unspecified). */
+size_t ifd_mise_workspace_bytes(int resolution0, int depth);
+int ifd_mise_init(int resolution0, int depth, void* workspace, size_t workspace_bytes, ifd_stream_t stream);
+int ifd_mise_query(int resolution0, int depth, void* workspace, size_t workspace_bytes, long long* points_out,
+                   long long capacity, long long* count_host, ifd_stream_t stream);
+int ifd_mise_update(int resolution0, int depth, double threshold, void* workspace, size_t workspace_bytes,
+                    const long long* points, const double* values, long long count, ifd_stream_t stream);
+int ifd_mise_to_dense(int resolution0, int depth, void* workspace, size_t workspace_bytes, double* dense_out,
+                      ifd_stream_t stream);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 long long ifd_launch_count(int reset);
 

@@ -168,7 +168,7 @@ void ifdo_sor(const float* xyz, int B, int K, int k, double alpha, uint8_t* keep
  * cells in (i, j, k) order; a vertex sits at cell-centre-shifted coordinates (i + 0.5, ...), is appended the first
  * time its edge is met and is found again through the cell that owns it (the cell whose far corner the edge touches);
  * on the i/j/k == 0 faces that owner does not exist and the vertex is appended again.  Restated data-driven: one
- * descriptor per cube edge.  Case tables: derived from the reference's behaviour (tools/gen_mc_tables.py).
+ * descriptor per cube edge.  Case tables: derived from the reference's behaviour (oracle/gen_mc_tables.py).
  * Call with verts == NULL to count.  Returns the number of vertices; *n_idx = number of triangle indices.
  * ------------------------------------------------------------------------------------------------ */
 #include "../../if-defense_b200/csrc/mc_tables.inc"

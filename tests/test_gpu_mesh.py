@@ -11,6 +11,7 @@ import torch
 
 from ifdefense_b200 import capi, mesh, models, onet as onet_mod, synth
 from oracle import c_oracle as co
+from oracle import mise_port
 
 from .conftest import GOLDEN
 
@@ -139,3 +140,72 @@ def test_generator3d_and_resample_points():
             return torch.full((9, 9, 9), -5.0, device="cuda")
     out = mesh.resample_points(Flat(dec), encode, pc[:700], num_points=1024, rng=np.random.default_rng(0))
     assert out.shape == (1024, 3) and np.array_equal(out[:700], pc[:700].astype(np.float32)) and (out[700:] == 0).all()
+
+
+def _run_mise(r0, depth, thr, fn):
+    ex = mesh.MISE(r0, depth, thr)
+    rounds = []
+    pts = ex.query()
+    while pts.shape[0] != 0:
+        rounds.append(int(pts.shape[0]))
+        ex.update(pts, torch.from_numpy(fn(pts.cpu().numpy())).cuda())
+        pts = ex.query()
+    return ex.to_dense().cpu().numpy(), rounds
+
+
+@pytest.mark.parametrize("name", ["s0", "s1", "s2", "s3", "d0", "big0", "big1"])
+def test_mise_equals_reference_fixture(name):
+    """The device MISE against what the reference's own Cython MISE did (tests/golden/mise.npz): the number of points it
+    asks for in every round and the dense lattice it hands to marching cubes."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, "mise.npz"))
+    r0, depth, kind = (int(x) for x in g[name + "_cfg"])
+    res = r0 << depth
+    dense, rounds = _run_mise(r0, depth, float(g[name + "_thr"]), lambda p: mise_port.analytic_field(p, res, kind))
+    assert rounds == list(g[name + "_rounds"])
+    assert hashlib.sha256(np.ascontiguousarray(dense).tobytes()).hexdigest() == str(g[name + "_sha256"])
+
+
+def test_mise_random_fields_vs_oracle_and_errors():
+    rng = np.random.default_rng(4)
+    for r0, depth in [(3, 1), (5, 2), (4, 3), (7, 0)]:
+        n = (r0 << depth) + 1
+        # a smooth random field (a few Fourier modes) plus plateaus at the threshold
+        ax = np.arange(n) / (n - 1.0)
+        X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+        F = sum(rng.standard_normal() * np.cos(2 * np.pi * (rng.integers(0, 3) * X + rng.integers(0, 3) * Y + rng.integers(0, 3) * Z)
+                                               + rng.random()) for _ in range(5))
+        F[np.abs(F) < 0.1] = 0.0
+        fn = lambda p: F[p[:, 0], p[:, 1], p[:, 2]]
+        want, want_rounds = mise_port.mise_loop(fn, r0, depth, 0.0)
+        got, rounds = _run_mise(r0, depth, 0.0, fn)
+        assert rounds == want_rounds and np.array_equal(got, want), (r0, depth)
+    ex = mesh.MISE(4, 2, 0.0)
+    with pytest.raises(ValueError, match="Point not in grid"):
+        ex.update(torch.tensor([[1, 0, 0]]), torch.tensor([0.5]))                 # not a coarse lattice point
+    with pytest.raises(ValueError, match="Point not in grid"):
+        ex.update(torch.tensor([[0, 0, 99]]), torch.tensor([0.5]))
+    assert ex.query().shape == (125, 3)
+    q = ex.query()
+    assert q.dtype == torch.int64 and len({tuple(r) for r in q.cpu().numpy().tolist()}) == 125 and (q % 4 == 0).all()
+
+
+def test_generator3d_mise_path_equals_mise_of_the_dense_lattice():
+    """generate_from_latent as the reference runs it (MISE refinement, generation.py:113-130) with the ONet decoder: the
+    lattice equals the oracle MISE fed from the densely evaluated lattice (a point's logit does not depend on which other
+    points are evaluated with it), and far fewer points are evaluated."""
+    case = synth.make_onet_case(1, K=64, seed=2)
+    c = case.c[:1]
+    sd = synth.onet_with_surface(models.synthetic_state_dict("onet", 0), c, occupied=0.3)
+    dec = onet_mod.ONetDecoder(sd)
+    full = mesh.Generator3D(dec, 0.2, resolution0=8, upsampling_steps=2, dense=True).value_grid(c).cpu().numpy().astype(np.float64)
+    gen = mesh.Generator3D(dec, 0.2, resolution0=8, upsampling_steps=2, points_batch_size=700)
+    grid = gen.value_grid(c).cpu().numpy()
+    thr = np.log(0.2) - np.log(0.8)
+    want, rounds = mise_port.mise_loop(lambda p: full[p[:, 0], p[:, 1], p[:, 2]], 8, 2, thr)
+    print("MISE rounds", rounds, "of", 33 ** 3)
+    assert len(rounds) >= 3 and gen.points_evaluated == sum(rounds) and gen.points_evaluated < 33 ** 3
+    assert np.array_equal(grid, want)
+    v, f = gen.generate_from_latent(None, c)
+    wv, wf = co.extract_mesh(want, 0.2, 0.1)
+    assert np.array_equal(v.cpu().numpy(), wv) and np.array_equal(f.cpu().numpy(), wf)

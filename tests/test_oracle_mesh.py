@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import c_oracle as co
-from oracle import mcubes_ref
+from oracle import mcubes_ref, mise_port
 
 from .conftest import GOLDEN, ROOT
 
@@ -95,3 +95,20 @@ def test_sample_surface_restatement_stays_on_the_mesh():
     area = np.array([0.5, 0.5, 0.5, np.sqrt(3) / 2])
     assert np.abs(share - area / area.sum()).max() < 0.03
     assert (p >= -1e-12).all() and (p.sum(axis=1) <= 1 + 1e-12).all()
+
+
+MISE_CASES = ["s0", "s1", "s2", "s3", "d0", "big0"]
+
+
+@pytest.mark.parametrize("name", MISE_CASES)
+def test_mise_restatement_equals_reference_fixture(name):
+    """tests/golden/mise.npz holds what the reference's own Cython MISE did on these fields: points per round, dense grid."""
+    import hashlib
+    g = np.load(os.path.join(GOLDEN, "mise.npz"))
+    r0, depth, kind = (int(x) for x in g[name + "_cfg"])
+    res = r0 << depth
+    dense, rounds = mise_port.mise_loop(lambda p: mise_port.analytic_field(p, res, kind), r0, depth, float(g[name + "_thr"]))
+    assert rounds == list(g[name + "_rounds"])
+    assert hashlib.sha256(np.ascontiguousarray(dense).tobytes()).hexdigest() == str(g[name + "_sha256"])
+    if name + "_dense" in g:
+        assert np.array_equal(dense, g[name + "_dense"].astype(np.float64))
