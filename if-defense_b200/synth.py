@@ -86,3 +86,28 @@ def onet_with_surface(sd, c, occupied=0.25, resolution=16):
     out = {k: v.clone() for k, v in sd.items()}
     out["decoder.fc_out.bias"] = out["decoder.fc_out.bias"] + shift
     return out
+
+
+def fill_classifier_state_(model, seed=0):
+    """Deterministic non-trivial weights for a victim classifier, a function of the parameter NAMES and shapes only, so that
+    the reference model and its mirror receive identical tensors (no victim checkpoint ships: baselines/README.md:23,31).
+    Weights ~ N(0, 1/fan_in), BatchNorm scale U(0.5, 1.5), shift and running mean N(0, 0.1^2), running variance U(0.5, 1.5)."""
+    import zlib
+    sd = model.state_dict()
+    for name in sorted(sd):
+        t = sd[name]
+        g = torch.Generator().manual_seed(seed * 1000003 + zlib.crc32(name.encode()))
+        if name.endswith("num_batches_tracked"):
+            continue
+        if name.endswith("running_var"):
+            t.copy_(torch.rand(t.shape, generator=g) + 0.5)
+        elif name.endswith("running_mean"):
+            t.copy_(torch.randn(t.shape, generator=g) * 0.1)
+        elif t.dim() == 1 and "bn" in name and name.endswith("weight"):
+            t.copy_(torch.rand(t.shape, generator=g) + 0.5)
+        elif t.dim() == 1:
+            t.copy_(torch.randn(t.shape, generator=g) * 0.1)
+        else:
+            fan_in = int(np.prod(t.shape[1:]))
+            t.copy_(torch.randn(t.shape, generator=g) / np.sqrt(fan_in))
+    return model
