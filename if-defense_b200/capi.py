@@ -58,6 +58,7 @@ SIGNATURES = {
     "ifd_mise_query": (_c_int, [_c_int, _c_int, _vp, _c_sz, _vp, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong), _vp]),
     "ifd_mise_update": (_c_int, [_c_int, _c_int, _c_d, _vp, _c_sz, _vp, _vp, ctypes.c_longlong, _vp]),
     "ifd_mise_to_dense": (_c_int, [_c_int, _c_int, _vp, _c_sz, _vp, _vp]),
+    "ifd_preprocess_pc": (_c_int, [_vp, _vp, _c_int, _c_int, ctypes.c_float, _vp, _vp, _vp]),
     "ifd_opt_params_default": (None, [ctypes.POINTER(OptParams)]),
     "ifd_convonet_opt_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "ifd_convonet_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

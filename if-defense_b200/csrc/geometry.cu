@@ -411,3 +411,101 @@ extern "C" int ifd_sor(const float* xyz, int B, int K, int k, double alpha, uint
   IFD_LAUNCH_CHECK("sor_kernel");
   return IFD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// preprocess_pc for a batch (ConvONet/opt_defense.py:114-130, numpy part), fused with the ragged selection that
+// follows SOR (:86-111): one CTA per cloud.  The kept points are compacted in input order, centred on their float32
+// mean (summed in point order, as np.mean(axis=0) does on a [K,3] array), divided by the largest bounding-box extent and
+// multiplied by padding_scale -- every operation rounded to float32 as numpy rounds it.
+// ------------------------------------------------------------------------------------------------
+namespace ifd {
+constexpr int kPreThreads = 256;
+
+__global__ void __launch_bounds__(kPreThreads) preprocess_pc_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ keep,
+                                                                    int K, float padding_scale, float* __restrict__ out,
+                                                                    int32_t* __restrict__ counts) {
+  __shared__ int warp_cnt[kPreThreads / 32];
+  __shared__ int base_s;
+  __shared__ float mean_s[3], ext_lo[3][kPreThreads / 32], ext_hi[3][kPreThreads / 32], scale_s;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const float* src = xyz + (size_t)b * K * 3;
+  float* dst = out + (size_t)b * K * 3;
+  if (t == 0) base_s = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < K; c0 += kPreThreads) {                      // stable compaction of the kept points
+    const int i = c0 + t;
+    const bool on = i < K && (keep == nullptr || keep[(size_t)b * K + i] != 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    int before = base_s;
+    for (int q = 0; q < w; ++q) before += warp_cnt[q];
+    if (on) {
+      const int at = before + __popc(bal & ((1u << lane) - 1));
+      dst[at * 3 + 0] = src[i * 3 + 0];
+      dst[at * 3 + 1] = src[i * 3 + 1];
+      dst[at * 3 + 2] = src[i * 3 + 2];
+    }
+    __syncthreads();
+    if (t == 0) {
+      int tot = 0;
+      for (int q = 0; q < kPreThreads / 32; ++q) tot += warp_cnt[q];
+      base_s += tot;
+    }
+    __syncthreads();
+  }
+  const int n = base_s;
+  if (t < 3) {                                                       // np.mean(pc, axis=0): sequential float32 sum / n
+    float s = 0.0f;
+    for (int i = 0; i < n; ++i) s = __fadd_rn(s, dst[i * 3 + t]);
+    mean_s[t] = __fdiv_rn(s, (float)n);
+  }
+  __syncthreads();
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = t; i < n; i += kPreThreads)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float c = __fsub_rn(dst[i * 3 + d], mean_s[d]);
+      dst[i * 3 + d] = c;
+      lo[d] = fminf(lo[d], c);
+      hi[d] = fmaxf(hi[d], c);
+    }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if (lane == 0) {
+      ext_lo[d][w] = lo[d];
+      ext_hi[d][w] = hi[d];
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    float scale = -INFINITY;
+    for (int d = 0; d < 3; ++d) {
+      float l = INFINITY, h = -INFINITY;
+      for (int q = 0; q < kPreThreads / 32; ++q) {
+        l = fminf(l, ext_lo[d][q]);
+        h = fmaxf(h, ext_hi[d][q]);
+      }
+      scale = fmaxf(scale, __fsub_rn(h, l));                         // (max_dim - min_dim).max()
+    }
+    scale_s = scale;
+    counts[b] = n;
+  }
+  __syncthreads();
+  const float scale = scale_s;
+  for (int e = t; e < K * 3; e += kPreThreads)
+    dst[e] = e < n * 3 ? __fmul_rn(__fdiv_rn(dst[e], scale), padding_scale) : 0.0f;   // centered / scale * padding_scale
+}
+}  // namespace ifd
+
+extern "C" int ifd_preprocess_pc(const float* xyz, const uint8_t* keep, int B, int K, float padding_scale, float* out,
+                                 int32_t* counts, ifd_stream_t stream) {
+  IFD_REQUIRE(xyz && out && counts && xyz != out && B > 0 && K > 0, "ifd_preprocess_pc: bad arguments");
+  preprocess_pc_kernel<<<B, kPreThreads, 0, as_stream(stream)>>>(xyz, keep, K, padding_scale, out, counts);
+  IFD_LAUNCH_CHECK("preprocess_pc_kernel");
+  return IFD_OK;
+}

@@ -31,6 +31,7 @@ class Args:
     sor_alpha = 1.1
     threshold = 0.2       # cfg['test']['threshold']
     input_npoint = 600    # cfg['data']['pointcloud_n'] (300 for ONet)
+    device_preprocess = True   # SOR selection + preprocess_pc + init gather on the device (same bits as the numpy path)
     encoder_chunk = 1     # sharded path only: clouds per encoder call.  1 makes the (torch/cuDNN) encoder see the same
                           # shapes however the job is split, so the result does not depend on the number of ranks
 
@@ -91,9 +92,49 @@ class Defender:
             out += [o.detach().cpu().numpy().astype(np.float32) for o in sor(x)]
         return out
 
+    def prepare_batch_device(self, raw, rng=None, gen=None):
+        """sor_process + preprocess_pc + the encoder subset + init_points (opt_defense.py:86-179) for one batch [B,K,3] with the
+        arrays on the device: SOR mask (`ifd_sor`), ragged selection + normalisation (`ifd_preprocess_pc`), gathers by the
+        indices the host RNGs draw (the same draws, in the same order, as the numpy path).  -> (sel [B,T,3], init [B,npoint,3])."""
+        from . import capi
+        a = self.args
+        x = torch.from_numpy(np.ascontiguousarray(np.asarray(raw)[..., :3], dtype=np.float32)).to(self.device)
+        B, K, _ = x.shape
+        L = capi.lib()
+        keep = None
+        if a.sor:
+            keep = torch.empty((B, K), dtype=torch.uint8, device=self.device)
+            capi.check(L.ifd_sor(capi.ptr(x), B, K, a.sor_k, float(a.sor_alpha), capi.ptr(keep), None, capi.stream()), "ifd_sor")
+        allp = torch.empty_like(x)
+        counts = torch.empty(B, dtype=torch.int32, device=self.device)
+        capi.check(L.ifd_preprocess_pc(capi.ptr(x), capi.ptr(keep), B, K, float(a.padding_scale), capi.ptr(allp), capi.ptr(counts),
+                                       capi.stream()), "ifd_preprocess_pc")
+        n = counts.cpu().numpy()
+        T = a.input_npoint
+        if T is None or (n <= T).any():
+            raise RuntimeError("device preprocess needs more than input_npoint points per cloud after SOR")
+        draw = rng if rng is not None else np.random
+        sel_idx = np.stack([draw.choice(int(k), T, replace=False) for k in n])                 # preprocess_pc :134-141
+        ini_idx = torch.stack([torch.randint(0, int(k), (a.sample_npoint,), generator=gen) for k in n])   # init_points :163-167
+        noise = torch.randn((B, a.sample_npoint, 3), generator=gen) * a.init_sigma
+        rows = torch.arange(B, device=self.device).view(B, 1)
+        sel = allp[rows, torch.from_numpy(sel_idx).to(self.device)]
+        pts = allp[rows, ini_idx.to(self.device)] + noise.to(self.device)
+        return sel, torch.clamp(pts, min=-0.5 * a.padding_scale, max=0.5 * a.padding_scale)
+
     def defend_point_cloud(self, pc, rng=None, gen=None, printing=False):
         """opt_defense.py:255-314.  pc: [N,K,3] array.  Returns float32 [N,sample_npoint,3]."""
         a = self.args
+        if a.device_preprocess and isinstance(pc, np.ndarray) and pc.ndim == 3:
+            out = np.zeros((len(pc), a.sample_npoint, 3), dtype=np.float32)
+            # SOR first for the whole file, as the reference does (:277-279): the draws of later batches do not depend on it
+            for lo in range(0, len(pc), a.batch_size):
+                sel, pts = self.prepare_batch_device(pc[lo:lo + a.batch_size], rng, gen)
+                with torch.no_grad():
+                    c = self.model.encode_inputs(sel)
+                out[lo:lo + a.batch_size] = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight,
+                                                                          iterations=a.iterations, printing=printing)
+            return out
         pcs = self.sor_process(pc) if a.sor else [np.asarray(p, dtype=np.float32) for p in pc]
         out = np.zeros((len(pcs), a.sample_npoint, 3), dtype=np.float32)
         for lo in range(0, len(pcs), a.batch_size):

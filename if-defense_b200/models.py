@@ -56,6 +56,19 @@ class _Up(nn.Module):
         self.conv1 = nn.Conv2d(2 * cout, cout, 3, padding=1)
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
 
+    def up(self, x):
+        """ConvTranspose2d(k = 2, stride = 2) never overlaps its outputs: on the GPU it is one fp32 GEMM
+        [B*H*W, Cin] x [Cin, Cout*4] followed by a pixel shuffle (cuDNN's fp32 path for it is a slow direct dgrad kernel:
+        45 % of the encoder's time at B = 192)."""
+        if not x.is_cuda:
+            return self.upconv(x)
+        B, cin, H, W = x.shape
+        w = self.upconv.weight                                             # [Cin, Cout, 2, 2]
+        cout = w.shape[1]
+        y = x.permute(0, 2, 3, 1).reshape(B * H * W, cin) @ w.reshape(cin, cout * 4)
+        y = y.view(B, H, W, cout, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, cout, 2 * H, 2 * W)
+        return y + self.upconv.bias.view(1, cout, 1, 1)
+
 
 class UNet(nn.Module):
     """2-D U-Net, concat merge, transpose-conv upsampling (the only mode the shipped config uses)."""
@@ -83,7 +96,7 @@ class UNet(nn.Module):
             if i < self.depth - 1:
                 x = F.max_pool2d(x, 2, 2)
         for i, u in enumerate(self.up_convs):
-            x = torch.cat((u.upconv(x), skips[-(i + 2)]), 1)
+            x = torch.cat((u.up(x), skips[-(i + 2)]), 1)
             x = F.relu(u.conv2(F.relu(u.conv1(x))))
         return self.conv_final(x)
 
@@ -131,19 +144,18 @@ class LocalPoolPointnet(nn.Module):
 
     def forward(self, p):
         """fp32 throughout (the reference runs fp32: TF32 convolutions -- torch's CUDA default -- would move the planes
-        by ~1e-3 relative) and with torch's deterministic scatter_add, so the planes are reproducible run to run."""
+        by ~1e-3 relative).  The scatter operators are the library's deterministic kernels and cuDNN's forward convolutions
+        have no atomics, so the planes are reproducible run to run without torch's deterministic mode (which would route
+        the U-Net through kernels 3-4x slower)."""
         if not p.is_cuda:
             return self._forward(p)
         tf32_c, tf32_m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-        det, warn = torch.are_deterministic_algorithms_enabled(), torch.is_deterministic_algorithms_warn_only_enabled()
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
-        torch.use_deterministic_algorithms(True, warn_only=True)
         try:
             return self._forward(p)
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32_c, tf32_m
-            torch.use_deterministic_algorithms(det, warn_only=warn)
 
     def _forward(self, p):
         if p.is_cuda:
@@ -165,8 +177,8 @@ class LocalPoolPointnet(nn.Module):
 
     def _forward_cuda(self, p):
         """The same forward on the GPU: bins, scatter_max + gather and scatter_mean are the library's kernels
-        (ifd_plane_bins, ifd_scatter_max_gather, ifd_scatter_mean_cl: deterministic, channels-last planes); the Linear
-        layers and the U-Net stay torch / cuDNN."""
+        (ifd_plane_bins, ifd_scatter_max_gather, ifd_scatter_mean_cl: deterministic); the Linear layers and the U-Net stay
+        torch / cuDNN, fed NCHW (cuDNN's fp32 kernels are ~1.7x faster on it than on channels_last)."""
         from . import capi
         capi.require_gpu()
         if list(self.plane_type) != ["xz", "xy", "yz"]:
@@ -191,7 +203,7 @@ class LocalPoolPointnet(nn.Module):
             capi.check(L.ifd_scatter_mean_cl(capi.ptr(c), capi.ptr(bins[i]), B, T, self.c_dim, nb, capi.ptr(out), st),
                        "ifd_scatter_mean_cl")
             plane = out.view(B, R, R, self.c_dim).permute(0, 3, 1, 2)        # [B,C,R,R], channels_last memory
-            fea[pl] = self.unet(plane) if self.unet is not None else plane
+            fea[pl] = self.unet(plane.contiguous()) if self.unet is not None else plane
         return fea
 
 

@@ -88,6 +88,14 @@ int ifd_ball_query(const float* xyz, const float* new_xyz, int B, int N, int S, 
 int ifd_sor(const float* xyz, int B, int K, int k, double alpha, uint8_t* keep_out, double* value_out,
             ifd_stream_t stream);
 
+/* preprocess_pc (ConvONet/opt_defense.py:114-130, the numpy part; ONet/remesh_defense.py:104-110) for a batch, fused with the
+ * ragged selection that follows SOR (opt_defense.py:86-111).  keep [B][K] uint8 from ifd_sor, or NULL (all points).
+ * out [B][K][3]: the counts_out[b] kept points of cloud b in input order, minus their float32 mean (summed in point order like
+ * np.mean(axis=0)), divided by the largest bounding-box extent, times padding_scale; the remaining rows are zero.  Bitwise equal
+ * to the numpy statements.  The random subset / init draws that follow stay with the caller. */
+int ifd_preprocess_pc(const float* xyz, const uint8_t* keep, int B, int K, float padding_scale, float* out,
+                      int32_t* counts_out, ifd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * ConvONet decoder (LocalDecoder, 3 feature planes)
  * ---------------------------------------------------------------------------------------------- */

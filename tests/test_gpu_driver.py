@@ -38,3 +38,44 @@ def test_defender_reference_loop_runs(defender, tmp_path):
     z = np.load(out)
     assert z["test_pc"].shape == (3, 1024, 3) and z["test_pc"].dtype == np.float32 and np.isfinite(z["test_pc"]).all()
     assert z["test_label"].dtype == np.uint8 and z["target_label"].dtype == np.uint8
+
+
+def test_preprocess_kernel_equals_numpy():
+    """ifd_preprocess_pc against the numpy statements of preprocess_pc (opt_defense.py:114-130), bit for bit, with and
+    without a SOR mask (ragged counts), including K that is not a multiple of the block size."""
+    import torch
+    from ifdefense_b200 import capi
+    rng = np.random.default_rng(1)
+    for K in (1024, 700, 257, 5):
+        pc = (rng.standard_normal((6, K, 3)) * rng.uniform(0.2, 2.0, size=(6, 1, 3)) + rng.uniform(-1, 1, size=(6, 1, 3))).astype(np.float32)
+        for masked in (False, True):
+            keep = (rng.random((6, K)) < 0.8).astype(np.uint8) if masked else None
+            if masked:
+                keep[:, 0] = 1
+            x = torch.from_numpy(pc).cuda()
+            out = torch.full_like(x, 7.0)
+            counts = torch.empty(6, dtype=torch.int32, device="cuda")
+            kd = torch.from_numpy(keep).cuda() if masked else None
+            capi.check(capi.lib().ifd_preprocess_pc(capi.ptr(x), capi.ptr(kd), 6, K, 0.9, capi.ptr(out), capi.ptr(counts), capi.stream()))
+            out, counts = out.cpu().numpy(), counts.cpu().numpy()
+            for b in range(6):
+                p = pc[b][keep[b] != 0] if masked else pc[b]
+                want, _ = driver.preprocess_pc(p, None, 0.9)
+                assert counts[b] == len(p)
+                assert np.array_equal(out[b, :len(p)], want), (K, masked, b)
+                assert (out[b, len(p):] == 0).all()
+
+
+def test_device_preprocess_path_equals_host_path():
+    """defend_point_cloud with SOR + preprocess + init gathers on the device gives the bits of the per-cloud numpy path
+    (the reference's own sequence) for the same RNG streams."""
+    import torch
+    model = models.build_convonet()
+    model.load_state_dict(models.synthetic_state_dict("convonet", 0))
+    pc = synth.clouds(5)
+    pc[0, :7] += 0.8                                         # a few outliers for SOR to remove
+    outs = []
+    for dev_path in (True, False):
+        d = driver.Defender(model, driver.Args(batch_size=3, iterations=6, device_preprocess=dev_path))
+        outs.append(d.defend_point_cloud(pc, rng=np.random.default_rng(5), gen=torch.Generator().manual_seed(5)))
+    assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])

@@ -79,7 +79,7 @@ def test_product_encoder_on_gpu_matches_oracle_and_feeds_the_loop():
         d = (got[k].cpu() - want[k]).abs().max().item()
         assert d < 2e-4 * want[k].abs().max().item(), (k, d)             # Linear / conv rounding (cuBLAS, cuDNN vs CPU)
     # channels_last planes are taken as they are (no transposing copy) and give the same decode as the NCHW route
-    pl_fast = convonet.planes_to_channels_last(got)
+    pl_fast = convonet.planes_to_channels_last({k: v.contiguous(memory_format=torch.channels_last) for k, v in got.items()})
     pl_ref = convonet.planes_to_channels_last({k: v.contiguous() for k, v in got.items()})
     assert torch.equal(pl_fast, pl_ref)
 
