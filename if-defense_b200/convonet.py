@@ -99,12 +99,26 @@ class Restorer:
     """Holds what the reference keeps in module globals (generator, args.threshold, args.lr) and exposes
     optimize_points with the reference's signature."""
 
-    def __init__(self, decoder, threshold=0.2, lr=1e-3, decode_kernel=0):
+    def __init__(self, decoder, threshold=0.2, lr=1e-3, decode_kernel=0, side_by_side=True):
         """decode_kernel: 0 = production default (tcgen05 tensor-core MLP, 3xTF32); 2 = fp32 SIMT kernels, for
-        bit-level trajectory comparisons with an fp32 reference (see include/ifd_b200.h, ifd_opt_params)."""
+        bit-level trajectory comparisons with an fp32 reference (see include/ifd_b200.h, ifd_opt_params).
+        side_by_side: a batch of >= 128 clouds is cut into equal parts whose loops run next to each other on two streams
+        (ifd_convonet_opt_batches with the batch's B_ref: the same bits, the launches of one loop fill the SMs the other
+        leaves idle)."""
         self.decoder, self.threshold, self.lr = decoder, float(threshold), float(lr)
         self.decode_kernel = int(decode_kernel)
+        self.side_by_side = side_by_side
         self.last_stats = None
+
+    def _parts(self, B):
+        if not self.side_by_side or B < 128:
+            return 1
+        if isinstance(self.side_by_side, int) and not isinstance(self.side_by_side, bool):
+            return self.side_by_side if B % self.side_by_side == 0 else 1
+        for n in range(2, 9):
+            if B % n == 0 and B // n <= 96:
+                return n
+        return 1
 
     def params(self, B_ref, rep_weight, iterations, want_stats=False, **over):
         return capi.default_params(n_steps=iterations + 1, B_ref=int(B_ref), rep_weight=float(rep_weight),
@@ -123,6 +137,17 @@ class Restorer:
         R = planes.shape[2]
         L = capi.lib()
         P = self.params(B if B_ref is None else B_ref, rep_weight, iterations, want_stats=printing)
+        parts = 1 if printing else self._parts(B)
+        if parts > 1:
+            Bc = B // parts
+            one = (L.ifd_convonet_opt_workspace_bytes(Bc, K) + 255) // 256 * 256
+            ws = torch.empty(2 * one, dtype=torch.uint8, device=x.device)
+            pls = [planes[:, i * Bc:(i + 1) * Bc].contiguous() for i in range(parts)]
+            pp = (ctypes.c_void_p * parts)(*[t.data_ptr() for t in pls])
+            xp = (ctypes.c_void_p * parts)(*[x[i * Bc:(i + 1) * Bc].data_ptr() for i in range(parts)])
+            capi.check(L.ifd_convonet_opt_batches(parts, pp, capi.ptr(self.decoder.blob), xp, Bc, K, R, C, H, nb, ctypes.byref(P),
+                                                  capi.ptr(ws), ws.numel(), capi.stream()), "ifd_convonet_opt_batches")
+            return x if return_tensor else x.cpu().numpy()
         ws_bytes = L.ifd_convonet_opt_workspace_bytes(B, K)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         n_stat = iterations // 100 + 1

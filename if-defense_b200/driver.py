@@ -126,14 +126,29 @@ class Defender:
         """opt_defense.py:255-314.  pc: [N,K,3] array.  Returns float32 [N,sample_npoint,3]."""
         a = self.args
         if a.device_preprocess and isinstance(pc, np.ndarray) and pc.ndim == 3:
+            # Two-stage pipeline: SOR + preprocess + encoder of batch j+1 are enqueued on a side stream while the loop of
+            # batch j runs on the current one.  The random draws happen in batch order, as in the serial code.
             out = np.zeros((len(pc), a.sample_npoint, 3), dtype=np.float32)
-            # SOR first for the whole file, as the reference does (:277-279): the draws of later batches do not depend on it
-            for lo in range(0, len(pc), a.batch_size):
-                sel, pts = self.prepare_batch_device(pc[lo:lo + a.batch_size], rng, gen)
-                with torch.no_grad():
-                    c = self.model.encode_inputs(sel)
-                out[lo:lo + a.batch_size] = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight,
-                                                                          iterations=a.iterations, printing=printing)
+            side = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+
+            def stage(lo):
+                with torch.cuda.stream(side), torch.no_grad():
+                    sel, pts = self.prepare_batch_device(pc[lo:lo + a.batch_size], rng, gen)
+                    planes = convonet.planes_to_channels_last(self.model.encode_inputs(sel))
+                    done = torch.cuda.Event()
+                    done.record(side)
+                return pts, planes, done
+
+            starts = list(range(0, len(pc), a.batch_size))
+            nxt = stage(starts[0]) if starts else None
+            for j, lo in enumerate(starts):
+                pts, planes, done = nxt
+                main.wait_event(done)
+                x = self.restorer.optimize_points(pts, None, planes, rep_weight=a.rep_weight, iterations=a.iterations,
+                                                  printing=printing, return_tensor=True)
+                nxt = stage(starts[j + 1]) if j + 1 < len(starts) else None
+                out[lo:lo + a.batch_size] = x.cpu().numpy()
             return out
         pcs = self.sor_process(pc) if a.sor else [np.asarray(p, dtype=np.float32) for p in pc]
         out = np.zeros((len(pcs), a.sample_npoint, 3), dtype=np.float32)

@@ -312,3 +312,17 @@ def test_errors(dec, planes, conv):
     with pytest.raises(RuntimeError, match="c_dim = hidden_size = 32"):
         capi.check(L.ifd_convonet_decode_fwd(capi.ptr(planes), capi.ptr(dec.blob), capi.ptr(x), 2, 256, 64, 64, 64, 5, 0.1,
                                              capi.ptr(x), capi.stream()))
+
+
+def test_large_batch_runs_as_side_by_side_parts_with_the_same_bits(conv, dec):
+    """Restorer cuts a batch of >= 128 clouds into equal parts whose loops run next to each other (B_ref = the batch):
+    same bits as the single loop."""
+    reps = 128 // conv["p0"].shape[0] + 1
+    p0 = torch.from_numpy(np.concatenate([conv["p0"]] * reps)[:128].copy())
+    p0 += torch.randn(p0.shape, generator=torch.Generator().manual_seed(1)) * 1e-3
+    c = {k: dev(np.concatenate([conv["planes_nchw"][i]] * reps)[:128]) for i, k in enumerate(("xz", "xy", "yz"))}
+    one = convonet.Restorer(dec, side_by_side=False).optimize_points(p0, None, c, rep_weight=500., iterations=8)
+    assert convonet.Restorer(dec)._parts(128) == 2 and convonet.Restorer(dec)._parts(192) == 2 and convonet.Restorer(dec)._parts(64) == 1
+    for n in (True, 4):
+        got = convonet.Restorer(dec, side_by_side=n).optimize_points(p0, None, c, rep_weight=500., iterations=8)
+        assert np.array_equal(got, one), n
