@@ -228,6 +228,7 @@ int ifd_convonet_opt_batches(int n_batches, const float* const* planes_cl, const
                              int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* params,
                              void* workspace, size_t workspace_bytes, ifd_stream_t stream);
 
+
 /* Host-buffer convenience call (the end-to-end seam): planes in the reference's NCHW layout
  * [3][B][C][R][R], weights, xyz are HOST pointers; does H2D, layout conversion, the loop, D2H of xyz and
  * synchronises.  Device scratch is cached per thread between calls and released by ifd_release_cache(). */

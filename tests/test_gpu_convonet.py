@@ -323,6 +323,6 @@ def test_large_batch_runs_as_side_by_side_parts_with_the_same_bits(conv, dec):
     c = {k: dev(np.concatenate([conv["planes_nchw"][i]] * reps)[:128]) for i, k in enumerate(("xz", "xy", "yz"))}
     one = convonet.Restorer(dec, side_by_side=False).optimize_points(p0, None, c, rep_weight=500., iterations=8)
     assert convonet.Restorer(dec)._parts(128) == 2 and convonet.Restorer(dec)._parts(192) == 2 and convonet.Restorer(dec)._parts(64) == 1
-    for n in (True, 4):
+    for n in (True, 4, 2):
         got = convonet.Restorer(dec, side_by_side=n).optimize_points(p0, None, c, rep_weight=500., iterations=8)
         assert np.array_equal(got, one), n
