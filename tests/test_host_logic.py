@@ -64,3 +64,19 @@ def test_npz_wire_format(tmp_path):
     z = np.load(out)
     assert z["test_pc"].dtype == np.float32 and z["test_pc"].shape == (3, 1024, 3)
     assert z["test_label"].dtype == np.uint8 and z["target_label"].dtype == np.uint8
+
+
+def test_mesh_and_classifier_paths_fail_loudly_without_gpu():
+    """No CPU fallback: the mesh tail and the classifier geometry ops raise when there is no CUDA device."""
+    import numpy as np
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from ifdefense_b200 import classifiers, mesh
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mesh.marching_cubes(np.zeros((4, 4, 4)), 0.5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mesh.MISE(4, 1, 0.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        classifiers.DGCNN()(torch.zeros(1, 3, 64))
