@@ -199,7 +199,10 @@ def main():
     #      side by side on two streams (one launch fills 128 of the 148 SMs); every step still restores its own batch
     n_max = max(args.steps, W)
     xs = [torch.empty_like(x) for _ in range(n_max)]
-    ws2_bytes = 2 * ((ws_bytes + 255) // 256 * 256)
+    lanes = int(os.environ.get("IFD_LANES", "2"))          # experiment knob: loops side by side (default 2)
+    if lanes != 2:
+        L.ifd_test_hook(2, lanes)
+    ws2_bytes = max(lanes, 2) * ((ws_bytes + 255) // 256 * 256)
     ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device="cuda")
 
     def run_steps(j0, n):

@@ -744,14 +744,16 @@ extern "C" int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const
 // per SM, B = 64), so the loops of two batches side by side keep the remaining SMs -- and every gap between dependent
 // launches -- busy.  Forks from `stream` into two internal streams and joins back into it.
 namespace {
+constexpr int kMaxLanes = 4;
 struct PairStreams {
-  cudaStream_t s[2] = {nullptr, nullptr};
-  cudaEvent_t fork = nullptr, join[2] = {nullptr, nullptr};
+  cudaStream_t s[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr, join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
 };
+int g_lanes = 2;   // loops side by side; ifd_test_hook(2, n) (the workspace must then hold n parts)
 thread_local PairStreams g_pair;
 int ensure_pair() {
   if (g_pair.fork) return IFD_OK;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kMaxLanes; ++i) {
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pair.s[i], cudaStreamNonBlocking));
     IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pair.join[i], cudaEventDisableTiming));
   }
@@ -765,20 +767,21 @@ extern "C" int ifd_convonet_opt_batches(int n_batches, const float* const* plane
                                         size_t workspace_bytes, ifd_stream_t stream) {
   IFD_REQUIRE(n_batches >= 0 && planes_cl && dec_weights && xyz && P && workspace && B > 0 && K > 0, "ifd_convonet_opt_batches: bad arguments");
   const size_t one = align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
-  if (workspace_bytes < 2 * one) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_opt_batches: workspace must hold 2 x ifd_convonet_opt_workspace_bytes (256-byte aligned)");
+  const int lanes = g_lanes;
+  if (workspace_bytes < (size_t)lanes * one) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_opt_batches: workspace must hold 2 x ifd_convonet_opt_workspace_bytes (256-byte aligned)");
   int rc = ensure_pair();
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   IFD_CUDA_TRY(cudaEventRecord(g_pair.fork, st));
-  for (int i = 0; i < 2; ++i) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pair.s[i], g_pair.fork, 0));
+  for (int i = 0; i < lanes; ++i) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pair.s[i], g_pair.fork, 0));
   for (int j = 0; j < n_batches; ++j) {
-    const int s = j & 1;
+    const int s = j % lanes;
     IFD_REQUIRE(planes_cl[j] && xyz[j], "ifd_convonet_opt_batches: null batch pointer");
     if ((rc = ifd_convonet_opt(planes_cl[j], dec_weights, xyz[j], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr,
                                (char*)workspace + (size_t)s * one, one, g_pair.s[s])))
       return rc;
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < lanes; ++i) {
     IFD_CUDA_TRY(cudaEventRecord(g_pair.join[i], g_pair.s[i]));
     IFD_CUDA_TRY(cudaStreamWaitEvent(st, g_pair.join[i], 0));
   }
@@ -815,6 +818,7 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
 
 extern "C" void ifd_test_hook(int key, int value) {
   if (key == 1) g_inbox_cap = value < 0 ? 0 : (value > kCsInbox ? kCsInbox : value);
+  if (key == 2) g_lanes = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);
 }
 
 extern "C" int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream) {

@@ -342,7 +342,9 @@ long long ifd_launch_count(int reset);
 int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream);
 
 /* Test instrumentation.  key 1: capacity (0..16, default 16) of the per-point inbox of non-mutual in-edges in the
- * fused tail kernel; lowering it forces the ordered-scan fallback that hubs take.  Results do not depend on it. */
+ * fused tail kernel; lowering it forces the ordered-scan fallback that hubs take.  Results do not depend on it.
+ * key 2: number of loops ifd_convonet_opt_batches runs side by side (1..4, default 2; the workspace must then hold that many
+ * parts).  Measurement knob: 3 / 4 lanes gave +1.6 / +2.4 % over 2 at B = 64 and were not adopted. */
 void ifd_test_hook(int key, int value);
 
 #define IFD_PROFILE_KINDS 4
