@@ -164,17 +164,13 @@ class Generator3D:
         if self.dense:
             return self.decoder.eval_dense_grid(c, self.resolution0 * 2 ** self.upsampling_steps, self.padding, self.points_batch_size)
         threshold = np.log(self.threshold) - np.log(1. - self.threshold)
-        box_size = 1 + self.padding
         cc = torch.as_tensor(c).detach().float().reshape(1, -1).cuda().contiguous()
         extractor = MISE(self.resolution0, self.upsampling_steps, threshold)            # generation.py:113-130
+        ws = self.decoder._prepare_eval(cc, self.points_batch_size)                   # once per shape, not per round
         self.points_evaluated = 0
         points = extractor.query()
         while points.shape[0] != 0:
-            pointsf = box_size * (points.float() / extractor.resolution - 0.5)
-            values = torch.empty(points.shape[0], dtype=torch.float32, device="cuda")
-            for lo in range(0, points.shape[0], self.points_batch_size):
-                x = pointsf[lo:lo + self.points_batch_size].contiguous().view(1, -1, 3)
-                values[lo:lo + x.shape[1]] = self.decoder._logits_nograd(x, cc)
+            values = self.decoder.eval_lattice_points(points, extractor.resolution, cc, ws, self.padding, self.points_batch_size)
             self.points_evaluated += int(points.shape[0])
             extractor.update(points, values)
             points = extractor.query()

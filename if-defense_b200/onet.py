@@ -74,28 +74,52 @@ class ONetDecoder:
     def decode(self, p, z, c, **kwargs):
         return dist.Bernoulli(logits=_DecodeFn.apply(p, c, self))
 
-    def _logits_nograd(self, x, cc):
-        """x [1,K,3] cuda, cc [1,512] cuda -> logits [K] cuda (forward only, nothing saved)."""
+    def _prepare_eval(self, cc, k_max):
+        """ifd_onet_prepare for ONE shape (cc [1,512] cuda) on a workspace that holds chunks of up to k_max points.  The
+        prepared state (weight images, folded CBN scale/shift) sits at the head of the workspace and depends on B only, so
+        every later ifd_onet_decode_fwd with K <= k_max can reuse it."""
+        ws = self.ws.get(1, k_max, cc.device)
+        capi.check(capi.lib().ifd_onet_prepare(capi.ptr(self.blob), capi.ptr(cc), 1, k_max, capi.ptr(ws), ws.numel(), capi.stream()),
+                   "ifd_onet_prepare")
+        return ws
+
+    def _logits_prepared(self, x, ws):
+        """x [1,K,3] cuda -> logits [K] cuda (forward only, nothing saved); ws from _prepare_eval with k_max >= K."""
         K = x.shape[1]
-        L = capi.lib()
-        ws = self.ws.get(1, K, x.device)
-        capi.check(L.ifd_onet_prepare(capi.ptr(self.blob), capi.ptr(cc), 1, K, capi.ptr(ws), ws.numel(), capi.stream()), "ifd_onet_prepare")
         logits = torch.empty((1, K), dtype=torch.float32, device=x.device)
-        capi.check(L.ifd_onet_decode_fwd(capi.ptr(self.blob), capi.ptr(x), 1, K, capi.ptr(logits), capi.ptr(ws), ws.numel(),
-                                         capi.stream()), "ifd_onet_decode_fwd")
+        capi.check(capi.lib().ifd_onet_decode_fwd(capi.ptr(self.blob), capi.ptr(x), 1, K, capi.ptr(logits), capi.ptr(ws), ws.numel(),
+                                                  capi.stream()), "ifd_onet_decode_fwd")
         return logits[0]
+
+    def _logits_nograd(self, x, cc):
+        """x [1,K,3] cuda, cc [1,512] cuda -> logits [K] cuda."""
+        return self._logits_prepared(x, self._prepare_eval(cc, x.shape[1]))
 
     def eval_points(self, p, z=None, c=None, points_batch_size=100000):
         """Generator3D.eval_points (ONet/im2mesh/onet/generation.py:138-158): occupancy logits of N points for ONE shape,
-        in chunks of points_batch_size (the reference's default, configs/default.yaml), returned on the CPU."""
+        in chunks of points_batch_size (the reference's default, configs/default.yaml), returned on the CPU.  The weight
+        images and the CBN fold are prepared once per call, not per chunk."""
         capi.require_gpu()
         p = torch.as_tensor(p).detach().float()
         cc = torch.as_tensor(c).detach().float().reshape(1, -1).cuda().contiguous()
         out = torch.empty(p.shape[0], dtype=torch.float32)
+        if p.shape[0] == 0:
+            return out
+        ws = self._prepare_eval(cc, min(points_batch_size, p.shape[0]))
         for lo in range(0, p.shape[0], points_batch_size):
             x = p[lo:lo + points_batch_size].cuda().contiguous().view(1, -1, 3)
-            out[lo:lo + x.shape[1]] = self._logits_nograd(x, cc).cpu()
+            out[lo:lo + x.shape[1]] = self._logits_prepared(x, ws).cpu()
         return out
+
+    def eval_lattice_points(self, points, resolution, cc, ws, padding=0.1, points_batch_size=100000):
+        """Logits (float32 cuda [N]) of integer lattice points [N,3] (cuda int64) of the `resolution` lattice, in the
+        reference's coordinates: box_size * (points / resolution - 0.5) in float32 (generation.py:121-124)."""
+        pointsf = (1.0 + padding) * (points.float() / resolution - 0.5)
+        values = torch.empty(points.shape[0], dtype=torch.float32, device=points.device)
+        for lo in range(0, points.shape[0], points_batch_size):
+            x = pointsf[lo:lo + points_batch_size].contiguous().view(1, -1, 3)
+            values[lo:lo + x.shape[1]] = self._logits_prepared(x, ws)
+        return values
 
     def eval_dense_grid(self, c, resolution=128, padding=0.1, points_batch_size=100000):
         """The occupancy field generate_from_latent needs (ONet/im2mesh/onet/generation.py:101-130), evaluated densely
@@ -108,10 +132,11 @@ class ONetDecoder:
         cc = torch.as_tensor(c).detach().float().reshape(1, -1).cuda().contiguous()
         ax = (1.0 + padding) * (torch.arange(n, dtype=torch.float32, device="cuda") / resolution - 0.5)
         out = torch.empty(n * n * n, dtype=torch.float32, device="cuda")
+        ws = self._prepare_eval(cc, min(points_batch_size, n * n * n))
         for lo in range(0, n * n * n, points_batch_size):
             idx = torch.arange(lo, min(lo + points_batch_size, n * n * n), device="cuda")
             x = torch.stack([ax[idx // (n * n)], ax[(idx // n) % n], ax[idx % n]], dim=1).contiguous().view(1, -1, 3)
-            out[lo:lo + x.shape[1]] = self._logits_nograd(x, cc)
+            out[lo:lo + x.shape[1]] = self._logits_prepared(x, ws)
         return out.view(n, n, n)
 
 

@@ -266,7 +266,9 @@ int ifd_onet_prepare(const float* dec_weights, const float* c, int B, int K, voi
                      ifd_stream_t stream);
 
 /* OccupancyNetwork.decode(p, z, c).logits, z_dim = 0 (ONet/opt_defense.py:212; ONet/im2mesh/onet/models/decoder.py:
- * 115-133; CResnetBlockConv1d ONet/im2mesh/layers.py:98-107).  Needs ifd_onet_prepare on the same workspace. */
+ * 115-133; CResnetBlockConv1d ONet/im2mesh/layers.py:98-107).  Needs ifd_onet_prepare on the same workspace with the same
+ * B; the prepared state sits at the head of the workspace and does not depend on K, so K may differ from the prepare call
+ * as long as workspace_bytes >= ifd_onet_workspace_bytes(B, K) (chunked evaluation of one shape). */
 int ifd_onet_decode_fwd(const float* dec_weights, const float* xyz, int B, int K, float* logits_out, void* workspace,
                         size_t workspace_bytes, ifd_stream_t stream);
 /* Forward + backward w.r.t. xyz for grad_logits [B][K] -> grad_xyz_out [B][K][3]. */
