@@ -32,8 +32,8 @@ class Args:
     threshold = 0.2       # cfg['test']['threshold']
     input_npoint = 600    # cfg['data']['pointcloud_n'] (300 for ONet)
     device_preprocess = True   # SOR selection + preprocess_pc + init gather on the device (same bits as the numpy path)
-    encoder_chunk = 1     # sharded path only: clouds per encoder call.  1 makes the (torch/cuDNN) encoder see the same
-                          # shapes however the job is split, so the result does not depend on the number of ranks
+    encoder_chunk = 8     # sharded path only: clouds per encoder call; chunks are aligned to the job's cloud indices and
+                          # padded to full size, so that a cloud's planes do not depend on the number of ranks
 
     def __init__(self, **over):
         for k, v in over.items():
@@ -95,7 +95,9 @@ class Defender:
     def prepare_batch_device(self, raw, rng=None, gen=None):
         """sor_process + preprocess_pc + the encoder subset + init_points (opt_defense.py:86-179) for one batch [B,K,3] with the
         arrays on the device: SOR mask (`ifd_sor`), ragged selection + normalisation (`ifd_preprocess_pc`), gathers by the
-        indices the host RNGs draw (the same draws, in the same order, as the numpy path).  -> (sel [B,T,3], init [B,npoint,3])."""
+        indices the host RNGs draw (the same draws, in the same order, as the numpy path).  `rng` / `gen` may be lists with
+        one generator per cloud (the sharded path: draws that do not depend on how the job is cut).
+        -> (sel [B,T,3], init [B,npoint,3])."""
         from . import capi
         a = self.args
         x = torch.from_numpy(np.ascontiguousarray(np.asarray(raw)[..., :3], dtype=np.float32)).to(self.device)
@@ -113,10 +115,18 @@ class Defender:
         T = a.input_npoint
         if T is None or (n <= T).any():
             raise RuntimeError("device preprocess needs more than input_npoint points per cloud after SOR")
-        draw = rng if rng is not None else np.random
-        sel_idx = np.stack([draw.choice(int(k), T, replace=False) for k in n])                 # preprocess_pc :134-141
-        ini_idx = torch.stack([torch.randint(0, int(k), (a.sample_npoint,), generator=gen) for k in n])   # init_points :163-167
-        noise = torch.randn((B, a.sample_npoint, 3), generator=gen) * a.init_sigma
+        if isinstance(rng, (list, tuple)):                                                     # one stream per cloud
+            sel_idx = np.stack([r.choice(int(k), T, replace=False) for r, k in zip(rng, n)])
+            ini_idx, noise = [], []
+            for g, k in zip(gen, n):                                                           # init_points per cloud
+                ini_idx.append(torch.randint(0, int(k), (a.sample_npoint,), generator=g))
+                noise.append(torch.randn((a.sample_npoint, 3), generator=g) * a.init_sigma)
+            ini_idx, noise = torch.stack(ini_idx), torch.stack(noise)
+        else:
+            draw = rng if rng is not None else np.random
+            sel_idx = np.stack([draw.choice(int(k), T, replace=False) for k in n])             # preprocess_pc :134-141
+            ini_idx = torch.stack([torch.randint(0, int(k), (a.sample_npoint,), generator=gen) for k in n])   # init_points :163-167
+            noise = torch.randn((B, a.sample_npoint, 3), generator=gen) * a.init_sigma
         rows = torch.arange(B, device=self.device).view(B, 1)
         sel = allp[rows, torch.from_numpy(sel_idx).to(self.device)]
         pts = allp[rows, ini_idx.to(self.device)] + noise.to(self.device)
@@ -163,27 +173,49 @@ class Defender:
                                                                       iterations=a.iterations, printing=printing)
         return out
 
+    def encode_chunked(self, sel, first=0):
+        """encode_inputs for clouds first .. first + len(sel) - 1 of the job, in chunks of exactly `encoder_chunk` clouds that
+        are aligned to the JOB's cloud indices: cloud i always sits at position i % encoder_chunk of a full-size batch
+        (positions outside this slice are filled with a copy of one of its clouds).  cuDNN / cuBLAS kernels are deterministic
+        functions of (shape, position in the batch, the sample's own data) -- measured: at some batch sizes the position
+        matters in the last bit -- so a cloud's planes do not depend on where the slice boundaries fall."""
+        step = self.args.encoder_chunk or 1
+        n = sel.shape[0]
+        out = None
+        with torch.no_grad():
+            g0 = first - first % step
+            for g in range(g0, first + n, step):
+                idx = torch.arange(g, g + step)
+                inside = (idx >= first) & (idx < first + n)
+                src = torch.where(inside, idx - first, torch.zeros_like(idx)).to(sel.device)
+                c = self.model.encode_inputs(sel[src].contiguous())
+                pos = torch.nonzero(inside).flatten().to(sel.device)
+                if out is None:
+                    out = {k: [] for k in c}
+                for k, v in c.items():
+                    out[k].append(v[pos])
+        return {k: torch.cat(v) for k, v in out.items()}
+
     def restore_slice(self, pc, lo, hi, B_ref, seed):
         """Clouds lo..hi-1 of a reference batch of B_ref clouds, every random draw taken from a per-cloud stream
         (seed, cloud index) so that the result does not depend on how the job is cut into slices."""
         a = self.args
         raw = np.asarray(pc[lo:hi])[..., :3]
-        pcs = self.sor_process(raw) if a.sor else [np.asarray(p, dtype=np.float32) for p in raw]
-        proc, pts = [], []
-        for j, p in enumerate(pcs):
-            i = lo + j
-            allp, sel = preprocess_pc(p, num_points=a.input_npoint, padding_scale=a.padding_scale,
-                                      rng=np.random.default_rng([int(seed), i]))
-            proc.append(sel)
-            g = torch.Generator().manual_seed((int(seed) * 1000003 + i) % (2 ** 63 - 1))
-            pts.append(init_points([allp], a.sample_npoint, a.init_sigma, a.padding_scale, g)[0])
-        sel = torch.from_numpy(np.stack(proc)).float().to(self.device)
-        step = a.encoder_chunk or len(proc)
-        with torch.no_grad():
-            parts = [self.model.encode_inputs(sel[i:i + step]) for i in range(0, len(proc), step)]
-        c = {k: torch.cat([q[k] for q in parts]) for k in parts[0]}
-        return self.restorer.optimize_points(torch.stack(pts), None, c, rep_weight=a.rep_weight, iterations=a.iterations,
-                                             B_ref=B_ref)
+        rngs = [np.random.default_rng([int(seed), i]) for i in range(lo, hi)]
+        gens = [torch.Generator().manual_seed((int(seed) * 1000003 + i) % (2 ** 63 - 1)) for i in range(lo, hi)]
+        if a.device_preprocess and raw.ndim == 3:
+            sel, pts = self.prepare_batch_device(raw, rngs, gens)
+        else:
+            pcs = self.sor_process(raw) if a.sor else [np.asarray(p, dtype=np.float32) for p in raw]
+            proc, pts = [], []
+            for p, r, g in zip(pcs, rngs, gens):
+                allp, s_ = preprocess_pc(p, num_points=a.input_npoint, padding_scale=a.padding_scale, rng=r)
+                proc.append(s_)
+                pts.append(init_points([allp], a.sample_npoint, a.init_sigma, a.padding_scale, g)[0])
+            sel = torch.from_numpy(np.stack(proc)).float().to(self.device)
+            pts = torch.stack(pts)
+        c = self.encode_chunked(sel, lo)
+        return self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight, iterations=a.iterations, B_ref=B_ref)
 
     def defend_point_cloud_sharded(self, pc, seed=0, rank=None, world=None):
         """defend_point_cloud across the ranks of torch.distributed (one process per GPU): every reference batch is

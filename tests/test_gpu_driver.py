@@ -79,3 +79,26 @@ def test_device_preprocess_path_equals_host_path():
         d = driver.Defender(model, driver.Args(batch_size=3, iterations=6, device_preprocess=dev_path))
         outs.append(d.defend_point_cloud(pc, rng=np.random.default_rng(5), gen=torch.Generator().manual_seed(5)))
     assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
+
+
+def test_sharded_slices_device_path_and_encoder_chunks():
+    """restore_slice: the device pre-processing path equals the per-cloud numpy path, and with fixed-size encoder chunks
+    (last one padded) a cloud's result does not depend on where the slice boundaries fall."""
+    model = models.build_convonet()
+    model.load_state_dict(models.synthetic_state_dict("convonet", 0))
+    pc = synth.clouds(6)
+    pc[2, :5] -= 0.7
+    dev_d = driver.Defender(model, driver.Args(batch_size=6, iterations=5, encoder_chunk=4, device_preprocess=True))
+    host_d = driver.Defender(model, driver.Args(batch_size=6, iterations=5, encoder_chunk=4, device_preprocess=False))
+    full = dev_d.restore_slice(pc, 0, 6, 6, 11)
+    assert np.array_equal(full, host_d.restore_slice(pc, 0, 6, 6, 11))
+    for cuts in ([0, 3, 6], [0, 1, 6], [0, 2, 4, 5, 6]):
+        out = np.concatenate([dev_d.restore_slice(pc, a, b, 6, 11) for a, b in zip(cuts[:-1], cuts[1:])])
+        assert np.array_equal(out, full), cuts
+    # the encoder alone: planes of a cloud do not depend on the slice it arrives in (chunks aligned to job indices)
+    import torch
+    sel = torch.rand(7, 600, 3, device="cuda", generator=torch.Generator("cuda").manual_seed(0)) - 0.5
+    whole = dev_d.encode_chunked(sel, 0)
+    for lo in (1, 3, 4, 6):
+        part = dev_d.encode_chunked(sel[lo:], lo)
+        assert all(torch.equal(whole[k][lo:], part[k]) for k in whole), lo
