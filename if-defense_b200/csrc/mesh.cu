@@ -438,7 +438,8 @@ static int mc_grid(McGrid* g, const void* vol, int dtype, int nx, int ny, int nz
   g->cy = g->py - 1;
   g->cz = g->pz - 1;
   g->ncells = (long long)g->cx * g->cy * g->cz;
-  IFD_REQUIRE(g->ncells < (1ll << 31), "marching cubes: lattice too large (2^31 cells)");
+  // vertex / index prefixes are 32-bit: at most 12 vertices and 15 indices per cell
+  IFD_REQUIRE(g->ncells <= (1ll << 28), "marching cubes: lattice too large (more than 2^28 cells)");
   return IFD_OK;
 }
 
