@@ -80,3 +80,40 @@ def test_mesh_and_classifier_paths_fail_loudly_without_gpu():
         mesh.MISE(4, 1, 0.0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         classifiers.DGCNN()(torch.zeros(1, 3, 64))
+
+
+def test_encode_chunked_places_clouds_at_job_aligned_positions():
+    """Defender.encode_chunked (host logic, CPU stub): every encoder call sees exactly `encoder_chunk` clouds, cloud i of the
+    job sits at position i % chunk, and the outputs come back in slice order."""
+    import types
+    import torch
+    from ifdefense_b200 import driver
+    calls = []
+
+    class Model:
+        def encode_inputs(self, x):
+            calls.append(x.clone())
+            pos = torch.arange(x.shape[0], dtype=torch.float32).view(-1, 1)
+            return {"xz": torch.cat([x[:, 0, :1], pos], dim=1)}          # (cloud tag, position in the batch)
+
+    stub = types.SimpleNamespace(args=types.SimpleNamespace(encoder_chunk=4), model=Model())
+    sel = torch.arange(100, 107, dtype=torch.float32).view(7, 1, 1).expand(7, 5, 3).contiguous()    # clouds tagged 100..106
+    for first in (0, 1, 3, 4, 6):
+        calls.clear()
+        out = driver.Defender.encode_chunked(stub, sel, first)["xz"]
+        assert out.shape == (7, 2)
+        assert torch.equal(out[:, 0], torch.arange(100, 107, dtype=torch.float32))                   # slice order kept
+        assert torch.equal(out[:, 1], ((torch.arange(7) + first) % 4).float())                       # job-aligned position
+        assert all(c.shape[0] == 4 for c in calls)                                                   # always full chunks
+        assert len(calls) == (first % 4 + 7 + 3) // 4
+
+
+def test_restorer_part_policy():
+    from ifdefense_b200 import convonet
+    r = convonet.Restorer.__new__(convonet.Restorer)
+    r.side_by_side = True
+    assert [r._parts(b) for b in (1, 64, 127, 128, 164, 192, 193, 256, 384)] == [1, 1, 1, 2, 2, 2, 1, 4, 4]
+    r.side_by_side = False
+    assert r._parts(192) == 1
+    r.side_by_side = 3
+    assert r._parts(192) == 3 and r._parts(128) == 1
