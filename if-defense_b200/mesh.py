@@ -197,3 +197,19 @@ def resample_points(generator, encode_inputs, ori_pc, num_points=1024, input_npo
             return ori_pc[rng.choice(ori_pc.shape[0], num_points, replace=False)]
         pc[:ori_pc.shape[0]] = ori_pc
         return pc
+
+
+def resample_points_sharded(generator, encode_inputs, clouds, num_points=1024, seed=0, rank=None, world=None, device=None,
+                            resample=None, **kw):
+    """The file loop of remesh_defense.py:189-225 over the ranks of torch.distributed (one process per GPU): clouds are
+    independent, so rank r re-meshes a contiguous block and one all_gather returns all [n, num_points, 3] clouds in input
+    order on every rank.  Cloud i draws from its own stream (seed, i), so the result does not depend on the number of ranks.
+    `resample` (default resample_points) is the per-cloud function."""
+    from . import shard
+    fn = resample if resample is not None else resample_points
+
+    def block(lo, hi, _n):
+        return np.stack([np.asarray(fn(generator, encode_inputs, clouds[i], num_points=num_points,
+                                       rng=np.random.default_rng([int(seed), i]), **kw), dtype=np.float32) for i in range(lo, hi)])
+
+    return shard.restore_sharded(block, len(clouds), max(len(clouds), 1), rank=rank, world=world, device=device)

@@ -79,3 +79,37 @@ def test_gloo_world(world, n, bs):
         assert p.exitcode == 0
     assert sorted(r for r, _, _ in res) == list(range(world))
     assert all(ok for _, ok, _ in res) and all(shape == (n, 5, 3) for _, _, shape in res)
+
+
+def _mesh_stub(generator, encode_inputs, pc, num_points=1024, rng=None):
+    """Stand-in for mesh.resample_points (needs a GPU): depends on the cloud and on the cloud's own random stream."""
+    return (pc[:num_points] * 0.5 + rng.random((num_points, 3))).astype(np.float32)
+
+
+def _mesh_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ifdefense_b200 import mesh
+        clouds = np.random.default_rng(3).normal(size=(n, 16, 3)).astype(np.float32)
+        got = mesh.resample_points_sharded(None, None, clouds, num_points=8, seed=5, resample=_mesh_stub)
+        want = mesh.resample_points_sharded(None, None, clouds, num_points=8, seed=5, resample=_mesh_stub, rank=0, world=1)
+        q.put((rank, np.array_equal(got, want), got.shape))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 5), (3, 2)])
+def test_gloo_mesh_resampling_is_independent_of_the_world_size(world, n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_mesh_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok and shape == (n, 8, 3) for _, ok, shape in res)
