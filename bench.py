@@ -108,6 +108,25 @@ def cpu_port_time(case, iterations, threads):
     return time.perf_counter() - t0
 
 
+_JSON_OUT = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout, but libraries write there too (NCCL prints its version banner to fd 1
+    under torchrun).  Everything that goes to fd 1 from here on lands on stderr; emit() writes to the real stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU path for this metric (oracle port), rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -126,7 +145,7 @@ def run_reference(args):
     full = per_step * (ITERS + 1)
     value = B / full
     sample = "B=%d x %d pts, %d of 201 Adam steps per bench step, scaled to 201" % (B, K, n_it)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "restored clouds/sec (N=1024, 200 iters)", "value": value, "unit": "clouds/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -321,7 +340,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "restored clouds/sec (N=1024, 200 iters)", "value": value, "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -334,4 +353,5 @@ def main():
 
 
 if __name__ == "__main__":
+    _protect_stdout()
     main()

@@ -117,3 +117,16 @@ def test_restorer_part_policy():
     assert r._parts(192) == 1
     r.side_by_side = 3
     assert r._parts(192) == 3 and r._parts(128) == 1
+
+
+def test_bench_emits_exactly_one_stdout_line_despite_library_chatter():
+    """bench.py's contract is one JSON line on stdout; NCCL prints its version banner to fd 1 under torchrun.  After
+    _protect_stdout() everything written to fd 1 goes to stderr and emit() alone reaches the real stdout."""
+    import subprocess
+    import sys
+    from .conftest import ROOT
+    code = ("import bench, os\nbench._protect_stdout()\nos.write(1, b'NCCL version x\\n')\nprint('chatter')\n"
+            "bench.emit('{\"a\": 1}')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and r.stdout == '{"a": 1}\n'
+    assert "NCCL version x" in r.stderr and "chatter" in r.stderr
