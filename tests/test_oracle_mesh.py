@@ -112,3 +112,31 @@ def test_mise_restatement_equals_reference_fixture(name):
     assert hashlib.sha256(np.ascontiguousarray(dense).tobytes()).hexdigest() == str(g[name + "_sha256"])
     if name + "_dense" in g:
         assert np.array_equal(dense, g[name + "_dense"].astype(np.float64))
+
+
+def test_oracle_generate_from_latent_equals_reference_generator3d():
+    """tests/golden/generator.npz records a run of the reference's OWN Generator3D.generate_from_latent (its MISE, its
+    marching cubes, its decoder, CPU).  Fed with the values that run evaluated, the oracle's MISE asks for exactly the same
+    points in every round and hands the same lattice to marching cubes; the oracle's extract_mesh returns the same
+    vertices and faces, bit for bit and in order.  The oracle decoder reproduces the logged values to fp32 rounding."""
+    import torch
+    from ifdefense_b200 import models
+    from oracle import torch_port as tp
+    g = np.load(os.path.join(GOLDEN, "generator.npz"))
+    res, thr = 32, np.log(0.2) - np.log(0.8)
+    ijk = np.rint((g["points_f"].astype(np.float64) / 1.1 + 0.5) * res).astype(np.int64)
+    assert np.abs((1.1 * (ijk.astype(np.float32) / res - 0.5)) - g["points_f"]).max() == 0       # exact inverse of :121-124
+    table = {tuple(p): v for p, v in zip(ijk.tolist(), g["values"].tolist())}
+    assert len(table) == len(ijk)                                                                # no point evaluated twice
+
+    def lookup(pts):
+        return np.array([table[tuple(p)] for p in pts.tolist()])                                 # KeyError = a point the reference never asked for
+    dense, rounds = mise_port.mise_loop(lookup, 8, 2, thr)
+    assert rounds == list(g["rounds"])
+    assert np.array_equal(dense, g["value_grid"].astype(np.float64))
+    v, f = co.extract_mesh(dense, threshold=0.2, padding=0.1)
+    assert np.array_equal(v, g["verts"]) and np.array_equal(f, g["faces"])
+    sd = models.synthetic_state_dict("onet", 0)
+    sd["decoder.fc_out.bias"] = sd["decoder.fc_out.bias"] + float(g["bias_shift"])
+    got = tp.onet_decode(sd, torch.from_numpy(g["points_f"])[None], torch.from_numpy(g["c"]))[0].numpy()
+    assert np.abs(got - g["values"]).max() < 2e-5
