@@ -67,3 +67,32 @@ def test_no_cpu_fallback(lib_path):
         defense.knn_point(5, torch.zeros(1, 16, 3))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         defense.repulsion_loss(torch.zeros(1, 16, 3))
+
+
+def test_header_is_plain_c_and_every_symbol_links(lib_path, tmp_path):
+    """include/ifd_b200.h compiles as strict C99, a C program that takes the address of EVERY declared entry point links
+    against the library, and tests/c_abi/abi_check.c (argument validation through the C ABI) runs without a GPU."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(lib_path)
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c",
+                           os.path.join(inc, "ifd_b200.h")])
+    src = tmp_path / "all_symbols.c"
+    syms = header_symbols()
+    src.write_text('#include <stdio.h>\n#include "ifd_b200.h"\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t t[] = {\n'
+                   + "".join("    (fn_t)%s,\n" % s for s in syms)
+                   + "  };\n  unsigned i, n = 0;\n  for (i = 0; i < sizeof t / sizeof t[0]; ++i) n += t[i] != 0;\n"
+                     '  printf("%u\\n", n);\n  return 0;\n}\n')
+    exe = tmp_path / "all_symbols"
+    link = ["-I", inc, "-L", libdir, "-lifd_b200", "-Wl,-rpath," + libdir]
+    subprocess.check_call([gcc, "-std=c99", "-Wall", str(src), "-o", str(exe)] + link)
+    assert int(subprocess.check_output([str(exe)]).decode()) == len(syms)
+    exe2 = tmp_path / "abi_check"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", os.path.join(ROOT, "tests", "c_abi", "abi_check.c"),
+                           "-o", str(exe2)] + link)
+    out = subprocess.run([str(exe2)], capture_output=True, text=True)
+    assert out.returncode == 0 and "abi ok" in out.stdout, out.stdout
