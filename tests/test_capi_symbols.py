@@ -96,3 +96,9 @@ def test_header_is_plain_c_and_every_symbol_links(lib_path, tmp_path):
                            "-o", str(exe2)] + link)
     out = subprocess.run([str(exe2)], capture_output=True, text=True)
     assert out.returncode == 0 and "abi ok" in out.stdout, out.stdout
+    # the C example of INTEGRATION.md builds and answers with its usage text
+    exe3 = tmp_path / "restore_host"
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", os.path.join(ROOT, "examples", "restore_host.c"),
+                           "-o", str(exe3)] + link)
+    out = subprocess.run([str(exe3)], capture_output=True, text=True)
+    assert out.returncode == 2 and "usage" in out.stderr
