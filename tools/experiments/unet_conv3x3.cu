@@ -227,3 +227,19 @@ int conv3x3_cl(const float* in0, const float* in1, const float* img, const float
 }
 
 }  // namespace ifd
+
+// C entry points for tools/experiments/test_unet_conv3x3.py (device pointers)
+extern "C" int exp_conv3x3_pack(const float* W, int Cout, int Cin, float* img, void* stream) {
+  const int n = Cout * Cin * 9;
+  ifd::conv3x3_pack_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, Cout, Cin, img);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+extern "C" int exp_conv3x3(const float* in0, const float* in1, const float* img, const float* bias, float* out, int B, int H, int W,
+                           int C0, int C1, int Cout, int relu, void* stream) {
+  return ifd::conv3x3_cl(in0, in1, img, bias, out, B, H, W, C0, C1, Cout, relu, (cudaStream_t)stream);
+}
+extern "C" int exp_maxpool2(const float* in, int B, int H, int W, int C, float* out, void* stream) {
+  const size_t n = (size_t)B * (H / 2) * (W / 2) * (C / 4);
+  ifd::maxpool2_cl_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, B, H, W, C, out);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
