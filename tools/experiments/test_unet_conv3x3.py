@@ -62,6 +62,29 @@ def main():
         print("B %d H %d Cin %d Cout %d: rc %d max|err| %.3g (scale %.3g)  ours %.3f ms  cuDNN fp32 %.3f ms" % (
             B, H, Cin, Cout, rc, err, want.abs().max().item(), ev[0].elapsed_time(ev[1]) / 10, ev[1].elapsed_time(ev[2]) / 10))
 
+    # 1x1 convolution, 2x2 transposed convolution, 2x2 max pooling
+    for B, H, Cin, Cout in [(2, 64, 32, 32), (2, 8, 256, 128), (2, 16, 128, 64), (2, 32, 64, 32)]:
+        x = torch.randn(B, H, H, Cin, device="cuda", generator=g)
+        xn = x.permute(0, 3, 1, 2).contiguous()
+        w1 = torch.randn(Cout, Cin, 1, 1, device="cuda", generator=g) / Cin ** 0.5
+        wt = torch.randn(Cin, Cout, 2, 2, device="cuda", generator=g) / Cin ** 0.5
+        b = torch.randn(Cout, device="cuda", generator=g) * 0.1
+        img1 = torch.empty((Cin // 32) * 2 * Cout * 32, device="cuda")
+        imgt = torch.empty((Cin // 32) * 2 * 4 * Cout * 32, device="cuda")
+        assert L.exp_gemm_pack(vp(w1.data_ptr()), Cout, Cin, 0, Cout, vp(img1.data_ptr()), vp(st)) == 0
+        assert L.exp_gemm_pack(vp(wt.data_ptr()), 4 * Cout, Cin, 1, Cout, vp(imgt.data_ptr()), vp(st)) == 0
+        o1 = torch.empty(B, H, H, Cout, device="cuda")
+        ot = torch.empty(B, 2 * H, 2 * H, Cout, device="cuda")
+        op = torch.empty(B, H // 2, H // 2, Cin, device="cuda")
+        r1 = L.exp_conv1x1(vp(x.data_ptr()), vp(img1.data_ptr()), vp(b.data_ptr()), vp(o1.data_ptr()), B, H, H, Cin, Cout, vp(st))
+        rt = L.exp_upconv2x2(vp(x.data_ptr()), vp(imgt.data_ptr()), vp(b.data_ptr()), vp(ot.data_ptr()), B, H, H, Cin, Cout, vp(st))
+        rp = L.exp_maxpool2(vp(x.data_ptr()), B, H, H, Cin, vp(op.data_ptr()), vp(st))
+        torch.cuda.synchronize()
+        e1 = (o1 - F.conv2d(xn, w1, b).permute(0, 2, 3, 1)).abs().max().item()
+        et = (ot - F.conv_transpose2d(xn, wt, b, stride=2).permute(0, 2, 3, 1)).abs().max().item()
+        ep = (op - F.max_pool2d(xn, 2, 2).permute(0, 2, 3, 1)).abs().max().item()
+        print("H %d Cin %d Cout %d: rc %d %d %d  1x1 err %.3g  upconv err %.3g  maxpool err %.3g" % (H, Cin, Cout, r1, rt, rp, e1, et, ep))
+
 
 if __name__ == "__main__":
     sys.exit(main())

@@ -8,7 +8,9 @@
 //     the image (padding = 1);
 //   * two inputs (skip connection + upsampled tensor) are read as one concatenated channel range, so torch.cat goes away;
 //   * N = output channels handled by one CTA (32 / 64 / 128), blockIdx.y selects the channel block;
-//   * epilogue: bias, optional ReLU, channels-last store.
+//   * epilogue: bias, optional ReLU, channels-last store;
+//   * the same kernel with one tap is the 1x1 convolution and, with N = 4 Cout and a pixel-shuffle store, the 2x2
+//     transposed convolution.
 // Compile check:  nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -I if-defense_b200/csrc -I include \
 //                      -c tools/experiments/unet_conv3x3.cu -o /tmp/unet_conv3x3.o
 // To do when it moves into csrc/: parity test against F.conv2d (fp32, TF32 off) at all five U-Net shapes, maxpool and the
@@ -35,6 +37,25 @@ __global__ void conv3x3_pack_kernel(const float* __restrict__ W, int Cout, int C
   chunk[Cout * kConvChunk + off] = __uint_as_float(umma::tf32_lo(w));
 }
 
+// Generic per-pixel GEMM operand: Bm[n][k] given by a functor of the torch tensor -> chunked K-major images (one tap).
+// mode 0: Conv2d 1x1 weight [N][K][1][1];  mode 1: ConvTranspose2d weight [K][Cout][2][2] with n = (dy * 2 + dx) * Cout + co.
+__global__ void gemm_pack_kernel(const float* __restrict__ W, int N, int K, int mode, int Cout, float* __restrict__ img) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * K) return;
+  const int n = e / K, k = e % K;
+  float w;
+  if (mode == 0) w = W[(size_t)n * K + k];
+  else {
+    const int q = n / Cout, co = n % Cout;
+    w = W[(((size_t)k * Cout + co) * 2 + q / 2) * 2 + q % 2];
+  }
+  const int kc = k / kConvChunk, kl = k % kConvChunk;
+  float* chunk = img + (size_t)kc * 2 * N * kConvChunk;
+  const uint32_t off = umma::img_offset(n, kl, N) / 4;
+  chunk[off] = __uint_as_float(umma::tf32_hi(w));
+  chunk[N * kConvChunk + off] = __uint_as_float(umma::tf32_lo(w));
+}
+
 struct ConvArgs {
   const float* in0;   // [B][H][W][C0] channels-last
   const float* in1;   // [B][H][W][C1] or nullptr (C1 = 0): channels C0 .. C0 + C1 - 1 of the concatenation
@@ -42,6 +63,9 @@ struct ConvArgs {
   const float* bias;  // [Cout]
   float* out;         // [B][H][W][Cout]
   int B, H, W, C0, C1, Cout, relu;
+  int taps;           // 9: 3x3 convolution with padding 1; 1: 1x1 convolution / per-pixel GEMM
+  int shuffle;        // 0: out[pixel][Cout]; otherwise Cout = 4 * shuffle and GEMM column q * shuffle + co goes to pixel
+                      // (2y + q / 2, 2x + q % 2), channel co of an image [B][2H][2W][shuffle]  (ConvTranspose2d k = 2, s = 2)
 };
 
 template <int N>
@@ -54,7 +78,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3x3_kernel(const ConvArgs
   const int warp = threadIdx.x >> 5;
   const int nb = blockIdx.y;                                        // output-channel block
   const int Cin = a.C0 + a.C1;
-  const int n_chunks = 9 * (Cin / kConvChunk);
+  const int n_chunks = a.taps * (Cin / kConvChunk);
   if (warp == 0) umma::tmem_alloc(tmem_slot, 256);                  // D: columns 0..N-1, A chunks: 128..255
   if (threadIdx.x == 32) {
     umma::mbar_init(&bars[0], 1);
@@ -89,7 +113,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3x3_kernel(const ConvArgs
   auto slice = [&](int kc) -> const float4* {
     const int per_tap = Cin / kConvChunk;
     const int tap = kc / per_tap, cc = kc % per_tap;
-    const int y = py + tap / 3 - 1, x = px + tap % 3 - 1;
+    const int y = a.taps == 9 ? py + tap / 3 - 1 : py, x = a.taps == 9 ? px + tap % 3 - 1 : px;
     if (y < 0 || y >= a.H || x < 0 || x >= a.W) return nullptr;
     const size_t pix = ((size_t)pb * a.H + y) * a.W + x;
     const int c = cc * kConvChunk;
@@ -160,13 +184,18 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv3x3_kernel(const ConvArgs
     umma::fence_after_sync();
   }
   float* orow = a.out + (size_t)rowc * a.Cout + nb * N;
+  if (a.shuffle) {                                   // the whole column block lies inside one (dy, dx) quadrant (N <= shuffle)
+    const int q = (nb * N) / a.shuffle, co0 = (nb * N) % a.shuffle;
+    const size_t opix = ((size_t)pb * 2 * a.H + 2 * py + q / 2) * 2 * a.W + 2 * px + q % 2;
+    orow = a.out + opix * a.shuffle + co0;
+  }
   const bool live = row < M;
 #pragma unroll 1
   for (int cl = 0; cl < N / 32; ++cl) {
     uint32_t d[32];
     umma::tmem_ld32(lane_t + cl * 32, d);
     float y[32];
-    const float4* b4 = reinterpret_cast<const float4*>(a.bias + nb * N + cl * 32);
+    const float4* b4 = reinterpret_cast<const float4*>(a.bias + (a.shuffle ? (nb * N) % a.shuffle : nb * N) + cl * 32);
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 bv = __ldg(b4 + q);
@@ -220,10 +249,25 @@ int conv3x3_cl(const float* in0, const float* in1, const float* img, const float
                int C1, int Cout, int relu, cudaStream_t st) {
   IFD_REQUIRE(in0 && img && bias && out && B > 0 && H > 0 && W > 0, "conv3x3_cl: bad arguments");
   IFD_REQUIRE(C0 % 32 == 0 && C1 % 32 == 0 && C0 > 0 && (C1 == 0 || in1) && Cout % 32 == 0 && Cout > 0, "conv3x3_cl: channels must be multiples of 32");
-  ConvArgs a{in0, in1, img, bias, out, B, H, W, C0, C1, Cout, relu};
+  ConvArgs a{in0, in1, img, bias, out, B, H, W, C0, C1, Cout, relu, 9, 0};
   if (Cout % 128 == 0) return launch_conv<128>(a, st);
   if (Cout % 64 == 0) return launch_conv<64>(a, st);
   return launch_conv<32>(a, st);
+}
+
+// 1x1 convolution (unet.py conv_final): weights packed by gemm_pack_kernel with N = Cout
+int conv1x1_cl(const float* in, const float* img, const float* bias, float* out, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  IFD_REQUIRE(in && img && bias && out && Cin % 32 == 0 && Cout % 32 == 0 && Cin > 0 && Cout > 0, "conv1x1_cl: bad arguments");
+  ConvArgs a{in, nullptr, img, bias, out, B, H, W, Cin, 0, Cout, 0, 1, 0};
+  return Cout % 128 == 0 ? launch_conv<128>(a, st) : Cout % 64 == 0 ? launch_conv<64>(a, st) : launch_conv<32>(a, st);
+}
+
+// ConvTranspose2d(Cin, Cout, kernel_size = 2, stride = 2) (unet.py upconv2x2): one GEMM with N = 4 Cout and a pixel-shuffle
+// store; out [B][2H][2W][Cout].  Weights packed by upconv_pack_kernel.
+int upconv2x2_cl(const float* in, const float* img, const float* bias, float* out, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  IFD_REQUIRE(in && img && bias && out && Cin % 32 == 0 && Cout % 32 == 0 && Cin > 0 && Cout > 0, "upconv2x2_cl: bad arguments");
+  ConvArgs a{in, nullptr, img, bias, out, B, H, W, Cin, 0, 4 * Cout, 0, 1, Cout};
+  return Cout % 128 == 0 ? launch_conv<128>(a, st) : Cout % 64 == 0 ? launch_conv<64>(a, st) : launch_conv<32>(a, st);
 }
 
 }  // namespace ifd
@@ -237,6 +281,18 @@ extern "C" int exp_conv3x3_pack(const float* W, int Cout, int Cin, float* img, v
 extern "C" int exp_conv3x3(const float* in0, const float* in1, const float* img, const float* bias, float* out, int B, int H, int W,
                            int C0, int C1, int Cout, int relu, void* stream) {
   return ifd::conv3x3_cl(in0, in1, img, bias, out, B, H, W, C0, C1, Cout, relu, (cudaStream_t)stream);
+}
+extern "C" int exp_gemm_pack(const float* W, int N, int K, int mode, int Cout, float* img, void* stream) {
+  ifd::gemm_pack_kernel<<<(N * K + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, N, K, mode, Cout, img);
+  return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+extern "C" int exp_conv1x1(const float* in, const float* img, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
+                           void* stream) {
+  return ifd::conv1x1_cl(in, img, bias, out, B, H, W, Cin, Cout, (cudaStream_t)stream);
+}
+extern "C" int exp_upconv2x2(const float* in, const float* img, const float* bias, float* out, int B, int H, int W, int Cin, int Cout,
+                             void* stream) {
+  return ifd::upconv2x2_cl(in, img, bias, out, B, H, W, Cin, Cout, (cudaStream_t)stream);
 }
 extern "C" int exp_maxpool2(const float* in, int B, int H, int W, int C, float* out, void* stream) {
   const size_t n = (size_t)B * (H / 2) * (W / 2) * (C / 4);
