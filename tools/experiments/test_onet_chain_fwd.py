@@ -1,4 +1,4 @@
-"""Round-2 starting point: builds tools/experiments/onet_chain_fwd.cu on the GPU box and compares the fused 10-layer forward
+"""Round-2 starting point: builds tools/experiments/onet_chain_fwd.cu.txt on the GPU box and compares the fused 10-layer forward
 chain with the product's layered path (ifd_onet_prepare + ifd_onet_decode_fwd), then times both on one MISE-sized round.
     python tools/experiments/test_onet_chain_fwd.py          (needs a B200; nothing here is part of the product)"""
 import ctypes
@@ -16,9 +16,9 @@ from ifdefense_b200 import models, onet as onet_mod, synth  # noqa: E402
 
 def build():
     out = os.path.join(tempfile.mkdtemp(prefix="exp_chain_"), "libexp_chain.so")
-    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-shared",
+    subprocess.check_call(["nvcc", "-x", "cu", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-shared",
                            "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "if-defense_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tools", "experiments", "onet_chain_fwd.cu"), "-o", out,
+                           os.path.join(ROOT, "tools", "experiments", "onet_chain_fwd.cu.txt"), "-o", out,
                            "-L", os.path.join(ROOT, "if-defense_b200"), "-lifd_b200",
                            "-Xlinker", "-rpath," + os.path.join(ROOT, "if-defense_b200")])
     return ctypes.CDLL(out)

@@ -1,4 +1,4 @@
-"""Round-2 starting point: builds tools/experiments/unet_conv3x3.cu into a scratch library on the GPU box and compares the
+"""Round-2 starting point: builds tools/experiments/unet_conv3x3.cu.txt into a scratch library on the GPU box and compares the
 tcgen05 implicit-GEMM convolution with F.conv2d (fp32, TF32 off) at the U-Net's shapes, then times both.
     python tools/experiments/test_unet_conv3x3.py            (needs a B200; nothing here is part of the product)"""
 import ctypes
@@ -16,9 +16,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 def build():
     out = os.path.join(tempfile.mkdtemp(prefix="exp_conv_"), "libexp_conv.so")
     # common.cuh's helpers (fail, launch counter, set_max_dyn_smem) live in the product library: link against it
-    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-shared",
+    subprocess.check_call(["nvcc", "-x", "cu", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-shared",
                            "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "if-defense_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tools", "experiments", "unet_conv3x3.cu"), "-o", out,
+                           os.path.join(ROOT, "tools", "experiments", "unet_conv3x3.cu.txt"), "-o", out,
                            "-L", os.path.join(ROOT, "if-defense_b200"), "-lifd_b200",
                            "-Xlinker", "-rpath," + os.path.join(ROOT, "if-defense_b200")])
     return ctypes.CDLL(out)
