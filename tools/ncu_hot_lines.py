@@ -16,7 +16,7 @@ def main():
     data = [r for r in rows[2:] if len(r) == len(hdr) and r[si].isdigit()]
     tot = sum(int(r[si]) for r in data)
     print('rows', len(data), 'total samples', tot, 'total inst', sum(int(r[ie]) for r in data))
-    names = [n for n in hdr if n.startswith('stall_')]
+    names = [n for n in hdr if n.startswith('stall_') and not n.endswith(')')]
     col = {n: hdr.index(n) for n in names}
     print({n: sum(int(r[col[n]]) for r in data) for n in names})
     cum = 0
