@@ -83,6 +83,10 @@ class Defender:
         self.decoder = convonet.ConvONetDecoder(sd, padding=self.model.decoder.padding, device=self.device)
         self.restorer = convonet.Restorer(self.decoder, threshold=self.args.threshold, lr=self.args.lr)
 
+    def _encode(self, sel):
+        """encode_inputs (opt_defense.py:300) in the layout the loop wants: the 3 planes, channels-last."""
+        return convonet.planes_to_channels_last(self.model.encode_inputs(sel))
+
     def sor_process(self, pc):
         """opt_defense.py:86-111: SOR in batches of 32 -> list of [K_i,3] float32 arrays."""
         sor = SORDefense(k=self.args.sor_k, alpha=self.args.sor_alpha)
@@ -145,7 +149,7 @@ class Defender:
             def stage(lo):
                 with torch.cuda.stream(side), torch.no_grad():
                     sel, pts = self.prepare_batch_device(pc[lo:lo + a.batch_size], rng, gen)
-                    planes = convonet.planes_to_channels_last(self.model.encode_inputs(sel))
+                    planes = self._encode(sel)
                     done = torch.cuda.Event()
                     done.record(side)
                 return pts, planes, done
@@ -190,11 +194,14 @@ class Defender:
                 src = torch.where(inside, idx - first, torch.zeros_like(idx)).to(sel.device)
                 c = self.model.encode_inputs(sel[src].contiguous())
                 pos = torch.nonzero(inside).flatten().to(sel.device)
+                if not isinstance(c, dict):                               # ONet: one latent code per cloud
+                    c = {"c": c}
                 if out is None:
                     out = {k: [] for k in c}
                 for k, v in c.items():
                     out[k].append(v[pos])
-        return {k: torch.cat(v) for k, v in out.items()}
+        out = {k: torch.cat(v) for k, v in out.items()}
+        return out["c"] if list(out) == ["c"] else out
 
     def restore_slice(self, pc, lo, hi, B_ref, seed):
         """Clouds lo..hi-1 of a reference batch of B_ref clouds, every random draw taken from a per-cloud stream
@@ -225,6 +232,25 @@ class Defender:
                                      rank=rank, world=world, device=self.device)
 
 
+class ONetDefender(Defender):
+    """ONet-Opt end to end (ONet/opt_defense.py, the twin of the ConvONet script: same functions and line numbers, 300 encoder
+    points, latent code c [B,512] instead of feature planes, DecoderCBatchNorm).  `model` is a models.OccupancyNetwork."""
+
+    def __init__(self, model, args=None, device="cuda"):
+        from . import onet
+        self.args = args or Args(input_npoint=300)
+        self.device = torch.device(device)
+        self.model = model.to(self.device).eval()
+        for p in self.model.parameters():
+            p.requires_grad = False
+        sd = {"decoder." + k: v for k, v in self.model.decoder.state_dict().items()}
+        self.decoder = onet.ONetDecoder(sd, device=self.device)
+        self.restorer = onet.ONetRestorer(self.decoder, threshold=self.args.threshold, lr=self.args.lr)
+
+    def _encode(self, sel):
+        return self.model.encode_inputs(sel)
+
+
 def get_save_name(path, tag="convonet_opt-", folder="ConvONet-Opt"):
     """opt_defense.py:242-252."""
     name = path.split('/')[-1]
@@ -239,7 +265,10 @@ def defend_npz_test_data(defender, path, **kw):
     npz = np.load(path)
     test_pc = npz['test_pc'][..., :3]
     out = defender.defend_point_cloud(test_pc, **kw)
-    save_path = get_save_name(path)
+    if isinstance(defender, ONetDefender):
+        save_path = get_save_name(path, tag="onet_opt-", folder="ONet-Opt")          # ONet/opt_defense.py:242-252
+    else:
+        save_path = get_save_name(path)
     fields = dict(test_pc=out.astype(np.float32), test_label=npz['test_label'].astype(np.uint8))
     if 'target_label' in npz.files:
         fields['target_label'] = npz['target_label'].astype(np.uint8)
