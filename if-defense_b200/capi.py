@@ -64,6 +64,7 @@ SIGNATURES = {
     "ifd_convonet_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                   ctypes.POINTER(OptParams), _vp, _vp, _c_sz, _vp]),
     "ifd_opt_tail_step": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, ctypes.POINTER(OptParams), _c_int, _vp, _vp, _vp]),
+    "ifd_convonet_opt_batches_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "ifd_convonet_opt_batches": (_c_int, [_c_int, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
                                           ctypes.POINTER(OptParams), _vp, _c_sz, _vp]),
     "ifd_convonet_opt_host": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
@@ -136,6 +137,19 @@ def require_gpu():
     if cc // 10 != 10:
         raise RuntimeError("ifdefense_b200 kernels are built for sm_100a only (device reports cc %d)" % cc)
     _cc_ok.add(dev)
+
+
+def use_device(device):
+    """One process per GPU (the reference's model: torch.distributed.launch --nproc_per_node): the C library launches on
+    the CURRENT CUDA device and its current stream.  Objects built with an explicit `device='cuda:N'` make N current
+    here, so that kernels, streams and cached buffers all live on the device that holds the tensors."""
+    import torch
+    device = torch.device(device)
+    if device.type == "cuda" and torch.cuda.is_available():
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx != torch.cuda.current_device():
+            torch.cuda.set_device(idx)
+    return device
 
 
 def ptr(t):

@@ -78,7 +78,7 @@ class ConvONetDecoder:
         self.padding = float(padding)
         blob = weights.pack_convonet_decoder(state_dict, prefix)
         self.blob_host = blob
-        self.device = torch.device(device)
+        self.device = capi.use_device(device)
         self.blob = torch.from_numpy(blob).to(self.device) if self.device.type == "cuda" else None
 
     def decode(self, p, c, **kwargs):
@@ -140,8 +140,7 @@ class Restorer:
         parts = 1 if printing else self._parts(B)
         if parts > 1:
             Bc = B // parts
-            one = (L.ifd_convonet_opt_workspace_bytes(Bc, K) + 255) // 256 * 256
-            ws = torch.empty(2 * one, dtype=torch.uint8, device=x.device)
+            ws = torch.empty(L.ifd_convonet_opt_batches_workspace_bytes(Bc, K), dtype=torch.uint8, device=x.device)
             pls = [planes[:, i * Bc:(i + 1) * Bc].contiguous() for i in range(parts)]
             pp = (ctypes.c_void_p * parts)(*[t.data_ptr() for t in pls])
             xp = (ctypes.c_void_p * parts)(*[x[i * Bc:(i + 1) * Bc].data_ptr() for i in range(parts)])

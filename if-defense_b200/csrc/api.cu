@@ -41,10 +41,26 @@ struct HostCache {
   float* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr;
+  int device = -1;          // the device `dev` and `stream` belong to
 };
 static thread_local HostCache g_cache;
 
+static int current_device(int* dev) {
+  IFD_CUDA_TRY(cudaGetDevice(dev));
+  return IFD_OK;
+}
+
 static int ensure_cache(size_t dev_bytes, size_t pinned_bytes) {
+  int dev = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (g_cache.device != dev && (g_cache.stream || g_cache.dev)) {   // the caller switched devices: start over on this one
+    if (g_cache.dev) cudaFree(g_cache.dev);
+    if (g_cache.stream) cudaStreamDestroy(g_cache.stream);
+    g_cache.dev = nullptr;
+    g_cache.bytes = 0;
+    g_cache.stream = nullptr;
+  }
+  g_cache.device = dev;
   if (!g_cache.stream) IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
   if (g_cache.bytes < dev_bytes) {
     if (g_cache.dev) cudaFree(g_cache.dev);
@@ -163,7 +179,13 @@ struct PipeCache {
   cudaEvent_t ready[3] = {nullptr, nullptr, nullptr}, done[3] = {nullptr, nullptr, nullptr}, freed[3] = {nullptr, nullptr, nullptr};
 };
 static thread_local PipeCache g_pipe;
+static thread_local int g_pipe_device = -1;
+void release_pipe();
 static int ensure_pipe(size_t dev_bytes) {
+  int dev = 0;
+  if (int rc = current_device(&dev)) return rc;
+  if (g_pipe_device != dev && (g_pipe.h2d || g_pipe.dev)) release_pipe();      // streams / buffers of another device
+  g_pipe_device = dev;
   if (!g_pipe.h2d) {
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.h2d, cudaStreamNonBlocking));
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[0], cudaStreamNonBlocking));

@@ -148,6 +148,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
     S.peer_loss = 0.0f;
   }
   __syncthreads();
+  // Distributed shared memory may only be touched once the peer CTA is known to be running AND has finished initialising
+  // the rows that are written remotely below (its warm-start copy of S.nbr, inbox_cnt, peer_loss): arrive here (release),
+  // wait just before the first remote store (acquire) -- the grid build and the kNN walk hide the barrier latency.
+  cluster.barrier_arrive();
   float4 me0 = make_float4(0.f, 0.f, 0.f, 0.f);        // point i (load order); re-assigned in cell order below
   if (live) {
     const float x = xs[3 * i + 0], y = xs[3 * i + 1], z = xs[3 * i + 2];
@@ -375,6 +379,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
         }
     }
   }
+  cluster.barrier_wait();                 // the peer has started and initialised its shared memory (see barrier_arrive above)
   if (live) {
     uint32_t w[4];
 #pragma unroll

@@ -295,66 +295,46 @@ __device__ __forceinline__ void tri_corner(const double* __restrict__ verts, lon
   p[2] = verts[v * 3 + 2];
 }
 
-// area = |cross(b - a, c - a)| / 2, chunk sums for the scan
-constexpr int kAreaBlock = 1024;
+// area = |cross(b - a, c - a)| / 2 per face
+constexpr int kAreaBlock = 256;
 __global__ void __launch_bounds__(kAreaBlock) face_area_kernel(const double* __restrict__ verts, const long long* __restrict__ faces,
-                                                               long long nf, double* __restrict__ area,
-                                                               double* __restrict__ block_sums) {
-  __shared__ double warp_sums[kAreaBlock / 32];
+                                                               long long nf, double* __restrict__ area) {
   const long long f = (long long)blockIdx.x * kAreaBlock + threadIdx.x;
-  double a = 0.0;
-  if (f < nf) {
-    double p0[3], p1[3], p2[3];
-    tri_corner(verts, faces[f * 3 + 0], p0);
-    tri_corner(verts, faces[f * 3 + 1], p1);
-    tri_corner(verts, faces[f * 3 + 2], p2);
-    const double ux = p1[0] - p0[0], uy = p1[1] - p0[1], uz = p1[2] - p0[2];
-    const double vx = p2[0] - p0[0], vy = p2[1] - p0[1], vz = p2[2] - p0[2];
-    const double cx = __dsub_rn(__dmul_rn(uy, vz), __dmul_rn(uz, vy));
-    const double cy = __dsub_rn(__dmul_rn(uz, vx), __dmul_rn(ux, vz));
-    const double cz = __dsub_rn(__dmul_rn(ux, vy), __dmul_rn(uy, vx));
-    a = __dmul_rn(sqrt(__dadd_rn(__dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy)), __dmul_rn(cz, cz))), 0.5);
-    area[f] = a;
-  }
-  // block-inclusive scan kept in `area`, block totals out
-  double inc = a;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double y = __shfl_up_sync(0xffffffffu, inc, o);
-    if ((threadIdx.x & 31) >= o) inc += y;
-  }
-  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = inc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double w = warp_sums[threadIdx.x];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double y = __shfl_up_sync(0xffffffffu, w, o);
-      if (threadIdx.x >= o) w += y;
-    }
-    warp_sums[threadIdx.x] = w;
-  }
-  __syncthreads();
-  inc += threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0.0;
-  if (f < nf) area[f] = inc;
-  if (threadIdx.x == kAreaBlock - 1) block_sums[blockIdx.x] = inc;
+  if (f >= nf) return;
+  double p0[3], p1[3], p2[3];
+  tri_corner(verts, faces[f * 3 + 0], p0);
+  tri_corner(verts, faces[f * 3 + 1], p1);
+  tri_corner(verts, faces[f * 3 + 2], p2);
+  const double ux = p1[0] - p0[0], uy = p1[1] - p0[1], uz = p1[2] - p0[2];
+  const double vx = p2[0] - p0[0], vy = p2[1] - p0[1], vz = p2[2] - p0[2];
+  const double cx = __dsub_rn(__dmul_rn(uy, vz), __dmul_rn(uz, vy));
+  const double cy = __dsub_rn(__dmul_rn(uz, vx), __dmul_rn(ux, vz));
+  const double cz = __dsub_rn(__dmul_rn(ux, vy), __dmul_rn(uy, vx));
+  area[f] = __dmul_rn(sqrt(__dadd_rn(__dadd_rn(__dmul_rn(cx, cx), __dmul_rn(cy, cy)), __dmul_rn(cz, cz))), 0.5);
 }
 
-// exclusive scan of the block totals in place by one thread per 32 ... the list is short (nf / 1024): sequential
-__global__ void area_scan_blocks_kernel(double* __restrict__ block_sums, int n, double* __restrict__ total) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// np.cumsum(area) in place, bit for bit: numpy's add.accumulate is ONE left-to-right chain of rounded fp64 additions, and
+// a prefix rounded where numpy rounds it cannot come out of a tree, so the chain is kept: one warp, coalesced 32-face
+// slabs (the next slab's load is in flight while the current one is consumed), every lane runs the same chain on values
+// broadcast by shuffle and keeps the prefix of its own face.  ~15 cycles per face: < 1 ms at 116 k faces.
+__global__ void __launch_bounds__(32) area_cumsum_serial_kernel(double* __restrict__ area, long long nf, double* __restrict__ total) {
+  const int lane = threadIdx.x;
   double run = 0.0;
-  for (int b = 0; b < n; ++b) {
-    const double x = block_sums[b];
-    block_sums[b] = run;
-    run += x;
+  double a = lane < nf ? area[lane] : 0.0;
+  for (long long base = 0; base < nf; base += 32) {
+    const long long fn = base + 32 + lane;
+    const double a_next = fn < nf ? area[fn] : 0.0;
+    double mine = 0.0;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const double x = __shfl_sync(0xffffffffu, a, l);
+      if (base + l < nf) run = __dadd_rn(run, x);
+      if (l == lane) mine = run;
+    }
+    if (base + lane < nf) area[base + lane] = mine;
+    a = a_next;
   }
-  *total = run;
-}
-
-__global__ void area_add_base_kernel(double* __restrict__ area_cum, long long nf, const double* __restrict__ block_sums) {
-  const long long f = (long long)blockIdx.x * kAreaBlock + threadIdx.x;
-  if (f < nf) area_cum[f] += block_sums[blockIdx.x];
+  if (lane == 0) *total = run;
 }
 
 // one sample per thread: face = searchsorted(cum, u0 * total) (left), point = origin + l0 * e0 + l1 * e1 with the pair
@@ -520,12 +500,10 @@ extern "C" int ifd_sample_surface(const double* verts, long long n_verts, const 
   double* bsum = reinterpret_cast<double*>(base + align256((size_t)n_faces * 8));
   double* total = reinterpret_cast<double*>(base + align256((size_t)n_faces * 8) + align256((size_t)nb * 8));
   cudaStream_t s = as_stream(stream);
-  face_area_kernel<<<nb, kAreaBlock, 0, s>>>(verts, faces, n_faces, cum, bsum);
+  face_area_kernel<<<nb, kAreaBlock, 0, s>>>(verts, faces, n_faces, cum);
   IFD_LAUNCH_CHECK("face_area_kernel");
-  area_scan_blocks_kernel<<<1, 32, 0, s>>>(bsum, nb, total);
-  IFD_LAUNCH_CHECK("area_scan_blocks_kernel");
-  area_add_base_kernel<<<nb, kAreaBlock, 0, s>>>(cum, n_faces, bsum);
-  IFD_LAUNCH_CHECK("area_add_base_kernel");
+  area_cumsum_serial_kernel<<<1, 32, 0, s>>>(cum, n_faces, total);
+  IFD_LAUNCH_CHECK("area_cumsum_serial_kernel");
   sample_surface_kernel<<<(count + 127) / 128, 128, 0, s>>>(verts, faces, n_faces, cum, total, uniforms, count, xyz_out, face_out);
   IFD_LAUNCH_CHECK("sample_surface_kernel");
   return IFD_OK;

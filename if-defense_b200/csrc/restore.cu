@@ -748,19 +748,36 @@ constexpr int kMaxLanes = 4;
 struct PairStreams {
   cudaStream_t s[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork = nullptr, join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  int device = -1;                  // the device the streams and events belong to
 };
 int g_lanes = 2;   // loops side by side; ifd_test_hook(2, n) (the workspace must then hold n parts)
 thread_local PairStreams g_pair;
 int ensure_pair() {
-  if (g_pair.fork) return IFD_OK;
+  int dev = 0;
+  IFD_CUDA_TRY(cudaGetDevice(&dev));
+  if (g_pair.fork && g_pair.device == dev) return IFD_OK;
+  if (g_pair.fork) {                // the caller switched devices: streams / events of the old one cannot be reused
+    for (int i = 0; i < kMaxLanes; ++i) {
+      if (g_pair.s[i]) cudaStreamDestroy(g_pair.s[i]);
+      if (g_pair.join[i]) cudaEventDestroy(g_pair.join[i]);
+    }
+    cudaEventDestroy(g_pair.fork);
+    g_pair = PairStreams();
+  }
   for (int i = 0; i < kMaxLanes; ++i) {
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pair.s[i], cudaStreamNonBlocking));
     IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pair.join[i], cudaEventDisableTiming));
   }
   IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pair.fork, cudaEventDisableTiming));
+  g_pair.device = dev;
   return IFD_OK;
 }
 }  // namespace
+
+extern "C" size_t ifd_convonet_opt_batches_workspace_bytes(int B, int K) {
+  if (B <= 0 || K <= 0) return 0;
+  return (size_t)g_lanes * align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
+}
 
 extern "C" int ifd_convonet_opt_batches(int n_batches, const float* const* planes_cl, const float* dec_weights, float* const* xyz,
                                         int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* P, void* workspace,
@@ -768,24 +785,31 @@ extern "C" int ifd_convonet_opt_batches(int n_batches, const float* const* plane
   IFD_REQUIRE(n_batches >= 0 && planes_cl && dec_weights && xyz && P && workspace && B > 0 && K > 0, "ifd_convonet_opt_batches: bad arguments");
   const size_t one = align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
   const int lanes = g_lanes;
-  if (workspace_bytes < (size_t)lanes * one) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_opt_batches: workspace must hold 2 x ifd_convonet_opt_workspace_bytes (256-byte aligned)");
+  if (workspace_bytes < (size_t)lanes * one) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "ifd_convonet_opt_batches: workspace must hold %d x ifd_convonet_opt_workspace_bytes (256-byte "
+             "aligned): ifd_convonet_opt_batches_workspace_bytes", lanes);
+    return fail(IFD_ERR_WORKSPACE, msg);
+  }
+  for (int j = 0; j < n_batches; ++j) IFD_REQUIRE(planes_cl[j] && xyz[j], "ifd_convonet_opt_batches: null batch pointer");
   int rc = ensure_pair();
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   IFD_CUDA_TRY(cudaEventRecord(g_pair.fork, st));
   for (int i = 0; i < lanes; ++i) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pair.s[i], g_pair.fork, 0));
-  for (int j = 0; j < n_batches; ++j) {
+  for (int j = 0; j < n_batches && rc == IFD_OK; ++j) {
     const int s = j % lanes;
-    IFD_REQUIRE(planes_cl[j] && xyz[j], "ifd_convonet_opt_batches: null batch pointer");
-    if ((rc = ifd_convonet_opt(planes_cl[j], dec_weights, xyz[j], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr,
-                               (char*)workspace + (size_t)s * one, one, g_pair.s[s])))
-      return rc;
+    rc = ifd_convonet_opt(planes_cl[j], dec_weights, xyz[j], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr,
+                          (char*)workspace + (size_t)s * one, one, g_pair.s[s]);
   }
+  // join on every exit path: whatever was enqueued on the lanes must be ordered before the caller's later work on `stream`
+  // (the caller may free or reuse the workspace right after an error)
   for (int i = 0; i < lanes; ++i) {
-    IFD_CUDA_TRY(cudaEventRecord(g_pair.join[i], g_pair.s[i]));
-    IFD_CUDA_TRY(cudaStreamWaitEvent(st, g_pair.join[i], 0));
+    const cudaError_t e1 = cudaEventRecord(g_pair.join[i], g_pair.s[i]);
+    const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(st, g_pair.join[i], 0) : e1;
+    if (e2 != cudaSuccess && rc == IFD_OK) rc = fail(IFD_ERR_CUDA, cudaGetErrorString(e2));
   }
-  return IFD_OK;
+  return rc;
 }
 
 extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,

@@ -75,7 +75,8 @@ class Defender:
 
     def __init__(self, model, args=None, device="cuda"):
         self.args = args or Args()
-        self.device = torch.device(device)
+        from . import capi
+        self.device = capi.use_device(device)
         self.model = model.to(self.device).eval()
         for p in self.model.parameters():
             p.requires_grad = False
@@ -117,18 +118,28 @@ class Defender:
                                        capi.stream()), "ifd_preprocess_pc")
         n = counts.cpu().numpy()
         T = a.input_npoint
-        if T is None or (n <= T).any():
-            raise RuntimeError("device preprocess needs more than input_npoint points per cloud after SOR")
-        if isinstance(rng, (list, tuple)):                                                     # one stream per cloud
+        # preprocess_pc :134-141: a cloud with more than input_npoint points is subsampled, otherwise ALL its points are the
+        # encoder input and no random number is drawn.  The reference then np.stack()s the batch, so the no-subsample case
+        # only exists when every cloud of the batch kept the same number of points (e.g. --sor=False and K <= input_npoint).
+        small = T is None or bool((n <= T).all())
+        if small and len(set(int(k) for k in n)) != 1:
+            raise RuntimeError("clouds of one batch keep different numbers of points (<= input_npoint) after SOR: the "
+                               "reference cannot stack them either (opt_defense.py:296)")
+        if not small and (n <= T).any():
+            raise RuntimeError("some clouds of the batch have <= input_npoint points after SOR and some more: the reference "
+                               "cannot stack them either (opt_defense.py:296)")
+        per_cloud = isinstance(rng, (list, tuple))                                             # one RNG stream per cloud
+        if small:
+            sel_idx = np.tile(np.arange(int(n[0])), (B, 1))
+        elif per_cloud:
             sel_idx = np.stack([r.choice(int(k), T, replace=False) for r, k in zip(rng, n)])
-            ini_idx, noise = [], []
-            for g, k in zip(gen, n):                                                           # init_points per cloud
-                ini_idx.append(torch.randint(0, int(k), (a.sample_npoint,), generator=g))
-                noise.append(torch.randn((a.sample_npoint, 3), generator=g) * a.init_sigma)
-            ini_idx, noise = torch.stack(ini_idx), torch.stack(noise)
         else:
             draw = rng if rng is not None else np.random
             sel_idx = np.stack([draw.choice(int(k), T, replace=False) for k in n])             # preprocess_pc :134-141
+        if isinstance(gen, (list, tuple)):                                                     # init_points per cloud
+            ini_idx = torch.stack([torch.randint(0, int(k), (a.sample_npoint,), generator=g) for g, k in zip(gen, n)])
+            noise = torch.stack([torch.randn((a.sample_npoint, 3), generator=g) * a.init_sigma for g in gen])
+        else:
             ini_idx = torch.stack([torch.randint(0, int(k), (a.sample_npoint,), generator=gen) for k in n])   # init_points :163-167
             noise = torch.randn((B, a.sample_npoint, 3), generator=gen) * a.init_sigma
         rows = torch.arange(B, device=self.device).view(B, 1)
@@ -239,7 +250,8 @@ class ONetDefender(Defender):
     def __init__(self, model, args=None, device="cuda"):
         from . import onet
         self.args = args or Args(input_npoint=300)
-        self.device = torch.device(device)
+        from . import capi
+        self.device = capi.use_device(device)
         self.model = model.to(self.device).eval()
         for p in self.model.parameters():
             p.requires_grad = False

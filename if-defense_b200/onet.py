@@ -67,7 +67,7 @@ class ONetDecoder:
 
     def __init__(self, state_dict, device="cuda", prefix="decoder."):
         self.blob_host = weights.pack_onet_decoder(state_dict, prefix)
-        self.device = torch.device(device)
+        self.device = capi.use_device(device)
         self.blob = torch.from_numpy(self.blob_host).to(self.device) if self.device.type == "cuda" else None
         self.ws = _Workspace()
 

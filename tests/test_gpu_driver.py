@@ -102,3 +102,17 @@ def test_sharded_slices_device_path_and_encoder_chunks():
     for lo in (1, 3, 4, 6):
         part = dev_d.encode_chunked(sel[lo:], lo)
         assert all(torch.equal(whole[k][lo:], part[k]) for k in whole), lo
+
+
+def test_small_clouds_use_all_points_like_the_reference():
+    """K <= input_npoint with --sor=False: preprocess_pc (opt_defense.py:134-141) hands ALL points to the encoder and draws
+    nothing; the device path does the same (it used to raise) and equals the per-cloud numpy path bit for bit."""
+    import torch
+    model = models.build_convonet()
+    model.load_state_dict(models.synthetic_state_dict("convonet", 0))
+    pc = synth.clouds(3)[:, :500]
+    outs = []
+    for dev_path in (True, False):
+        d = driver.Defender(model, driver.Args(batch_size=3, iterations=4, sor=False, device_preprocess=dev_path))
+        outs.append(d.defend_point_cloud(pc, rng=np.random.default_rng(2), gen=torch.Generator().manual_seed(2)))
+    assert outs[0].shape == (3, 1024, 3) and np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1])
