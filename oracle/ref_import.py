@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY (container-side): import the *unmodified* reference classes from
 /root/reference on CPU so that golden vectors can be generated from the reference itself.
 
-/root/reference does not exist on the GPU box; nothing that runs there may import this module.
-It is used only by tests/golden/make_golden.py and by the (skipped-when-absent) tests that pin
+/root/reference does not exist on the GPU box.  There, the only user is bench.py's reference arm
+(`--impl reference`), which drives the unmodified copy vendored into oracle/_ref/pyref by `make -C oracle pyref`.
+Otherwise it is used by tests/golden/make_golden.py and by the (skipped-when-absent) tests that pin
 oracle/torch_port.py bit-for-bit against the real reference.
 
 Shim recipe:
@@ -18,7 +19,18 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("IFD_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyref")
+
+
+def _default_root():
+    """/root/reference in the build container; on the GPU box the UNMODIFIED copy of the hot path's Python files that
+    `make -C oracle pyref` placed in the git-ignored oracle/_ref/pyref (it travels with the snapshot)."""
+    if os.path.isdir("/root/reference/ConvONet/src"):
+        return "/root/reference"
+    return _VENDORED
+
+
+REF_ROOT = os.environ.get("IFD_REFERENCE_ROOT") or _default_root()
 
 
 def available() -> bool:
