@@ -595,26 +595,28 @@ def main():
                              "query through a per-step uniform grid, so it is bound by barriers and divergence, not by the FMA pipe"}
         roofs = [roof, roof_tail]
 
-        if not args.no_cpu_baseline:
-            import torch as _t
-            cores = os.cpu_count() or 1
-            _t.set_num_threads(cores)
-            case0 = batches[0][0]
-            case0.c = {k: v.cpu() for k, v in case0.c.items()}
-            decode_fn, rep_fn, kind, what = _reference_fns(case0)
-            loop = _RefLoop(decode_fn, rep_fn, case0.p0.cpu())
-            loop.run(2)                                                 # warm-up
-            n_it = 50                                                   # >= 50 consecutive Adam steps (about 15 s on 16 cores)
-            t0 = time.perf_counter()
-            loop.run(n_it)
-            t = time.perf_counter() - t0
-            cpu = {"value": B / (t / n_it * (ITERS + 1)), "unit": "clouds/s", "cores": cores, "kind": kind,
-                   "sample": "B=%d x %d pts, Adam steps 3..%d of one restoration in %.1f s, scaled to 201; %s" % (B, K, n_it + 2, t, what)}
-
     if rank == 0 and not args.no_onet:
         onet = onet_leg(L)
         if roofs is not None:
             roofs.append(dict(onet["decoder_gemm"], kernel="onet_gemm_kernel x 20 per Adam step (ONet-Opt leg)"))
+    if rank == 0 and not args.no_cpu_baseline:
+        import torch as _t
+        cores = os.cpu_count() or 1
+        _t.set_num_threads(cores)
+        case0 = batches[0][0]
+        case0.c = {k: v.cpu() for k, v in case0.c.items()}
+        decode_fn, rep_fn, kind, what = _reference_fns(case0)
+        loop = _RefLoop(decode_fn, rep_fn, case0.p0.cpu())
+        loop.run(2)                                                 # warm-up
+        n_it = 50                                                   # >= 50 consecutive Adam steps (about 15 s on 16 cores)
+        t0 = time.perf_counter()
+        loop.run(n_it)
+        t = time.perf_counter() - t0
+        from oracle import ref_import
+        ref_import.restore_cuda()                                   # the reference's CPU shim turns Tensor.cuda into the identity
+        cpu = {"value": B / (t / n_it * (ITERS + 1)), "unit": "clouds/s", "cores": cores, "kind": kind,
+               "sample": "B=%d x %d pts, Adam steps 3..%d of one restoration in %.1f s, scaled to 201; %s" % (B, K, n_it + 2, t, what)}
+
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

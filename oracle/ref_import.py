@@ -67,11 +67,23 @@ def _common_shims():
         _load._ifd_patched = True
         yaml.load = _load
     if not getattr(torch.Tensor.cuda, "_ifd_patched", False):
+        _orig_cuda = torch.Tensor.cuda
+
         def _cuda(self, *a, **k):
             return self
 
         _cuda._ifd_patched = True
+        _cuda._ifd_orig = _orig_cuda
         torch.Tensor.cuda = _cuda
+
+
+def restore_cuda():
+    """Undo the Tensor.cuda identity patch (a process that also drives the GPU calls this when it is done with the
+    reference classes: RepulsionLoss needs the patch at every forward, defense/repulsion_loss.py:47)."""
+    import torch
+    orig = getattr(torch.Tensor.cuda, "_ifd_orig", None)
+    if orig is not None:
+        torch.Tensor.cuda = orig
 
 
 def load(which: str):

@@ -52,8 +52,10 @@ def test_loop_short_horizon_vs_reference(conv, dec, planes):
     x, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1, decode_kernel=2)
     assert np.abs(x - conv["final_20_normalized"]).max() < 1e-4
     x, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1)                          # production default (tensor cores)
-    d = np.abs(x - conv["final_20_normalized"])
-    assert (d < 1e-4).mean() > 0.97 and np.median(d) < 1e-6
+    assert np.abs(x - conv["final_20_normalized"]).max() < 1e-4                       # north_star's tolerance, max-abs
+    for n_steps, tol in ((1, 1e-6), (2, 1e-6), (10, 5e-6), (20, 2e-5)):               # and the fp32 kernels' own bounds
+        x, _ = run_opt(dec, planes, conv["p0"], n_steps)                              # (measured: 5e-10 / 3e-8 / 6e-8 / 2.9e-7)
+        assert np.abs(x - conv["trace/xyz_%d" % (n_steps - 1)]).max() < tol, n_steps
 
 
 def test_late_state_single_step(conv, dec, planes):
@@ -176,7 +178,9 @@ def test_tensor_core_201_steps_statistical(conv, dec, planes):
     x, st = run_opt(dec, planes, conv["p0"], 201, stats=True, decode_kernel=3)
     ref = conv["final_201_raw"]
     d = np.abs(x - ref)
-    assert np.isfinite(x).all() and np.median(d) < 1e-3 and d.max() < 0.1
+    # measured on a B200 (profiles/r02_parity_record.json, fixture 2 x 256): median 5.5e-5, p99 1.6e-3, max 1.9e-2, 62.5 % within
+    # 1e-4 -- the same as the fp32 kernels (4.5e-5 / 1.2e-3 / 5.5e-3 / 63 %): the 201-step trajectory amplifies ANY rounding difference
+    assert np.isfinite(x).all() and np.median(d) < 1.5e-4 and np.quantile(d, 0.99) < 5e-3 and d.max() < 0.06 and (d <= 1e-4).mean() > 0.5
     np.testing.assert_allclose(st[0], conv["stats_201"][0], rtol=2e-5)
     np.testing.assert_allclose(st[1:], conv["stats_201"][1:], rtol=0.05)
 
@@ -188,7 +192,8 @@ def test_201_steps_statistical_parity(conv, dec, planes):
     ref = conv["final_201_raw"]
     d = np.abs(x - ref)
     assert np.isfinite(x).all()
-    assert np.median(d) < 1e-3 and d.max() < 0.1
+    # thresholds = the recorded distribution (profiles/r02_parity_record.json: median 5.5e-5, p99 1.6e-3, max 1.9e-2) + margin
+    assert np.median(d) < 1.5e-4 and np.quantile(d, 0.99) < 5e-3 and d.max() < 0.06 and (d <= 1e-4).mean() > 0.5
     # the printed diagnostics: exact at iteration 0, statistically equal later
     np.testing.assert_allclose(st[0], conv["stats_201"][0], rtol=2e-5)
     np.testing.assert_allclose(st[1:], conv["stats_201"][1:], rtol=0.05)

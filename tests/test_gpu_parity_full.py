@@ -13,8 +13,12 @@ from tests.gpu_util import run_opt
 
 pytestmark = pytest.mark.gpu
 
-# (steps, max |d| fp32 kernels, fraction of coordinates within 1e-4 for the 3xTF32 default, median bound for both)
-CONV_ROWS = ((1, 2e-6, 1.0, 2e-8), (2, 4e-6, 0.9999, 5e-8), (10, 5e-5, 0.9995, 3e-7), (20, 5e-4, 0.999, 6e-7))
+# (steps, max |d|, fraction of coordinates within 1e-4, p99 |d|) -- the same bounds for the fp32 kernels (decode_kernel = 2)
+# and the production default (tcgen05, 3xTF32): at this size both sit at the same distance from the oracle.  Measured on a
+# B200 (profiles/r02_parity_record.json): max 1.3e-5 / 4.2e-5 at 1 step, 1.25e-4 at 10, 3.9e-4 at 20 (both kernels, the same
+# few coordinates: |gradient| ~ Adam's eps, where step 1 is lr * g / (|g| + 1e-8) instead of lr * sign(g)); within 1e-4:
+# 1.0 / 1.0 / 0.99999 / 0.99992; p99 0 / 6.5e-9 / 3.0e-8 / 6.0e-8; median 0 throughout.
+CONV_ROWS = ((1, 1e-4, 1.0, 1e-8), (2, 1.5e-4, 1.0, 5e-8), (10, 5e-4, 0.9999, 3e-7), (20, 1.5e-3, 0.9997, 6e-7))
 
 
 @pytest.fixture(scope="module")
@@ -34,15 +38,15 @@ def cfg2():
 def test_convonet_config2_vs_oracle(cfg2, kernel):
     """ConvONet-Opt, 64 x 1024 points, 1 / 2 / 10 / 20 Adam steps: fp32 kernels and the production default."""
     case, dec, planes, ref = cfg2
-    for steps, max_fp32, frac_tc, med in CONV_ROWS:
+    for steps, dmax, frac, p99 in CONV_ROWS:
         x, _ = run_opt(dec, planes, case.p0, steps, decode_kernel=kernel)
         d = np.abs(x - ref[steps - 1])
-        print("kernel %d steps %2d: median %.2e p99.9 %.2e max %.2e within 1e-4: %.6f" %
-              (kernel, steps, np.median(d), np.quantile(d, 0.999), d.max(), (d <= 1e-4).mean()))
-        assert np.median(d) < med, (kernel, steps, np.median(d))
-        assert (d <= 1e-4).mean() >= frac_tc, (kernel, steps, (d <= 1e-4).mean())
-        if kernel == 2:
-            assert d.max() < max_fp32, (steps, d.max())
+        print("kernel %d steps %2d: median %.2e p99 %.2e max %.2e within 1e-4: %.6f" %
+              (kernel, steps, np.median(d), np.quantile(d, 0.99), d.max(), (d <= 1e-4).mean()))
+        assert np.median(d) == 0.0, (kernel, steps, np.median(d))
+        assert np.quantile(d, 0.99) <= p99, (kernel, steps, np.quantile(d, 0.99))
+        assert (d <= 1e-4).mean() >= frac, (kernel, steps, (d <= 1e-4).mean())
+        assert d.max() < dmax, (kernel, steps, d.max())
 
 
 def test_onet_config_b64_vs_oracle():
@@ -53,9 +57,11 @@ def test_onet_config_b64_vs_oracle():
     tp.optimize_points(lambda p: tp.onet_decode(case.sd, p, case.c), case.p0, rep_weight=500., iterations=4, normalize=False,
                        trace=tr, trace_steps=[0, 1, 4])
     rest = onet_mod.ONetRestorer(onet_mod.ONetDecoder(case.sd), threshold=0.2, lr=1e-3)
-    for steps, frac, med in ((1, 0.9999, 2e-8), (2, 0.9995, 5e-8), (5, 0.999, 2e-7)):
+    # measured (profiles/r02_parity_record.json, 64 x 1024): max 3.1e-5 / 4.8e-5 at 1 / 2 steps, within 1e-4: 1.0 / 1.0 / 0.9999 (10 steps)
+    for steps, frac, p99, dmax in ((1, 1.0, 1e-8, 1e-4), (2, 1.0, 5e-8, 2e-4), (5, 0.9999, 2e-7, 1e-3)):
         x = rest.optimize_points(case.p0.cuda(), None, case.c.cuda(), rep_weight=500., iterations=steps - 1, normalize=False)
         d = np.abs(x - tr["xyz"][steps - 1])
-        print("onet steps %d: median %.2e p99.9 %.2e max %.2e within 1e-4: %.6f" %
-              (steps, np.median(d), np.quantile(d, 0.999), d.max(), (d <= 1e-4).mean()))
-        assert np.median(d) < med and (d <= 1e-4).mean() >= frac, (steps, np.median(d), (d <= 1e-4).mean())
+        print("onet steps %d: median %.2e p99 %.2e max %.2e within 1e-4: %.6f" %
+              (steps, np.median(d), np.quantile(d, 0.99), d.max(), (d <= 1e-4).mean()))
+        assert np.median(d) == 0.0 and np.quantile(d, 0.99) <= p99, (steps, np.quantile(d, 0.99))
+        assert (d <= 1e-4).mean() >= frac and d.max() < dmax, (steps, (d <= 1e-4).mean(), d.max())

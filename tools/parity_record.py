@@ -7,7 +7,9 @@ For ConvONet-Opt at BASELINE.json configs[1] (B = 64 x 1024 points) and on the K
 (B = 64 at 20 steps, B = 8 at 201 steps), the |d xyz| distribution (median, p99, p99.9, max, fraction <= 1e-4 / 1e-5) after
 1, 2, 10, 20, 100 and 201 Adam steps (raw coordinates, before normalize_batch_pc) for
 
-  * oracle with all host threads  vs  oracle with half of them   -- the reference's own reproducibility,
+  * oracle with all host threads  vs  oracle with half of them   -- the reference's run-to-run reproducibility,
+  * oracle  vs  oracle started one ulp away (1 % of the input coordinates moved to the next float)  -- the sensitivity of
+    the 201-step trajectory itself: what ANY implementation that is not bit-identical to stock PyTorch CPU must expect,
   * GPU fp32 kernels (decode_kernel = 2)  vs  oracle,
   * GPU production default (tcgen05, 3xTF32)  vs  oracle,
   * GPU default vs GPU fp32.
@@ -57,11 +59,16 @@ def convonet_block(B, K, seed, n_steps, cores, noise_floor=True):
     fn = lambda p: tp.convonet_decode(case.sd, p, case.c)
     ref, t_ref = oracle_trace(fn, case.p0, n_steps, cores)
     out = {"B": B, "K": K, "oracle_threads": cores, "oracle_seconds": t_ref, "rows": {}}
-    alt = None
+    alt = ulp = None
     if noise_floor:
         alt, t_alt = oracle_trace(fn, case.p0, n_steps, max(1, cores // 2))
         out["oracle_alt_threads"] = max(1, cores // 2)
         out["oracle_alt_seconds"] = t_alt
+        g = torch.Generator().manual_seed(11)
+        sel = torch.rand(case.p0.shape, generator=g) < 0.01
+        p1 = torch.where(sel, torch.nextafter(case.p0, torch.full_like(case.p0, 10.0)), case.p0)
+        ulp, _ = oracle_trace(fn, p1, n_steps, cores)
+        out["one_ulp_perturbed_fraction"] = float(sel.float().mean())
     for s in STEPS:
         if s > n_steps:
             continue
@@ -71,6 +78,7 @@ def convonet_block(B, K, seed, n_steps, cores, noise_floor=True):
                "gpu_default_vs_gpu_fp32": dist_row(g0, g2)}
         if alt is not None:
             row["oracle_vs_oracle_half_threads"] = dist_row(alt[s], ref[s])
+            row["oracle_vs_oracle_1ulp_start"] = dist_row(ulp[s], ref[s])
         out["rows"][str(s)] = row
     return out
 
