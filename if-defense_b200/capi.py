@@ -27,6 +27,18 @@ class OptParams(ctypes.Structure):
     ]
 
 
+class TcLinearArgs(ctypes.Structure):
+    """struct ifd_tc_linear_args (include/ifd_b200.h)."""
+    _fields_ = [
+        ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("n_seg", ctypes.c_int32),
+        ("a_ptr", ctypes.c_void_p * 3), ("a_ld", ctypes.c_int32 * 3), ("a_width", ctypes.c_int32 * 3), ("a_relu", ctypes.c_int32 * 3),
+        ("a_group", ctypes.c_int32 * 3),
+        ("wimg", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("resid", ctypes.c_void_p), ("ld_resid", ctypes.c_int32),
+        ("relu_out", ctypes.c_int32), ("out", ctypes.c_void_p), ("ld_out", ctypes.c_int32),
+        ("shuffle_cout", ctypes.c_int32), ("shuffle_H", ctypes.c_int32), ("shuffle_W", ctypes.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/ifd_b200.h declares
 SIGNATURES = {
     "ifd_last_error": (ctypes.c_char_p, []),
@@ -47,6 +59,11 @@ SIGNATURES = {
     "ifd_plane_bins": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
     "ifd_scatter_max_gather": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "ifd_scatter_mean_cl": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "ifd_tc_packed_floats": (_c_sz, [_c_int, ctypes.POINTER(ctypes.c_int), _c_int]),
+    "ifd_tc_pack": (_c_int, [_vp, _c_int, ctypes.POINTER(ctypes.c_int), _c_int, _c_int, _vp, _vp]),
+    "ifd_tc_linear": (_c_int, [ctypes.POINTER(TcLinearArgs), _vp]),
+    "ifd_group_max": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "ifd_tc_conv3x3": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _c_int, _vp, _vp]),
     "ifd_mc_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
     "ifd_mc_count": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _c_d, _vp, _c_sz,
                               ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), _vp]),

@@ -23,6 +23,9 @@ def planes_to_channels_last(c):
     """dict of [B,C,R,R] (encoder output) -> one device tensor [3,B,R,R,C] in kernel layout."""
     if isinstance(c, torch.Tensor):          # already converted
         return c
+    cl = getattr(c, "channels_last", None)
+    if cl is not None:                       # models.LocalPoolPointnet on CUDA: the planes are born in the kernel layout
+        return cl
     capi.require_gpu()
     if all(c[k].dim() == 4 and c[k].dtype == torch.float32 and c[k].is_contiguous(memory_format=torch.channels_last)
            and not c[k].is_contiguous() for k in PLANES):

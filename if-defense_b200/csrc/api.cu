@@ -21,6 +21,8 @@ struct ProfRec { int kind; cudaEvent_t e0, e1; };
 static thread_local bool g_prof_on = false;
 static thread_local std::vector<ProfRec>* g_prof = nullptr;
 
+bool profile_on() { return g_prof_on; }
+
 ProfileScope::ProfileScope(int kind, cudaStream_t st) : kind_(kind), st_(st) {
   if (!g_prof_on) return;
   if (cudaEventCreate(&e0_) != cudaSuccess) { e0_ = nullptr; return; }
@@ -120,9 +122,10 @@ extern "C" int ifd_profile_read(double* ms_out, long long* launches_out) {
   return IFD_PROFILE_KINDS;
 }
 
-namespace ifd { void release_pipe(); }
+namespace ifd { void release_pipe(); void release_graphs(); }
 extern "C" void ifd_release_cache(void) {
   release_pipe();
+  release_graphs();
   if (g_cache.dev) cudaFree(g_cache.dev);
   if (g_cache.pinned) cudaFreeHost(g_cache.pinned);
   if (g_cache.stream) cudaStreamDestroy(g_cache.stream);

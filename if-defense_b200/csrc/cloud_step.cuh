@@ -52,12 +52,19 @@ struct CloudStepArgs {
   float radius, h, eps, rep_coef;
   float omb1, b2, omb2, adam_eps;
   AdamStepConst sc;
+  int bar_mode;          // cluster barrier before the first remote store -- 0: none, 1: arrive.release / wait.acquire,
+                         // 2: arrive.relaxed / wait (execution barrier only; the default)
+  const LoopJob* job;    // non-null: xyz / m / v / g_occ / nbr come from this record (graph replay)
+  int zero_mv;           // first step of a fresh run: Adam state is zero, m and v are not read
 };
 
 struct CloudStepSmem {
   float4 pos[kCsMaxK];                       // x y z |x|^2
   uint32_t cell[kCsCells + 4];               // counting sort: cell[c] = first slot of cell c, cell[c + 1] = end
-  uint16_t nbr[kCsMaxK][kCsKK];              // this step's lists (column 0 = the dropped "self" column)
+  uint16_t nbr[kCsMaxK][kCsKK];              // last step's lists (warm start), filled locally from global memory
+  uint16_t nbrn[kCsMaxK][kCsKK];             // this step's lists (column 0 = the dropped "self" column): own rows written here
+                                             // and into the peer CTA's copy -- a separate array, so the peer's warm-start
+                                             // initialisation of `nbr` can never overwrite a list that arrived early
   uint16_t inbox[kCsMaxK][kCsInbox];         // sources of non-mutual in-edges
   uint32_t inbox_cnt[kCsMaxK];
   uint16_t sorted[kCsMaxK];                  // point indices in cell order
@@ -109,6 +116,14 @@ __device__ __forceinline__ bool cs_row_has(const uint16_t* row, int k, int who) 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudStepArgs a) {
   extern __shared__ __align__(16) unsigned char cs_raw[];
+  // graph replay: the buffers of THIS launch are in the job record.  (Plain locals on purpose: copying the argument struct
+  // and overwriting its pointer members made nvcc 12.9 drop the assignment of `xyz` -- the kernel then kept using the
+  // capture-time pointer, which only shows when a replay runs on other buffers than the capture did.)
+  float* const g_xyz = a.job ? a.job->xyz : a.xyz;
+  float* const g_m = a.job ? a.job->m : a.m;
+  float* const g_v = a.job ? a.job->v : a.v;
+  const float* const g_gocc = a.job ? a.job->g_occ : a.g_occ;
+  int32_t* const g_nbr = a.job ? a.job->nbr : a.nbr;
   CloudStepSmem& S = *reinterpret_cast<CloudStepSmem*>(cs_raw);
   cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
   const int half = (int)cluster.block_rank();                  // which side of the split this CTA owns
@@ -121,13 +136,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
   const size_t cloud3 = (size_t)b * K * 3;
   float* xs = reinterpret_cast<float*>(&S.inbox[0][0]);        // xyz staging (the inbox is not in use yet)
   for (int e = i; e < 3 * K; e += kCsThreads) {
-    xs[e] = a.xyz[cloud3 + e];
-    S.gmv[0][e] = a.g_occ[cloud3 + e];
-    S.gmv[1][e] = a.m[cloud3 + e];
-    S.gmv[2][e] = a.v[cloud3 + e];
+    xs[e] = g_xyz[cloud3 + e];
+    S.gmv[0][e] = g_gocc[cloud3 + e];
+    S.gmv[1][e] = a.zero_mv ? 0.0f : g_m[cloud3 + e];
+    S.gmv[2][e] = a.zero_mv ? 0.0f : g_v[cloud3 + e];
   }
   if (live && a.warm) {                                        // previous lists -> 16-bit rows
-    const int4* pv = reinterpret_cast<const int4*>(a.nbr + ((size_t)b * K + i) * kCsKK);
+    const int4* pv = reinterpret_cast<const int4*>(g_nbr + ((size_t)b * K + i) * kCsKK);
     const int4 p0 = pv[0], p1 = pv[1];
     const int prev[kCsKK] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
     uint32_t w[4];
@@ -148,10 +163,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
     S.peer_loss = 0.0f;
   }
   __syncthreads();
-  // Distributed shared memory may only be touched once the peer CTA is known to be running AND has finished initialising
-  // the rows that are written remotely below (its warm-start copy of S.nbr, inbox_cnt, peer_loss): arrive here (release),
-  // wait just before the first remote store (acquire) -- the grid build and the kNN walk hide the barrier latency.
-  cluster.barrier_arrive();
+  // Distributed shared memory may only be touched once the peer CTA is known to be running: arrive here, wait just before
+  // the first remote store -- the grid build and the kNN walk hide the barrier latency.  No memory ordering is needed from
+  // this pair (the rows written remotely, `nbrn`, are not initialised by their owner; the inbox counters are only pushed
+  // to after the full cluster.sync below), so the arrive is relaxed.
+  if (a.bar_mode == 1) cluster.barrier_arrive();
+  else if (a.bar_mode == 2) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   float4 me0 = make_float4(0.f, 0.f, 0.f, 0.f);        // point i (load order); re-assigned in cell order below
   if (live) {
     const float x = xs[3 * i + 0], y = xs[3 * i + 1], z = xs[3 * i + 2];
@@ -379,7 +396,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
         }
     }
   }
-  cluster.barrier_wait();                 // the peer has started and initialised its shared memory (see barrier_arrive above)
+  if (a.bar_mode == 1) cluster.barrier_wait();          // the peer has started (see the arrive above)
+  else if (a.bar_mode == 2) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
   if (live) {
     uint32_t w[4];
 #pragma unroll
@@ -389,9 +407,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
       w[s] = (uint32_t)e0 | ((uint32_t)e1 << 16);
     }
     const uint4 row16 = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(&S.nbr[p][0]) = row16;            // this CTA's copy
-    *reinterpret_cast<uint4*>(&P.nbr[p][0]) = row16;            // the peer's copy (distributed shared memory)
-    int4* pv = reinterpret_cast<int4*>(a.nbr + ((size_t)b * K + p) * kCsKK);   // warm start of the next step
+    *reinterpret_cast<uint4*>(&S.nbrn[p][0]) = row16;           // this CTA's copy
+    *reinterpret_cast<uint4*>(&P.nbrn[p][0]) = row16;           // the peer's copy (distributed shared memory)
+    int4* pv = reinterpret_cast<int4*>(g_nbr + ((size_t)b * K + p) * kCsKK);   // warm start of the next step
     pv[0] = make_int4(top.id[0], top.id[1], top.id[2], top.id[3]);
     pv[1] = make_int4(top.id[4], top.id[5], top.id[6], top.id[7]);
   }
@@ -412,7 +430,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
         sx -= gx;
         sy -= gy;
         sz -= gz;
-        if (cs_row_has(S.nbr[j], k, p)) {      // j -> p exists too: its gradient on p is bitwise -g
+        if (cs_row_has(S.nbrn[j], k, p)) {     // j -> p exists too: its gradient on p is bitwise -g
           ax += (double)(-gx);
           ay += (double)(-gy);
           az += (double)(-gz);
@@ -447,7 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
       const float4 tj = S.pos[j];
       double hx = 0.0, hy = 0.0, hz = 0.0;
       for (int q = lane; q < K; q += 32) {
-        if (!cs_row_has(S.nbr[q], k, j) || cs_row_has(S.nbr[j], k, q)) continue;
+        if (!cs_row_has(S.nbrn[q], k, j) || cs_row_has(S.nbrn[j], k, q)) continue;
         float gx, gy, gz, l;
         cs_pair(S.pos[q], tj, a.radius, a.h, a.eps, gx, gy, gz, l);
         hx += (double)gx;
@@ -493,7 +511,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
       az += S.hubsum[h][2];
     } else {                                   // more than kCsMaxHub hubs: ordered scan of every list
       for (int q = 0; q < K; ++q) {
-        if (!cs_row_has(S.nbr[q], k, p)) continue;
+        if (!cs_row_has(S.nbrn[q], k, p)) continue;
         bool mutual = false;
 #pragma unroll
         for (int s = 1; s < kCsKK; ++s) mutual |= (s <= k) && (top.id[s] == q);
@@ -514,9 +532,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
       const float g = S.gmv[0][3 * p + c] + r3[c] * a.rep_coef;
       float mm = S.gmv[1][3 * p + c], vv = S.gmv[2][3 * p + c];
       adam_update(p3[c], mm, vv, g, a.omb1, a.b2, a.omb2, a.adam_eps, a.sc);
-      a.xyz[o3 + c] = p3[c];
-      a.m[o3 + c] = mm;
-      a.v[o3 + c] = vv;
+      g_xyz[o3 + c] = p3[c];
+      g_m[o3 + c] = mm;
+      g_v[o3 + c] = vv;
       if (a.rep_grad_out) a.rep_grad_out[o3 + c] = r3[c];
     }
     ls[p] = lsum;                                               // pair-loss sum of point p

@@ -71,6 +71,21 @@ inline cudaError_t set_max_dyn_smem(const void* kernel, size_t bytes) {
   return e;
 }
 
+// Every device pointer of one restoration loop.  The loop's kernels can take their pointers from such a record in device
+// memory instead of from their launch arguments, so that ONE instantiated CUDA graph of the ~400 launches serves any set of
+// buffers: a launch of the loop is then "write the record, launch the graph" (restore.cu).
+struct LoopJob {
+  const float* planes;   // [3][B][R][R][C] channels-last
+  const float* W;        // packed decoder blob
+  const float* Wimg;     // UMMA weight images (workspace)
+  float* xyz;            // [B][K][3] in / out
+  float* g_occ;          // [B][K][3] (workspace)
+  float* m;              // Adam state (workspace)
+  float* v;
+  int32_t* nbr;          // [B][K][8] warm-start neighbour lists (workspace)
+};
+bool profile_on();       // api.cu: per-kernel event timing is enabled on this thread
+
 inline cudaStream_t as_stream(ifd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -31,8 +31,11 @@ constexpr int kV3TileCols = 96;                    // D | A_hi | A_lo
 constexpr uint32_t kV3TmemCols = 512;
 
 // blob (kernel layout, W^T [in][out] per layer) -> UMMA images.  out: [2 dirs][n_layers][hi|lo][1024] floats.
-__global__ void convonet_pack_umma_kernel(const float* __restrict__ Wb, int n_layers, float* __restrict__ out) {
+__global__ void convonet_pack_umma_kernel(const float* __restrict__ Wb_arg, int n_layers, float* __restrict__ out_arg,
+                                          const LoopJob* __restrict__ job) {
   using L = ConvDecLayout<32>;
+  const float* __restrict__ Wb = job ? job->W : Wb_arg;
+  float* __restrict__ out = job ? const_cast<float*>(job->Wimg) : out_arg;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_layers * 1024) return;
   const int l = e >> 10, i = (e >> 5) & 31, o = e & 31;        // WT[i][o] = W[o][i]
@@ -110,6 +113,7 @@ struct DecodeV3Args {
   double* stat_part;
   int n, K, B, R, n_blocks;
   float denom, target, ginv;
+  const LoopJob* job;    // non-null: planes / W / Wimg / xyz / grad_out come from this record (graph replay)
 };
 
 struct DecodeV3Smem {

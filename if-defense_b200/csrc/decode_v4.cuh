@@ -4,7 +4,7 @@
 // (two L2-bound gather phases around a 30-layer tcgen05 round-trip chain), and since the loops of two batches run
 // side by side (ifd_convonet_opt_batches) SM time is what limits throughput.  v4 = 256 threads, 256 points, 2 tiles,
 // 192 TMEM columns, 128 registers, and 88 KB of shared memory because the weight images are streamed per ResNet block
-// instead of held for the whole direction: two CTAs (from the same or from different launches) are resident per SM and
+// (one TMA bulk copy per stage) instead of held for the whole direction: two CTAs (from the same or from different launches) are resident per SM and
 // fill each other's stalls.  Arithmetic, layouts and helpers are v3's (same bits per point).
 #pragma once
 #include "decode_v3.cuh"
@@ -26,6 +26,12 @@ struct DecodeV4Smem {
 
 __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v4_kernel(const DecodeV3Args a) {
   extern __shared__ float4 smem4[];
+  // graph replay: the buffers of THIS launch are in the job record (uniform branch, five 8-byte loads per thread)
+  const float* __restrict__ g_planes = a.job ? a.job->planes : a.planes;
+  const float* __restrict__ g_W = a.job ? a.job->W : a.W;
+  const float* __restrict__ g_Wimg = a.job ? a.job->Wimg : a.Wimg;
+  const float* __restrict__ g_xyz = a.job ? a.job->xyz : a.xyz;
+  float* __restrict__ g_grad = a.job ? a.job->g_occ : a.grad_out;
   using L = ConvDecLayout<32>;
   const int n_layers = 3 * a.n_blocks;
   float* wimg = reinterpret_cast<float*>(smem4);                           // [2 stage buffers][3 layers][2048]
@@ -34,13 +40,13 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v4_kernel(const
   uint64_t* bars = reinterpret_cast<uint64_t*>(gpart + kV4Pts);             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* vec = reinterpret_cast<float*>(reinterpret_cast<char*>(bars) + 256);   // [n_layers][32] biases | fc_p 4x32 | fc_out 2x32
-  const float* Wb = a.W;
+  const float* Wb = g_W;
 
   const int tile0 = blockIdx.x * kV4Pts;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int group = warp >> 2;                                              // tile of this thread
   const int grp = lane >> 3, j4 = lane & 7;
-  const float4* __restrict__ planes4 = reinterpret_cast<const float4*>(a.planes);
+  const float4* __restrict__ planes4 = reinterpret_cast<const float4*>(g_planes);
   const uint32_t plane4 = (uint32_t)(a.R * a.R * 8);              // one plane of one cloud, in float4 units
 
   if (warp == 0) umma::tmem_alloc(tmem_slot, kV4TmemCols);
@@ -49,28 +55,32 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v4_kernel(const
     umma::fence_mbar_init();
   }
   // Weight images are streamed one ResNet block (3 layers, 24 KB) at a time through two stage buffers: stage t < n_blocks
-  // is forward block t, stage t >= n_blocks is backward (transposed images) block 2 n_blocks - 1 - t.  The next stage
-  // is fetched with cp.async while the current one computes, so a CTA needs 48 KB of images instead of 120 KB and two
-  // CTAs share an SM -- one's gathers (L2-bound) run under the other's MLP chain (latency-bound).
+  // is forward block t, stage t >= n_blocks is backward (transposed images) block 2 n_blocks - 1 - t.  One thread fetches
+  // the next stage with ONE TMA bulk copy (cp.async.bulk -> mbarrier complete_tx) while the current one computes, so a CTA
+  // needs 48 KB of images instead of 120 KB and two CTAs share an SM -- one's gathers (L2-bound) run under the other's MLP
+  // chain (latency-bound).
+  uint64_t* wbar = bars + 2;                                                 // [2]: bytes of stage buffer t & 1 have landed
   const int n_stages = 2 * a.n_blocks;
-  auto prefetch_stage = [&](int t) {
+  auto prefetch_stage = [&](int t) {                                         // thread 0 only
     const int blk = t < a.n_blocks ? t : n_stages - 1 - t;
-    const float4* src = reinterpret_cast<const float4*>(a.Wimg + ((size_t)(t < a.n_blocks ? 0 : n_layers) + 3 * blk) * kV3ImgFloats);
-    const uint32_t dst = umma::smem_u32(wimg + (size_t)(t & 1) * kV4StageFloats);
-    for (int i = threadIdx.x; i < kV4StageFloats / 4; i += kV4Threads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + i) : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* src = g_Wimg + ((size_t)(t < a.n_blocks ? 0 : n_layers) + 3 * blk) * kV3ImgFloats;
+    umma::mbar_arrive_expect_tx(&wbar[t & 1], kV4StageFloats * 4);
+    umma::bulk_g2s(wimg + (size_t)(t & 1) * kV4StageFloats, src, kV4StageFloats * 4, &wbar[t & 1]);
   };
-  // every thread: its copies of stage t have landed, everybody is done with stage t - 1 (whose buffer stage t + 1 takes)
+  // every thread: everybody is done with stage t - 1 (whose buffer stage t + 1 takes), the bytes of stage t have landed
   auto begin_stage = [&](int t) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    if (t + 1 < n_stages) prefetch_stage(t + 1);
+    umma::mbar_wait(&wbar[t & 1], (uint32_t)((t >> 1) & 1));
+    if (threadIdx.x == 0 && t + 1 < n_stages) prefetch_stage(t + 1);
   };
-  prefetch_stage(0);
+  if (threadIdx.x == 0) {
+    umma::mbar_init(&wbar[0], 1);
+    umma::mbar_init(&wbar[1], 1);
+    umma::fence_mbar_init();
+    prefetch_stage(0);
+  }
   for (int i = threadIdx.x; i < (n_layers + 6) * 32; i += kV4Threads) {
     const int row = i >> 5, c = i & 31;
     float v;
@@ -83,7 +93,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v4_kernel(const
   // ---------------- own point (slot = thread) and its geometry
   const int slot = threadIdx.x;
   const int pi = min(tile0 + slot, a.n - 1);
-  const float p0 = a.xyz[(size_t)pi * 3 + 0], p1 = a.xyz[(size_t)pi * 3 + 1], p2 = a.xyz[(size_t)pi * 3 + 2];
+  const float p0 = g_xyz[(size_t)pi * 3 + 0], p1 = g_xyz[(size_t)pi * 3 + 1], p2 = g_xyz[(size_t)pi * 3 + 2];
   const V3Geom geo = v3_geom(p0, p1, p2, a.R, a.denom, pi / a.K);
   // ---------------- forward gather: warp w serves tile slots 32w .. 32w+31 (its own threads' points), four points
   //                  per pass, 8 lanes x float4 = one 128-byte texel
@@ -292,9 +302,9 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v4_kernel(const
     if (j4 == 0 && pi_raw < a.n) {
       const float4 gp = gpart[gslot];
       const size_t o = (size_t)pi_raw * 3;
-      a.grad_out[o + 0] = gp.x + gi[0] * (((pk[0] >> 17) & 1) ? dsc : 0.0f);
-      a.grad_out[o + 1] = gp.y + gi[1] * (((pk[1] >> 17) & 1) ? dsc : 0.0f);
-      a.grad_out[o + 2] = gp.z + gi[2] * (((pk[2] >> 17) & 1) ? dsc : 0.0f);
+      g_grad[o + 0] = gp.x + gi[0] * (((pk[0] >> 17) & 1) ? dsc : 0.0f);
+      g_grad[o + 1] = gp.y + gi[1] * (((pk[1] >> 17) & 1) ? dsc : 0.0f);
+      g_grad[o + 2] = gp.z + gi[2] * (((pk[2] >> 17) & 1) ? dsc : 0.0f);
     }
   }
   umma::fence_before_sync();

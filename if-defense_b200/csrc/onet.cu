@@ -17,6 +17,7 @@
 // forward pass are kept in HBM (11 x [M][256] fp32) for the dgrad masks -- 740 MB at B=64, K=1024.
 #include "common.cuh"
 #include "ifd_math.cuh"
+#include "tc_gemm.cuh"
 #include "umma.cuh"
 
 namespace ifd {
@@ -93,6 +94,87 @@ struct GemmArgs {
   const float* mask_t;   // [B][256]
   float* out;            // [M][256]
   int M, K;              // rows, points per cloud
+};
+
+// The same layer on the shared GEMM engine (tc_gemm.cuh): warp-specialised, A chunks produced into shared memory while the
+// previous chunk's MMAs run, weights by TMA bulk copies, epilogue of tile i under the main loop of tile i + 1.  The weight
+// images of onet_pack_layer_kernel ARE the engine's format (one N tile of 256, eight chunks, hi | lo per chunk).
+struct OnetLayerParams {
+  int M, n_chunks, n_tiles_n;
+  const float* wimg;
+  GemmArgs g;
+};
+struct OnetLayerPolicy {
+  using Params = OnetLayerParams;
+  struct Row { int row, b; };
+  static __device__ __forceinline__ Row row_begin(const Params& P, int row) {
+    const int rc = min(row, P.M - 1);
+    return Row{row, rc / P.g.K};
+  }
+  static __device__ __forceinline__ void load(const Params& P, const Row& r, int kc, float (&x)[32]) {
+    if (r.row >= P.M) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k] = 0.0f;
+      return;
+    }
+    const float4* p4 = reinterpret_cast<const float4*>(P.g.A + (size_t)r.row * kOH + kc * kChunk);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(p4 + q);
+      x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+    if (P.g.pro_s) {                    // CBN (eval mode, folded) + ReLU on read
+      const float4* s4 = reinterpret_cast<const float4*>(P.g.pro_s + (size_t)r.b * kOH + kc * kChunk);
+      const float4* t4 = reinterpret_cast<const float4*>(P.g.pro_t + (size_t)r.b * kOH + kc * kChunk);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 s = __ldg(s4 + q), t = __ldg(t4 + q);
+        x[4 * q + 0] = fmaxf(fmaf(s.x, x[4 * q + 0], t.x), 0.0f);
+        x[4 * q + 1] = fmaxf(fmaf(s.y, x[4 * q + 1], t.y), 0.0f);
+        x[4 * q + 2] = fmaxf(fmaf(s.z, x[4 * q + 2], t.z), 0.0f);
+        x[4 * q + 3] = fmaxf(fmaf(s.w, x[4 * q + 3], t.w), 0.0f);
+      }
+    }
+  }
+  static __device__ __forceinline__ void store(const Params& P, const Row& r, int col0, const float (&y_in)[32]) {
+    if (r.row >= P.M) return;
+    const GemmArgs& a = P.g;
+    float y[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) y[k] = y_in[k];
+    if (a.mask_x) {                     // dgrad through relu(s * x + t): scale by s where the pre-activation was positive
+      const float4* x4 = reinterpret_cast<const float4*>(a.mask_x + (size_t)r.row * kOH + col0);
+      const float4* s4 = reinterpret_cast<const float4*>(a.mask_s + (size_t)r.b * kOH + col0);
+      const float4* t4 = reinterpret_cast<const float4*>(a.mask_t + (size_t)r.b * kOH + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 xs = __ldg(x4 + q), s = __ldg(s4 + q), t = __ldg(t4 + q);
+        y[4 * q + 0] = fmaf(s.x, xs.x, t.x) > 0.0f ? y[4 * q + 0] * s.x : 0.0f;
+        y[4 * q + 1] = fmaf(s.y, xs.y, t.y) > 0.0f ? y[4 * q + 1] * s.y : 0.0f;
+        y[4 * q + 2] = fmaf(s.z, xs.z, t.z) > 0.0f ? y[4 * q + 2] * s.z : 0.0f;
+        y[4 * q + 3] = fmaf(s.w, xs.w, t.w) > 0.0f ? y[4 * q + 3] * s.w : 0.0f;
+      }
+    }
+    if (a.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(a.bias + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 bv = __ldg(b4 + q);
+        y[4 * q + 0] += bv.x; y[4 * q + 1] += bv.y; y[4 * q + 2] += bv.z; y[4 * q + 3] += bv.w;
+      }
+    }
+    if (a.resid) {
+      const float4* r4 = reinterpret_cast<const float4*>(a.resid + (size_t)r.row * kOH + col0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 rv = r4[q];        // plain load: the dgrad residual buffer is updated in place
+        y[4 * q + 0] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
+      }
+    }
+    float4* o4 = reinterpret_cast<float4*>(a.out + (size_t)r.row * kOH + col0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o4[q] = make_float4(y[4 * q + 0], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+  }
 };
 
 __global__ void __launch_bounds__(kGemmThreads, 2) onet_gemm_kernel(const GemmArgs a) {
@@ -392,7 +474,13 @@ OnetWs carve_onet(void* base, int B, int K) {
   w.bytes = off;
   return w;
 }
+int g_onet_engine = 1;     // ifd_test_hook(5, 0 / 1): 1 = the warp-specialised GEMM engine, 0 = the first-generation kernel
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+  if (g_onet_engine) {
+    OnetLayerParams P{};
+    P.M = a.M; P.n_chunks = kOH / kChunk; P.n_tiles_n = 1; P.wimg = a.img; P.g = a;
+    return tc::launch<OnetLayerPolicy>(P, 256, st);
+  }
   const size_t smem = (size_t)2 * kHalfImgFloats * 4 + 64;
   IFD_CUDA_TRY(set_max_dyn_smem((const void*)onet_gemm_kernel, smem));
   onet_gemm_kernel<<<dim3((a.M + kGemmThreads - 1) / kGemmThreads, 2), kGemmThreads, smem, st>>>(a);
@@ -549,9 +637,10 @@ extern "C" int ifd_onet_decode_bwd(const float* dec_weights, const float* xyz, c
 // Loop pieces shared with the ConvONet path (restore.cu)
 namespace ifd {
 int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int K, const ifd_opt_params* P, int i, void* conv_ws,
-                  bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st);
+                  bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st,
+                  const LoopJob* job, bool fresh);
 int opt_begin(float* m, float* v, bool zero_state, int B, int K, const ifd_opt_params* P, void* conv_ws, cudaStream_t st);
-int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st);
+int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st, const LoopJob* job);
 float* opt_ws_gocc(void* conv_ws, int B, int K);
 float* opt_ws_m(void* conv_ws, int B, int K);
 float* opt_ws_v(void* conv_ws, int B, int K);
@@ -573,7 +662,8 @@ extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz
   if (rc) return rc;
   float* m = adam_m ? adam_m : opt_ws_m(conv_ws, B, K);
   float* v = adam_v ? adam_v : opt_ws_v(conv_ws, B, K);
-  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, P, conv_ws, st))) return rc;
+  const bool fresh = !adam_m || P->step0 == 0;
+  if ((rc = opt_begin(m, v, fresh, B, K, P, conv_ws, st))) return rc;
   float* g_occ = opt_ws_gocc(conv_ws, B, K);
   const int M = B * K;
   const float ginv = (float)K / (float)((long long)P->B_ref * K);
@@ -589,7 +679,11 @@ extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz
       IFD_LAUNCH_CHECK("onet_head_kernel");
       if ((rc = onet_backward(dec_weights, w, B, K, g_occ, st))) return rc;
     }
-    if ((rc = opt_step_tail(xyz, m, v, g_occ, B, K, P, i, conv_ws, stat, w.stat, n_dec, stats_out, true, st))) return rc;
+    if ((rc = opt_step_tail(xyz, m, v, g_occ, B, K, P, i, conv_ws, stat, w.stat, n_dec, stats_out, true, st, nullptr, fresh))) return rc;
   }
-  return opt_finish(xyz, B, K, P->normalize_out, st);
+  return opt_finish(xyz, B, K, P->normalize_out, st, nullptr);
 }
+
+namespace ifd {
+void onet_set_engine(int on) { g_onet_engine = on ? 1 : 0; }
+}  // namespace ifd

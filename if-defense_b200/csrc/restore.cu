@@ -8,6 +8,8 @@
 //                                 integer atomics on an exact long accumulator (bitwise reproducible)
 //   adam_kernel                   g = g_occ + coef * acc ; torch-2.11 Adam update of xyz, m, v ; re-zero acc
 // then normalize_kernel (centre + unit sphere, opt_defense.py:76-83).
+#include <string.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -36,6 +38,7 @@ struct DecodeArgs {
   double* stat_part;         // optional [gridDim.x][2]: sum bce, sum sigmoid
   int B, K, R, n_blocks, wtotal4;
   float denom, target, ginv;
+  const LoopJob* job;        // decode v4 only (graph replay)
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -286,9 +289,10 @@ __global__ void adam_kernel(float* __restrict__ xyz, float* __restrict__ m, floa
 
 // normalize_batch_pc (opt_defense.py:76-83): one CTA per cloud.
 constexpr int kNormThreads = 256;
-__global__ void __launch_bounds__(kNormThreads) normalize_kernel(float* __restrict__ xyz, int K) {
+__global__ void __launch_bounds__(kNormThreads) normalize_kernel(float* __restrict__ xyz_arg, int K, const LoopJob* __restrict__ job) {
   __shared__ float red[3][kNormThreads / 32];
   __shared__ float bc[3];
+  float* xyz = job ? job->xyz : xyz_arg;
   float* cloud = xyz + (size_t)blockIdx.x * K * 3;
   float s[3] = {0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < K; i += kNormThreads)
@@ -430,7 +434,7 @@ static int launch_decode_v4(const DecodeArgs& a, const float* wimg, cudaStream_t
   DecodeV3Args v{};
   v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
   v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
-  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv;
+  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv; v.job = a.job;
   const size_t smem = DecodeV4Smem::bytes(a.n_blocks);
   if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v4: plane array too large for 32-bit texel indices");
   IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v4_kernel, smem));
@@ -501,6 +505,7 @@ float* opt_ws_m(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).m; }
 float* opt_ws_v(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).v; }
 
 static int g_inbox_cap = kCsInbox;   // ifd_test_hook(1, cap)
+static int g_bar_mode = 2;           // ifd_test_hook(4, mode): CloudStepArgs::bar_mode
 
 // The fused per-cloud tail (cloud_step.cuh) handles one point per thread; larger clouds and k + 1 > 8 use the
 // first-generation kernels (knn_repulsion_kernel + adam_kernel), as does tail_kernel == 1.
@@ -511,7 +516,7 @@ bool opt_tail_fused(int K, const ifd_opt_params* P) {
 int opt_begin(float* m, float* v, bool zero_state, int B, int K, const ifd_opt_params* P, void* ws, cudaStream_t st) {
   OptWorkspace w = carve_opt_ws(ws, B, K);
   const size_t n = (size_t)B * K * 3;
-  if (zero_state) {
+  if (zero_state && !opt_tail_fused(K, P)) {       // the fused tail treats step 0 of a fresh run as m = v = 0 itself (zero_mv)
     IFD_CUDA_TRY(cudaMemsetAsync(m, 0, n * sizeof(float), st));
     IFD_CUDA_TRY(cudaMemsetAsync(v, 0, n * sizeof(float), st));
   }
@@ -521,7 +526,8 @@ int opt_begin(float* m, float* v, bool zero_state, int B, int K, const ifd_opt_p
 
 // After the decoder produced g_occ for step i: kNN + repulsion, optional diagnostics, Adam.
 int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int K, const ifd_opt_params* P, int i, void* ws,
-                  bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st) {
+                  bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st,
+                  const LoopJob* job, bool fresh) {
   OptWorkspace w = carve_opt_ws(ws, B, K);
   const size_t n = (size_t)B * K * 3;
   const bool rep = P->rep_weight > 0.0;
@@ -537,9 +543,10 @@ int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int
   if (opt_tail_fused(K, P)) {
     CloudStepArgs c{};
     c.xyz = xyz; c.m = m; c.v = v; c.g_occ = g_occ; c.nbr = w.nbr; c.loss_part = stat ? w.loss_part : nullptr;
-    c.K = K; c.k = P->knn_k; c.warm = (i > 0 && warm_ok) ? 1 : 0; c.inbox_cap = g_inbox_cap;
+    c.K = K; c.k = P->knn_k; c.warm = (i > 0 && warm_ok) ? 1 : 0; c.inbox_cap = g_inbox_cap; c.bar_mode = g_bar_mode;
     c.radius = (float)P->rep_radius; c.h = (float)P->rep_h; c.eps = (float)P->rep_eps; c.rep_coef = rep_coef;
     c.omb1 = omb1; c.b2 = (float)P->beta2; c.omb2 = omb2; c.adam_eps = (float)P->adam_eps; c.sc = sc;
+    c.job = job; c.zero_mv = (fresh && i == 0 && P->step0 == 0) ? 1 : 0;
     {
       ProfileScope ps(1, st);
       IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
@@ -574,9 +581,9 @@ int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int
   return IFD_OK;
 }
 
-int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st) {
+int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st, const LoopJob* job) {
   if (normalize) {
-    normalize_kernel<<<B, kNormThreads, 0, st>>>(xyz, K);
+    normalize_kernel<<<B, kNormThreads, 0, st>>>(xyz, K, job);
     IFD_LAUNCH_CHECK("normalize_kernel");
   }
   return IFD_OK;
@@ -584,6 +591,159 @@ int opt_finish(float* xyz, int B, int K, int normalize, cudaStream_t st) {
 }  // namespace ifd
 
 using namespace ifd;
+
+namespace {
+int g_use_graph = 1;   // ifd_test_hook(3, 0 / 1)
+
+// The loop of optimize_points (opt_defense.py:210-239) as a sequence of launches on `st`.  With `job` the kernels take every
+// buffer pointer from that device record (graph capture); the pointer arguments are then only used for shapes.
+int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, float* m, float* v, bool fresh, int B, int K, int R,
+                 int n_blocks, const ifd_opt_params* P, double* stats_out, void* workspace, const LoopJob* job, cudaStream_t st) {
+  OptWorkspace w = carve_opt_ws(workspace, B, K);
+  int rc;
+  if ((rc = opt_begin(m, v, fresh, B, K, P, workspace, st))) return rc;
+  DecodeArgs a{};
+  a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_out = w.g_occ; a.job = job;
+  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(P->padding);
+  a.target = (float)P->occ_target;
+  // d/dlogit of (mean over B_ref*K) * K: autograd multiplies K, then divides by the element count
+  a.ginv = (float)K / (float)((long long)P->B_ref * K);
+  const int dk = P->decode_kernel == 0 ? 4 : P->decode_kernel;
+  const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads          // CTAs of the decode kernel (stat partials)
+                    : dk == 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
+  if (dk >= 3) {
+    const int nl = 3 * n_blocks;
+    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, job);
+    IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
+  }
+  for (int i = 0; i < P->n_steps; ++i) {
+    const bool stat = P->want_stats && stats_out && (i % 100 == 0);
+    a.stat_part = stat ? w.dec_part : nullptr;
+    {
+      ProfileScope ps(0, st);
+      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
+                   : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+      if (rc) return rc;
+    }
+    if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1, st, job, fresh))) return rc;
+  }
+  return opt_finish(xyz, B, K, P->normalize_out, st, job);
+}
+
+// ---- cached graphs of the loop --------------------------------------------------------------------------------------------
+constexpr int kJobSlots = 8;       // one LoopJob record + one set of graphs per caller stream (LRU over 8 streams)
+struct GraphKey {
+  int B, K, R, n_blocks, slot, inbox_cap;
+  ifd_opt_params P;
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec;
+  long long kernels;
+  unsigned long long used;
+};
+struct GraphCache {
+  int device = -1;
+  LoopJob* jobs = nullptr;                         // device, [kJobSlots]
+  cudaStream_t cap = nullptr;                      // capture stream
+  cudaStream_t owner[kJobSlots] = {};              // caller stream that owns slot i
+  bool taken[kJobSlots] = {};
+  unsigned long long slot_used[kJobSlots] = {};
+  unsigned long long tick = 0;
+  std::vector<GraphEntry> entries;
+};
+thread_local GraphCache g_graphs;
+
+void drop_graphs() {
+  for (GraphEntry& e : g_graphs.entries) cudaGraphExecDestroy(e.exec);
+  g_graphs.entries.clear();
+  if (g_graphs.jobs) cudaFree(g_graphs.jobs);
+  if (g_graphs.cap) cudaStreamDestroy(g_graphs.cap);
+  g_graphs = GraphCache();
+}
+
+__global__ void set_job_kernel(LoopJob* slot, const LoopJob job) { *slot = job; }
+
+int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, const ifd_opt_params* P, cudaStream_t st) {
+  GraphCache& g = g_graphs;
+  int dev = 0;
+  IFD_CUDA_TRY(cudaGetDevice(&dev));
+  if (g.device != dev) {
+    if (g.device >= 0) drop_graphs();
+    IFD_CUDA_TRY(cudaMalloc((void**)&g.jobs, kJobSlots * sizeof(LoopJob)));
+    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g.cap, cudaStreamNonBlocking));
+    g.device = dev;
+  }
+  // the record (and the graphs that read it) belong to the caller's stream: launches on one stream are ordered, two
+  // streams never share a record
+  int slot = -1;
+  for (int i = 0; i < kJobSlots; ++i)
+    if (g.taken[i] && g.owner[i] == st) slot = i;
+  if (slot < 0) {
+    for (int i = 0; i < kJobSlots && slot < 0; ++i)
+      if (!g.taken[i]) slot = i;
+    if (slot < 0) {                                // every record is taken: recycle the least recently used one
+      slot = 0;
+      for (int i = 1; i < kJobSlots; ++i)
+        if (g.slot_used[i] < g.slot_used[slot]) slot = i;
+      if (cudaStreamSynchronize(g.owner[slot]) != cudaSuccess) cudaGetLastError();     // (a destroyed stream is simply done)
+    }
+    g.taken[slot] = true;
+    g.owner[slot] = st;
+  }
+  g.slot_used[slot] = ++g.tick;
+
+  GraphKey key;
+  memset(&key, 0, sizeof key);
+  key.B = B; key.K = K; key.R = R; key.n_blocks = n_blocks; key.slot = slot; key.inbox_cap = g_inbox_cap * 4 + g_bar_mode;
+  memcpy(&key.P, P, sizeof(ifd_opt_params));
+  GraphEntry* hit = nullptr;
+  for (GraphEntry& e : g.entries)
+    if (memcmp(&e.key, &key, sizeof key) == 0) hit = &e;
+  if (!hit) {
+    // attributes first (cudaFuncSetAttribute is not a stream operation, but keep the capture free of anything else)
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v4_kernel, DecodeV4Smem::bytes(n_blocks)));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
+    const long long before = launch_counter_ref();
+    IFD_CUDA_TRY(cudaStreamBeginCapture(g.cap, cudaStreamCaptureModeThreadLocal));
+    // shapes only: every pointer the kernels use comes from the record of this slot
+    int rc = enqueue_loop(job.planes, job.W, job.xyz, job.m, job.v, true, B, K, R, n_blocks, P, nullptr,
+                          (void*)nullptr, g.jobs + slot, g.cap);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(g.cap, &graph);
+    const long long kernels = launch_counter_ref() - before;
+    launch_counter_ref() = before;                 // captured, not launched
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ee != cudaSuccess) return cuda_fail(ee, "cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return cuda_fail(ei, "cudaGraphInstantiate");
+    if (g.entries.size() >= 16) {                  // evict the least recently used graph
+      size_t lru = 0;
+      for (size_t i = 1; i < g.entries.size(); ++i)
+        if (g.entries[i].used < g.entries[lru].used) lru = i;
+      cudaGraphExecDestroy(g.entries[lru].exec);
+      g.entries.erase(g.entries.begin() + lru);
+    }
+    g.entries.push_back(GraphEntry{key, exec, kernels, 0});
+    hit = &g.entries.back();
+  }
+  hit->used = ++g.tick;
+  set_job_kernel<<<1, 1, 0, st>>>(g.jobs + slot, job);
+  IFD_LAUNCH_CHECK("set_job_kernel");
+  IFD_CUDA_TRY(cudaGraphLaunch(hit->exec, st));
+  count_launch((int)hit->kernels);
+  return IFD_OK;
+}
+}  // namespace
+
+namespace ifd {
+void release_graphs() { drop_graphs(); }
+}  // namespace ifd
 
 extern "C" size_t ifd_convonet_decoder_nfloats(int C, int H, int n_blocks) {
   if (C != H || H <= 0 || n_blocks <= 0) return 0;
@@ -685,35 +845,18 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   OptWorkspace w = carve_opt_ws(workspace, B, K);
   float* m = adam_m ? adam_m : w.m;
   float* v = adam_v ? adam_v : w.v;
-  if ((rc = opt_begin(m, v, !adam_m || P->step0 == 0, B, K, P, workspace, st))) return rc;
-
-  DecodeArgs a{};
-  a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_out = w.g_occ;
-  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(P->padding);
-  a.target = (float)P->occ_target;
-  // d/dlogit of (mean over B_ref*K) * K: autograd multiplies K, then divides by the element count
-  a.ginv = (float)K / (float)((long long)P->B_ref * K);
   const int dk = P->decode_kernel == 0 ? 4 : P->decode_kernel;
   if (dk < 1 || dk > 4) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0..4");
-  const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads          // CTAs of the decode kernel (stat partials)
-                    : dk == 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
-  if (dk >= 3) {
-    const int nl = 3 * n_blocks;
-    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg);
-    IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
+  if (dk == 4 && (unsigned long long)3 * B * R * R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v4: plane array too large for 32-bit texel indices");
+  const bool stats = P->want_stats && stats_out;
+  // The common case -- a fresh run of the production kernels without diagnostics -- replays ONE cached CUDA graph of the
+  // whole loop (pack, n_steps x {decode, cloud_step}, normalise): the kernels read their buffers from a LoopJob record, so
+  // the graph does not depend on the pointers and the host enqueues two operations instead of ~400.
+  if (g_use_graph && dk == 4 && !stats && !adam_m && P->step0 == 0 && P->n_steps >= 4 && opt_tail_fused(K, P) && !profile_on()) {
+    LoopJob job{planes_cl, dec_weights, w.wimg, xyz, w.g_occ, m, v, w.nbr};
+    return launch_loop_graph(job, B, K, R, n_blocks, P, st);
   }
-  for (int i = 0; i < P->n_steps; ++i) {
-    const bool stat = P->want_stats && stats_out && (i % 100 == 0);
-    a.stat_part = stat ? w.dec_part : nullptr;
-    {
-      ProfileScope ps(0, st);
-      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
-                   : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
-      if (rc) return rc;
-    }
-    if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1, st))) return rc;
-  }
-  return opt_finish(xyz, B, K, P->normalize_out, st);
+  return enqueue_loop(planes_cl, dec_weights, xyz, m, v, !adam_m || P->step0 == 0, B, K, R, n_blocks, P, stats_out, workspace, nullptr, st);
 }
 
 // One loop tail as a seam of its own (opt_defense.py:219-228: repulsion loss, its backward, Adam step).
@@ -728,7 +871,7 @@ extern "C" int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const
   const double t = (double)(step_index + 1);
   CloudStepArgs c{};
   c.xyz = xyz; c.m = adam_m; c.v = adam_v; c.g_occ = g_occ; c.nbr = nbr; c.loss_part = loss_sum_out; c.rep_grad_out = rep_grad_out;
-  c.K = K; c.k = P->knn_k; c.warm = warm ? 1 : 0; c.inbox_cap = g_inbox_cap;
+  c.K = K; c.k = P->knn_k; c.warm = warm ? 1 : 0; c.inbox_cap = g_inbox_cap; c.bar_mode = g_bar_mode;
   c.radius = (float)P->rep_radius; c.h = (float)P->rep_h; c.eps = (float)P->rep_eps;
   c.rep_coef = ((float)P->rep_weight / (float)P->B_ref) / (float)(K * P->knn_k);
   c.omb1 = (float)(1.0 - P->beta1); c.b2 = (float)P->beta2; c.omb2 = (float)(1.0 - P->beta2); c.adam_eps = (float)P->adam_eps;
@@ -833,16 +976,20 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   a.ginv = (float)K / (float)((long long)B_ref * K);
   if (dk >= 3) {
     const int nl = 3 * n_blocks;
-    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg);
+    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, nullptr);
     IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
   }
   return dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
                  : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
 }
 
+namespace ifd { void onet_set_engine(int on); }
 extern "C" void ifd_test_hook(int key, int value) {
+  if (key == 5) onet_set_engine(value);
   if (key == 1) g_inbox_cap = value < 0 ? 0 : (value > kCsInbox ? kCsInbox : value);
   if (key == 2) g_lanes = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);
+  if (key == 3) g_use_graph = value ? 1 : 0;
+  if (key == 4) g_bar_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
 }
 
 extern "C" int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream) {

@@ -1,0 +1,283 @@
+// tc_gemm.cuh -- one warp-specialised, persistent tcgen05 GEMM engine for every dense contraction of the path that is not
+// the fused ConvONet decode: the Linear stacks of both encoders, the U-Net's convolutions (implicit GEMM, channels-last),
+// the transposed convolutions, and the 256-wide ONet layers.
+//
+//   Out[m][n] = epilogue( sum_k A(m, k) * W[n][k] ),   fp32 semantics through 3xTF32 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi,
+//   fp32 accumulation in TMEM).  The tensor core truncates the accumulator at every MMA, so what limits the accuracy of a
+//   long K is the NUMBER of accumulations at full magnitude: for NT <= 128 the two small cross terms go to a second
+//   accumulator (2^-11 of the magnitude, so its truncations do not count) and only the four hi.hi MMAs per chunk touch the
+//   main one; the epilogue adds the two.  Measured: 3.3e-5 -> ~1e-5 absolute at K = 1152, |result| ~ 1.
+//
+// A CTA walks tiles of 128 rows x NT columns (tile index = blockIdx.x + i * gridDim.x).  Roles:
+//   warps 0-3  A producers: thread r owns row r of the tile; per K chunk of 32 it asks the Policy for the 32 values of
+//              its row (a global row of a matrix, a 3x3 tap of a channels-last image, a pooled pixel, ...), splits them into
+//              TF32 hi / lo and writes the two K-major no-swizzle UMMA images of the chunk into a pipeline stage;
+//   warp 9     B loader: one thread, ONE TMA bulk copy (cp.async.bulk) per chunk of the pre-packed weight image
+//              [NT x 32] hi | lo, completion counted in bytes on the stage's mbarrier;
+//   warp 8     MMA issuer: one thread, 12 tcgen05.mma (M = 128, N = NT, K = 8) per chunk, both operands from shared memory,
+//              tcgen05.commit releases the stage; the accumulator of a tile lives in one of TWO TMEM stages;
+//   warps 4-7  epilogue: tcgen05.ld the finished accumulator (thread = row), hand 32 columns at a time to the Policy
+//              (bias, ReLU, residual, pixel shuffle, ...), while the MMA warp is already on the next tile.
+// Stage hand-off is mbarrier-only (no __syncthreads in the main loop).
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ifd {
+namespace tc {
+
+constexpr int kThreads = 320;
+constexpr int kChunk = 32;                       // K per pipeline stage
+constexpr int kAStageBytes = 2 * 128 * kChunk * 4;   // hi + lo images of the A chunk: 32 KB
+
+__host__ __device__ constexpr int b_stage_bytes(int NT) { return 2 * NT * kChunk * 4; }
+__host__ __device__ constexpr int stages_for(int NT) { return NT >= 256 ? 2 : (NT >= 128 ? 3 : 4); }
+__host__ __device__ constexpr size_t smem_bytes(int NT) {
+  return (size_t)stages_for(NT) * (kAStageBytes + b_stage_bytes(NT)) + 256;
+}
+
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, one elected thread issues
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+
+// Weight pre-pack: W (row-major [N][K], row stride ldw; or its transpose when `transposed`: element (n, k) = W[k * ldw + n])
+// -> [N_pad / NT tiles][K_pad / 32 chunks][hi | lo][NT x 32] K-major UMMA images, zero padded.
+static __global__ void pack_weights_kernel(const float* __restrict__ W, int N, int K, int ldw, int transposed, int NT, int n_tiles,
+                                    int n_chunks, float* __restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n_tiles * n_chunks * NT * kChunk;
+  if (e >= total) return;
+  const int kl = (int)(e % kChunk);
+  const int nl = (int)((e / kChunk) % NT);
+  const int kc = (int)((e / ((long long)kChunk * NT)) % n_chunks);
+  const int nt = (int)(e / ((long long)kChunk * NT * n_chunks));
+  const int n = nt * NT + nl, k = kc * kChunk + kl;
+  float w = 0.0f;
+  if (n < N && k < K) w = transposed ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k];
+  float* img = out + ((size_t)nt * n_chunks + kc) * (2 * NT * kChunk);
+  const uint32_t off = umma::img_offset(nl, kl, NT) / 4;
+  img[off] = __uint_as_float(umma::tf32_hi(w));
+  img[NT * kChunk + off] = __uint_as_float(umma::tf32_lo(w));
+}
+
+// A Policy provides
+//   struct Params (trivially copyable; must contain  int M, n_chunks, n_tiles_n;  const float* wimg;)
+//   struct Row;                                                            per-row state of the producer / epilogue thread
+//   static __device__ Row row_begin(const Params&, int row);               row < M is NOT guaranteed (check yourself)
+//   static __device__ void load(const Params&, const Row&, int kc, float (&x)[32]);        the 32 A values of chunk kc
+//   static __device__ void store(const Params&, const Row&, int col0, const float (&y)[32]); columns col0 .. col0 + 31
+template <class Policy, int NT>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy::Params P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int S = stages_for(NT);
+  constexpr int kBStage = b_stage_bytes(NT);
+  constexpr bool kSplit = NT <= 128;                        // second accumulator for the small cross terms (see the header)
+  constexpr uint32_t kAcc = kSplit ? 2 * NT : NT;           // TMEM columns per accumulator stage (main | small)
+  constexpr uint32_t kTmemCols = 2 * kAcc;                  // 64 .. 512, a power of two
+  unsigned char* a_st = smem_raw;                           // [S][32 KB]
+  unsigned char* b_st = smem_raw + (size_t)S * kAStageBytes;    // [S][kBStage]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_st + (size_t)S * kBStage);
+  uint64_t* full_a = bars;                 // [S] 128 producer arrivals
+  uint64_t* full_b = bars + S;             // [S] 1 arrival + tx bytes
+  uint64_t* empty = bars + 2 * S;          // [S] tcgen05.commit
+  uint64_t* acc_full = bars + 3 * S;       // [2] tcgen05.commit after the last chunk of a tile
+  uint64_t* acc_empty = bars + 3 * S + 2;  // [2] 128 epilogue arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      umma::mbar_init(&full_a[s], 128);
+      umma::mbar_init(&full_b[s], 1);
+      umma::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      umma::mbar_init(&acc_full[s], 1);
+      umma::mbar_init(&acc_empty[s], 128);
+    }
+    umma::fence_mbar_init();
+  }
+  if (warp == 8) umma::tmem_alloc(tmem_slot, kTmemCols);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  const int m_tiles = (P.M + 127) / 128;
+  const int n_tiles = m_tiles * P.n_tiles_n;
+  const int n_chunks = P.n_chunks;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ A producers
+    const int r = threadIdx.x;                      // row of the tile
+    uint32_t it = 0;                                // global chunk counter -> stage / phase
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int mt = t / P.n_tiles_n;
+      const typename Policy::Row row = Policy::row_begin(P, mt * 128 + r);
+      for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        float x[32];
+        Policy::load(P, row, kc, x);                // global loads first: they fly while we wait for the stage
+        umma::mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* hi = a_st + (size_t)s * kAStageBytes + (r >> 3) * 128 + (r & 7) * 16;
+        unsigned char* lo = hi + 128 * kChunk * 4;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          uint4 h, l;
+          h.x = umma::tf32_hi_fast(x[4 * g + 0]); h.y = umma::tf32_hi_fast(x[4 * g + 1]);
+          h.z = umma::tf32_hi_fast(x[4 * g + 2]); h.w = umma::tf32_hi_fast(x[4 * g + 3]);
+          l.x = __float_as_uint(x[4 * g + 0] - __uint_as_float(h.x)); l.y = __float_as_uint(x[4 * g + 1] - __uint_as_float(h.y));
+          l.z = __float_as_uint(x[4 * g + 2] - __uint_as_float(h.z)); l.w = __float_as_uint(x[4 * g + 3] - __uint_as_float(h.w));
+          *reinterpret_cast<uint4*>(hi + g * 2048) = h;      // k group g: 16 core-matrix rows of 128 B per 8 tile rows
+          *reinterpret_cast<uint4*>(lo + g * 2048) = l;
+        }
+        umma::fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core's async proxy
+        mbar_arrive(&full_a[s]);
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ epilogue (warp - 4 = TMEM lane quarter)
+    const int r = threadIdx.x - 128;
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+      const int mt = t / P.n_tiles_n, nt = t % P.n_tiles_n;
+      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+      const typename Policy::Row row = Policy::row_begin(P, mt * 128 + r);
+      umma::mbar_wait(&acc_full[as], aph);
+      umma::fence_after_sync();
+      const uint32_t taddr = tmem + as * kAcc + ((uint32_t)((warp - 4) * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < NT / 32; ++c) {
+        uint32_t d[32];
+        umma::tmem_ld32(taddr + c * 32, d);
+        float y[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(d[k]);
+        if (kSplit) {
+          umma::tmem_ld32(taddr + NT + c * 32, d);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) y[k] += __uint_as_float(d[k]);
+        }
+        Policy::store(P, row, nt * NT + c * 32, y);
+      }
+      umma::fence_before_sync();
+      mbar_arrive(&acc_empty[as]);
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma::idesc_tf32(128, NT);
+      uint32_t it = 0, tl = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        umma::mbar_wait(&acc_empty[as], aph ^ 1);   // the epilogue drained this accumulator stage (two tiles ago)
+        umma::fence_after_sync();
+        const uint32_t d_t = tmem + as * kAcc;
+        for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          umma::mbar_wait(&full_a[s], ph);
+          umma::mbar_wait(&full_b[s], ph);
+          umma::fence_after_sync();
+          const uint32_t sa = umma::smem_u32(a_st + (size_t)s * kAStageBytes);
+          const uint32_t sb = umma::smem_u32(b_st + (size_t)s * kBStage);
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {    // lo.hi, hi.lo, hi.hi (small terms first)
+            const uint32_t a_s = sa + (part == 0 ? 128 * kChunk * 4 : 0);
+            const uint32_t b_s = sb + (part == 1 ? NT * kChunk * 4 : 0);
+            const uint32_t d_p = (kSplit && part < 2) ? d_t + NT : d_t;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t later = kSplit ? (part == 1 ? 1u : (uint32_t)q) : (uint32_t)(part | q);    // 0 only for the first MMA into an accumulator
+              mma_tf32_ss(d_p, umma::smem_desc_kmajor(a_s + q * 4096, 2048, 128),
+                          umma::smem_desc_kmajor(b_s + q * (NT * 32), NT * 16, 128), idesc, (kc | later) ? 1u : 0u);
+            }
+          }
+          umma::commit(&empty[s]);                  // the stage is free once these MMAs have read it
+        }
+        umma::commit(&acc_full[as]);                // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ B loader (TMA bulk copies)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nt = t % P.n_tiles_n;
+        const float* src = P.wimg + (size_t)nt * n_chunks * (2 * NT * kChunk);
+        for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          umma::mbar_wait(&empty[s], ph ^ 1);
+          umma::mbar_arrive_expect_tx(&full_b[s], kBStage);
+          umma::bulk_g2s(b_st + (size_t)s * kBStage, src + (size_t)kc * (2 * NT * kChunk), kBStage, &full_b[s]);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// Tile width of the encoder operators: at most 128 columns, so that every tile keeps the small cross terms in a second
+// accumulator (the long K of a convolution, up to 9 x 256, needs it to stay at fp32-class accuracy).  256-wide tiles are
+// used by the ONet decoder layers only (K = 256, one A pass per row matters more there).
+inline int pick_nt(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : 128); }
+
+inline int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <class Policy>
+int launch(const typename Policy::Params& P, int NT, cudaStream_t st) {
+  const int tiles = ((P.M + 127) / 128) * P.n_tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  if (grid <= 0) return IFD_OK;
+  const size_t smem = smem_bytes(NT);
+  switch (NT) {
+    case 32:
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 32>, smem));
+      gemm_kernel<Policy, 32><<<grid, kThreads, smem, st>>>(P);
+      break;
+    case 64:
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 64>, smem));
+      gemm_kernel<Policy, 64><<<grid, kThreads, smem, st>>>(P);
+      break;
+    case 128:
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 128>, smem));
+      gemm_kernel<Policy, 128><<<grid, kThreads, smem, st>>>(P);
+      break;
+    default:
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 256>, smem));
+      gemm_kernel<Policy, 256><<<grid, kThreads, smem, st>>>(P);
+      break;
+  }
+  IFD_LAUNCH_CHECK("tc::gemm_kernel");
+  return IFD_OK;
+}
+
+
+}  // namespace tc
+}  // namespace ifd

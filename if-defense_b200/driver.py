@@ -32,8 +32,10 @@ class Args:
     threshold = 0.2       # cfg['test']['threshold']
     input_npoint = 600    # cfg['data']['pointcloud_n'] (300 for ONet)
     device_preprocess = True   # SOR selection + preprocess_pc + init gather on the device (same bits as the numpy path)
-    encoder_chunk = 8     # sharded path only: clouds per encoder call; chunks are aligned to the job's cloud indices and
-                          # padded to full size, so that a cloud's planes do not depend on the number of ranks
+    encoder_chunk = 0     # sharded path only: 0 = encode a slice in one call (the library's own encoder kernels do not depend on
+                          # the batch a cloud arrives in); n > 0 = chunks of exactly n clouds aligned to the job's cloud
+                          # indices and padded to full size, for encoders that run on torch / cuDNN (their results were
+                          # measured to depend on a sample's position in the batch)
 
     def __init__(self, **over):
         for k, v in over.items():
@@ -194,7 +196,10 @@ class Defender:
         (positions outside this slice are filled with a copy of one of its clouds).  cuDNN / cuBLAS kernels are deterministic
         functions of (shape, position in the batch, the sample's own data) -- measured: at some batch sizes the position
         matters in the last bit -- so a cloud's planes do not depend on where the slice boundaries fall."""
-        step = self.args.encoder_chunk or 1
+        if not self.args.encoder_chunk:
+            with torch.no_grad():
+                return self.model.encode_inputs(sel)
+        step = self.args.encoder_chunk
         n = sel.shape[0]
         out = None
         with torch.no_grad():

@@ -39,6 +39,43 @@ class ResnetBlockFC(nn.Module):
         return (x if self.shortcut is None else self.shortcut(x)) + dx
 
 
+class _PackedCache:
+    """Weight images of a module for the tensor-core GEMM engine (tc.py), rebuilt when a parameter changes or moves."""
+
+    def __init__(self):
+        self.key, self.val = None, None
+
+    def get(self, module, build):
+        ps = list(module.parameters())
+        key = tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
+        if self.key != key:
+            with torch.no_grad():
+                self.val = build()
+            self.key = key
+        return self.val
+
+
+def _pack_resblock(tc, blk, seg_widths):
+    """ResnetBlockFC on the GEMM engine = two launches: h = fc_0(relu(x)); out = [fc_1 | shortcut] . [relu(h) | x] + b1
+    (the shortcut GEMM rides in the K dimension of the second one; x itself may be a concatenation)."""
+    size_h = blk.fc_0.out_features
+    w1 = blk.fc_1.weight if blk.shortcut is None else torch.cat([blk.fc_1.weight, blk.shortcut.weight], dim=1)
+    segs1 = [size_h] + (list(seg_widths) if blk.shortcut is not None else [])
+    return {"w0": tc.pack(blk.fc_0.weight, seg_widths), "b0": blk.fc_0.bias.detach().float().contiguous(),
+            "w1": tc.pack(w1, segs1), "b1": blk.fc_1.bias.detach().float().contiguous(),
+            "size_h": size_h, "out": blk.fc_1.out_features, "shortcut": blk.shortcut is not None}
+
+
+def _run_resblock(tc, pk, segs):
+    """segs: [(tensor [M, ld], width[, group])] -- the block's input x as K segments (no ReLU flags: set here)."""
+    h = tc.linear([(s[0], s[1], True) + tuple(s[2:]) for s in segs], pk["w0"], pk["size_h"], bias=pk["b0"])
+    if pk["shortcut"]:
+        return tc.linear([(h, pk["size_h"], True)] + [(s[0], s[1], False) + tuple(s[2:]) for s in segs], pk["w1"], pk["out"], bias=pk["b1"])
+    if len(segs) != 1:
+        raise RuntimeError("identity shortcut needs a single input segment")
+    return tc.linear([(h, pk["size_h"], True)], pk["w1"], pk["out"], bias=pk["b1"], resid=segs[0][0])
+
+
 # ------------------------------------------------------------------------------------------ ConvONet
 
 
@@ -87,6 +124,48 @@ class UNet(nn.Module):
             if isinstance(m, nn.Conv2d):
                 nn.init.xavier_normal_(m.weight)
                 nn.init.constant_(m.bias, 0)
+
+    def _pack(self, tc):
+        def conv(c):                                                      # [Cout, Cin, 3, 3] -> [Cout, 9 Cin], k = (ky 3 + kx) Cin + ci
+            return tc.pack(c.weight.permute(0, 2, 3, 1).reshape(c.out_channels, -1)), c.bias.detach().float().contiguous()
+
+        def convt(c):                                                     # [Cin, Cout, 2, 2] -> [4 Cout, Cin], n = (i 2 + j) Cout + co
+            return tc.pack(c.weight.permute(2, 3, 1, 0).reshape(4 * c.out_channels, c.in_channels)), c.bias.detach().float().contiguous()
+
+        return {"down": [(conv(d.conv1), conv(d.conv2)) for d in self.down_convs],
+                "up": [(convt(u.upconv), conv(u.conv1), conv(u.conv2)) for u in self.up_convs],
+                "final": (tc.pack(self.conv_final.weight.reshape(self.conv_final.out_channels, -1)),
+                          self.conv_final.bias.detach().float().contiguous())}
+
+    def forward_cl(self, x, out=None):
+        """The forward on channels-last tensors [B, H, W, C] with every convolution on the tcgen05 GEMM engine (csrc/tc_ops.cu):
+        the 2x2 max-pool is taken on read by the next convolution, the skip concatenation is two K segments of the first
+        up-convolution's GEMM, the transposed convolution is a GEMM with a pixel-shuffle epilogue.  -> [B, H, W, num_classes]
+        (written into `out` when given).  unet.py:225-239."""
+        from . import tc
+        if not hasattr(self, "_tc_cache"):
+            self._tc_cache = _PackedCache()
+        pk = self._tc_cache.get(self, lambda: self._pack(tc))
+        skips = []
+        for i, d in enumerate(self.down_convs):
+            (w1, b1), (w2, b2) = pk["down"][i]
+            x = tc.conv3x3(x, w1, b1, d.conv1.out_channels, pool=i > 0)
+            x = tc.conv3x3(x, w2, b2, d.conv2.out_channels)
+            skips.append(x)
+        for i, u in enumerate(self.up_convs):
+            (wt, bt), (w1, b1), (w2, b2) = pk["up"][i]
+            B, H, W, cin = x.shape
+            cout = u.upconv.out_channels
+            up = tc.linear([(x.view(B * H * W, cin), cin, False)], wt, 4 * cout, bias=bt, shuffle=(cout, H, W))
+            x = tc.conv3x3(up, w1, b1, cout, src1=skips[-(i + 2)])
+            x = tc.conv3x3(x, w2, b2, cout)
+        B, H, W, c = x.shape
+        wf, bf = pk["final"]
+        ncls = self.conv_final.out_channels
+        if out is None:
+            out = torch.empty((B, H, W, ncls), dtype=torch.float32, device=x.device)
+        tc.linear([(x.view(B * H * W, c), c, False)], wf, ncls, bias=bf, out=out.view(B * H * W, ncls))
+        return out
 
     def forward(self, x):
         skips = []
@@ -176,35 +255,66 @@ class LocalPoolPointnet(nn.Module):
         return fea
 
     def _forward_cuda(self, p):
-        """The same forward on the GPU: bins, scatter_max + gather and scatter_mean are the library's kernels
-        (ifd_plane_bins, ifd_scatter_max_gather, ifd_scatter_mean_cl: deterministic); the Linear layers and the U-Net stay
-        torch / cuDNN, fed NCHW (cuDNN's fp32 kernels are ~1.7x faster on it than on channels_last)."""
-        from . import capi
+        """The same forward on the GPU with every operator on the library's own kernels: bins, scatter_max + gather and
+        scatter_mean (ifd_plane_bins, ifd_scatter_max_gather, ifd_scatter_mean_cl: deterministic), the Linear stack and the
+        U-Net on the tcgen05 GEMM engine (tc.py; fp32 semantics through 3xTF32).  The three planes go through the shared U-Net
+        as ONE batch of 3 B images and come out channels-last, the layout the decode kernel gathers from.  Nothing here
+        depends on a cloud's position in the batch (no library picks an algorithm by batch size)."""
+        from . import capi, tc
         capi.require_gpu()
         if list(self.plane_type) != ["xz", "xy", "yz"]:
             raise RuntimeError("the CUDA encoder path is built for plane_type ['xz', 'xy', 'yz']")
         L, st = capi.lib(), capi.stream()
         x = p.detach().float().contiguous()
         B, T, _ = x.shape
-        R, nb = self.reso_plane, self.reso_plane ** 2
+        R, nb, H = self.reso_plane, self.reso_plane ** 2, self.hidden_dim
+        if not hasattr(self, "_tc_cache"):
+            self._tc_cache = _PackedCache()
+
+        def build():
+            return {"pos": (tc.pack(self.fc_pos.weight), self.fc_pos.bias.detach().float().contiguous()),
+                    "blocks": [_pack_resblock(tc, blk, [2 * H] if i == 0 else [H, H]) for i, blk in enumerate(self.blocks)],
+                    "c": (tc.pack(self.fc_c.weight), self.fc_c.bias.detach().float().contiguous())}
+        params = [q for m in (self.fc_pos, self.blocks, self.fc_c) for q in m.parameters()]
+        pk = self._tc_cache.get(_ParamView(params), build)
         bins = torch.empty((3, B, T), dtype=torch.int32, device=x.device)
         capi.check(L.ifd_plane_bins(capi.ptr(x), B, T, R, float(self.padding), capi.ptr(bins), st), "ifd_plane_bins")
-        net = self.blocks[0](self.fc_pos(x))
-        for block in self.blocks[1:]:
-            src = net.contiguous()
-            pooled = torch.empty_like(src)
-            capi.check(L.ifd_scatter_max_gather(capi.ptr(src), capi.ptr(bins), 3, B, T, src.shape[2], nb, capi.ptr(pooled), st),
+        M = B * T
+        net0 = tc.linear([(x.view(M, 3), 3, False)], pk["pos"][0], 2 * H, bias=pk["pos"][1])
+        net = _run_resblock(tc, pk["blocks"][0], [(net0, 2 * H)])
+        for i in range(1, len(self.blocks)):
+            pooled = torch.empty_like(net)
+            capi.check(L.ifd_scatter_max_gather(capi.ptr(net), capi.ptr(bins), 3, B, T, H, nb, capi.ptr(pooled), st),
                        "ifd_scatter_max_gather")
-            net = block(torch.cat([src, pooled], dim=2))
-        c = self.fc_c(net).contiguous()
-        fea = {}
-        for i, pl in enumerate(self.plane_type):
-            out = torch.empty((B, nb, self.c_dim), dtype=torch.float32, device=x.device)
-            capi.check(L.ifd_scatter_mean_cl(capi.ptr(c), capi.ptr(bins[i]), B, T, self.c_dim, nb, capi.ptr(out), st),
+            net = _run_resblock(tc, pk["blocks"][i], [(net, H), (pooled, H)])
+        c = tc.linear([(net, H, False)], pk["c"][0], self.c_dim, bias=pk["c"][1])
+        planes_in = torch.empty((3, B, R, R, self.c_dim), dtype=torch.float32, device=x.device)
+        for i in range(3):
+            capi.check(L.ifd_scatter_mean_cl(capi.ptr(c), capi.ptr(bins[i]), B, T, self.c_dim, nb, capi.ptr(planes_in[i]), st),
                        "ifd_scatter_mean_cl")
-            plane = out.view(B, R, R, self.c_dim).permute(0, 3, 1, 2)        # [B,C,R,R], channels_last memory
-            fea[pl] = self.unet(plane.contiguous()) if self.unet is not None else plane
+        if self.unet is not None:
+            planes = self.unet.forward_cl(planes_in.view(3 * B, R, R, self.c_dim)).view(3, B, R, R, self.c_dim)
+        else:
+            planes = planes_in
+        fea = PlaneFeatures((pl, planes[i].permute(0, 3, 1, 2)) for i, pl in enumerate(self.plane_type))   # [B,C,R,R] views
+        fea.channels_last = planes                                        # the kernel layout [3,B,R,R,C], no copy needed
         return fea
+
+
+class _ParamView:
+    """Just enough of nn.Module for _PackedCache: a fixed list of parameters."""
+
+    def __init__(self, params):
+        self._params = list(params)
+
+    def parameters(self):
+        return self._params
+
+
+class PlaneFeatures(dict):
+    """encode_inputs' dict {'xz', 'xy', 'yz': [B, C, R, R]} whose three tensors are views of one channels-last buffer
+    `channels_last` [3, B, R, R, C] -- what the decode kernels read (convonet.planes_to_channels_last takes it as is)."""
+    channels_last = None
 
 
 class LocalDecoder(nn.Module):
@@ -265,11 +375,40 @@ class ResnetPointnet(nn.Module):
         self.fc_c = nn.Linear(hidden_dim, c_dim)
 
     def forward(self, p):
+        if p.is_cuda:
+            return self._forward_cuda(p)
         net = self.block_0(self.fc_pos(p))
         for i in range(1, 5):
             pooled = net.max(dim=1, keepdim=True)[0].expand(net.size())
             net = getattr(self, "block_%d" % i)(torch.cat([net, pooled], dim=2))
         return self.fc_c(F.relu(net.max(dim=1)[0]))
+
+    def _forward_cuda(self, p):
+        """ResnetPointnet.forward (ONet/im2mesh/encoder/pointnet.py:85-113) on the library's kernels: every Linear layer on
+        the tcgen05 GEMM engine (tc.py, fp32 semantics), the global max-pool as ifd_group_max; the pooled vector is read as
+        a per-cloud K segment instead of being expanded and concatenated."""
+        from . import capi, tc
+        capi.require_gpu()
+        x = p.detach().float().contiguous()
+        B, T, _ = x.shape
+        blocks = [getattr(self, "block_%d" % i) for i in range(5)]
+        H = blocks[0].fc_1.out_features
+        if not hasattr(self, "_tc_cache"):
+            self._tc_cache = _PackedCache()
+
+        def build():
+            return {"pos": (tc.pack(self.fc_pos.weight), self.fc_pos.bias.detach().float().contiguous()),
+                    "blocks": [_pack_resblock(tc, blk, [2 * H] if i == 0 else [H, H]) for i, blk in enumerate(blocks)],
+                    "c": (tc.pack(self.fc_c.weight), self.fc_c.bias.detach().float().contiguous())}
+        pk = self._tc_cache.get(self, build)
+        M = B * T
+        net0 = tc.linear([(x.view(M, 3), 3, False)], pk["pos"][0], 2 * H, bias=pk["pos"][1])
+        net = _run_resblock(tc, pk["blocks"][0], [(net0, 2 * H)])
+        for i in range(1, 5):
+            pooled = tc.group_max(net, B, T)                              # [B, H]
+            net = _run_resblock(tc, pk["blocks"][i], [(net, H), (pooled, H, T)])
+        pooled = tc.group_max(net, B, T)
+        return tc.linear([(pooled, H, True)], pk["c"][0], self.fc_c.out_features, bias=pk["c"][1])
 
 
 class CBatchNorm1d(nn.Module):

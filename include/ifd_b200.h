@@ -159,6 +159,54 @@ int ifd_scatter_mean_cl(const float* src, const int32_t* bins, int B, int T, int
                         ifd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense layers of the encoders on the tensor cores (tcgen05, 3xTF32 = fp32 semantics; csrc/tc_gemm.cuh)
+ *
+ * One warp-specialised GEMM engine  Out[m][n] = epilogue(sum_k A(m,k) W[n][k])  serves nn.Linear with fused ReLU / bias /
+ * residual (ResnetBlockFC: ConvONet/src/layers.py:39-48; fc_pos, fc_c: ConvONet/src/encoder/pointnet.py:41-45,
+ * ONet/im2mesh/encoder/pointnet.py:85-113), nn.Conv2d(3x3, padding 1) on channels-last tensors, nn.ConvTranspose2d(2, stride 2)
+ * and the 1x1 convolution of the U-Net (ConvONet/src/encoder/unet.py:117-239).  Weights are packed once per model into
+ * the engine's image format with ifd_tc_pack.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Size in floats of the packed image of W [N][sum(seg_widths)] (every K segment is padded to a multiple of 32). */
+size_t ifd_tc_packed_floats(int N, const int* seg_widths, int n_seg);
+/* W: device, row-major [N][sum(seg_widths)] with row stride ldw -> out (device, ifd_tc_packed_floats floats, 16-byte aligned). */
+int ifd_tc_pack(const float* W, int N, const int* seg_widths, int n_seg, int ldw, float* out, ifd_stream_t stream);
+
+typedef struct ifd_tc_linear_args {
+  int32_t M, N;              /* rows, output features */
+  int32_t n_seg;             /* 1..3 input segments, concatenated along K in this order (torch.cat(..., dim = -1) on read) */
+  const float* a_ptr[3];     /* [M][a_ld] row-major device pointers */
+  int32_t a_ld[3];           /* row strides in floats */
+  int32_t a_width[3];        /* columns used of each segment (= the widths given to ifd_tc_pack) */
+  int32_t a_relu[3];         /* 1: the segment passes through ReLU on read (fc(relu(x))) */
+  int32_t a_group[3];        /* > 0: the segment holds one row per group of a_group consecutive rows (a per-cloud vector
+                                expanded over the cloud's points on read); 0: one row per output row */
+  const float* wimg;         /* packed weights */
+  const float* bias;         /* [N] or NULL */
+  const float* resid;        /* [M][ld_resid] added to the result, or NULL */
+  int32_t ld_resid;
+  int32_t relu_out;          /* 1: ReLU on the result */
+  float* out;                /* [M][ld_out] */
+  int32_t ld_out;
+  /* ConvTranspose2d(kernel 2, stride 2) epilogue: rows are the B*H*W input pixels (channels-last), N = 4 * cout with
+   * n = (i * 2 + j) * cout + co, out is [B][2H][2W][cout] channels-last, bias is [cout].  0 = plain Linear. */
+  int32_t shuffle_cout, shuffle_H, shuffle_W;
+} ifd_tc_linear_args;
+int ifd_tc_linear(const ifd_tc_linear_args* args, ifd_stream_t stream);
+
+/* out[g][c] = max_t x[g * T + t][c]: the global max-pool of ResnetPointnet (ONet/im2mesh/encoder/pointnet.py:103,110). */
+int ifd_group_max(const float* x, int groups, int T, int C, float* out, ifd_stream_t stream);
+
+/* nn.Conv2d(C0 + C1 -> Cout, 3, padding = 1) (+ ReLU) on channels-last device tensors.  Input = the channel concatenation
+ * [src0 | src1] (torch.cat((from_up, from_down), 1), unet.py:187; src1 = NULL, C1 = 0 for a single input) of
+ * [B][H][W][C] tensors; with pool != 0 the input is F.max_pool2d(src0, 2, 2) of a [B][2H][2W][C0] tensor, taken on read
+ * (unet.py:151).  wimg = ifd_tc_pack of the weight as [Cout][9 * (C0 + C1)] with k = (ky * 3 + kx) * (C0 + C1) + ci.
+ * Channel counts are multiples of 32.  out [B][H][W][Cout]. */
+int ifd_tc_conv3x3(const float* src0, int C0, const float* src1, int C1, int B, int H, int W, int pool, const float* wimg,
+                   const float* bias, int relu_out, int Cout, float* out, ifd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * The restoration loop
  * ---------------------------------------------------------------------------------------------- */
 

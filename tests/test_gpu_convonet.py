@@ -331,3 +331,53 @@ def test_large_batch_runs_as_side_by_side_parts_with_the_same_bits(conv, dec):
     for n in (True, 4, 2):
         got = convonet.Restorer(dec, side_by_side=n).optimize_points(p0, None, c, rep_weight=500., iterations=8)
         assert np.array_equal(got, one), n
+
+
+def test_graph_replay_equals_direct_launches(conv, dec, planes):
+    """The production loop replays one cached CUDA graph whose kernels read their buffers from a device-side job record
+    (ifd_convonet_opt: fresh run, default kernels, no diagnostics).  Same bits as the ~400 direct launches; the graph is
+    reused for other buffers, other streams get their own record."""
+    L = capi.lib()
+    L.ifd_launch_count(1)
+    a, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1)
+    n_graph = L.ifd_launch_count(1)
+    L.ifd_test_hook(3, 0)
+    try:
+        b, _ = run_opt(dec, planes, conv["p0"], 20, normalize=1)
+        n_direct = L.ifd_launch_count(1)
+    finally:
+        L.ifd_test_hook(3, 1)
+    assert np.array_equal(a, b)
+    assert n_graph == n_direct + 1                       # the same kernels + the job-record write
+    assert np.abs(a - conv["final_20_normalized"]).max() < 1e-4
+    # replays on other buffers (new xyz / workspace allocations, a copy of the planes) and on another stream
+    pl2 = planes.clone()
+    c, _ = run_opt(dec, pl2, conv["p0"].copy(), 20, normalize=1)
+    assert np.array_equal(a, c)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        d, _ = run_opt(dec, pl2, conv["p0"], 20, normalize=1)
+    assert np.array_equal(a, d)
+    # two replays back to back on one stream, every buffer of both alive at the same time (distinct addresses: a kernel that
+    # kept a capture-time pointer instead of the record's would restore the wrong cloud -- nvcc 12.9 once compiled
+    # cloud_step_kernel that way, and single replays on recycled allocations could not see it)
+    C, H, nb = dec.dims
+    P = capi.default_params(n_steps=20, B_ref=2, normalize_out=1)
+    with torch.cuda.stream(side):
+        xa, xb = dev(conv["p0"]).clone(), dev(conv["p0"] * 0.97).clone()
+        wsb = L.ifd_convonet_opt_workspace_bytes(2, 256)
+        wsa, wsb_t = torch.empty(wsb, dtype=torch.uint8, device="cuda"), torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        for x, ws in ((xa, wsa), (xb, wsb_t)):
+            capi.check(L.ifd_convonet_opt(capi.ptr(pl2), capi.ptr(dec.blob), capi.ptr(x), None, None, 2, 256, 64, C, H, nb,
+                                          ctypes.byref(P), None, capi.ptr(ws), wsb, side.cuda_stream))
+        side.synchronize()
+    assert np.array_equal(xa.cpu().numpy(), a)
+    wb, _ = run_opt(dec, planes, conv["p0"] * 0.97, 20, normalize=1)
+    assert np.array_equal(xb.cpu().numpy(), wb)
+    e, _ = run_opt(dec, planes, conv["p0"], 7)           # another step count: another graph
+    L.ifd_test_hook(3, 0)
+    try:
+        f, _ = run_opt(dec, planes, conv["p0"], 7)
+    finally:
+        L.ifd_test_hook(3, 1)
+    assert np.array_equal(e, f)
