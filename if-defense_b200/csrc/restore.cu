@@ -983,9 +983,10 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
                  : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
 }
 
-namespace ifd { void onet_set_engine(int on); }
+namespace ifd { void onet_set_engine(int on); void tc_set_cluster(int n); }
 extern "C" void ifd_test_hook(int key, int value) {
   if (key == 5) onet_set_engine(value);
+  if (key == 6) tc_set_cluster(value);
   if (key == 1) g_inbox_cap = value < 0 ? 0 : (value > kCsInbox ? kCsInbox : value);
   if (key == 2) g_lanes = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);
   if (key == 3) g_use_graph = value ? 1 : 0;

@@ -13,12 +13,20 @@
 //              its row (a global row of a matrix, a 3x3 tap of a channels-last image, a pooled pixel, ...), splits them into
 //              TF32 hi / lo and writes the two K-major no-swizzle UMMA images of the chunk into a pipeline stage;
 //   warp 9     B loader: one thread, ONE TMA bulk copy (cp.async.bulk) per chunk of the pre-packed weight image
-//              [NT x 32] hi | lo, completion counted in bytes on the stage's mbarrier;
+//              [NT x 32] hi | lo, completion counted in bytes on the stage's mbarrier; in a cluster every CTA fetches 1 / CL
+//              of the chunk and multicasts it to all CTAs (L2 -> SM weight traffic / CL);
 //   warp 8     MMA issuer: one thread, 12 tcgen05.mma (M = 128, N = NT, K = 8) per chunk, both operands from shared memory,
 //              tcgen05.commit releases the stage; the accumulator of a tile lives in one of TWO TMEM stages;
 //   warps 4-7  epilogue: tcgen05.ld the finished accumulator (thread = row), hand 32 columns at a time to the Policy
 //              (bias, ReLU, residual, pixel shuffle, ...), while the MMA warp is already on the next tile.
 // Stage hand-off is mbarrier-only (no __syncthreads in the main loop).
+//
+// Measured and kept out (round 2, ncu on the 256-wide ONet layer: 93 us, LSU wavefronts 71 % of peak, tensor pipe 31 %): the
+// thread-per-row float4 accesses of producers and epilogue cost 32 L1 wavefronts per instruction.  A coalesced mapping (eight
+// lanes per 128-byte row piece, bank-rotated image stride, epilogue transposed through an XOR-swizzled scratch) cut the LSU
+// load to 13 % and was still SLOWER (ONet step 2.1 -> 3.0 ms, U-Net 12.5 -> 18.4 ms): eight address computations per chunk
+// and lane instead of one, and a latency chain per 32 columns in the epilogue.  The way out is TMA tensor loads of the raw A
+// tile and TMA stores of the output tile (no LSU traffic at all), not another lane mapping.
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -77,7 +85,34 @@ static __global__ void pack_weights_kernel(const float* __restrict__ W, int N, i
 //   static __device__ Row row_begin(const Params&, int row);               row < M is NOT guaranteed (check yourself)
 //   static __device__ void load(const Params&, const Row&, int kc, float (&x)[32]);        the 32 A values of chunk kc
 //   static __device__ void store(const Params&, const Row&, int col0, const float (&y)[32]); columns col0 .. col0 + 31
-template <class Policy, int NT>
+// ---- thread-block clusters: the CTAs of a cluster work on different row tiles of the SAME column tile in lock step, so a
+// weight chunk is fetched from L2 once per cluster: every CTA loads 1 / CL of it and TMA-multicasts that piece into the
+// same stage of all CL shared memories (each CTA's mbarrier counts the bytes of all pieces); a stage is reused when the
+// MMAs of ALL CTAs have read it (tcgen05.commit multicast onto every CTA's `empty` barrier).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          umma::smem_u32(dst_smem)),
+      "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   umma::smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+template <class Policy, int NT, int CL>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy::Params P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int S = stages_for(NT);
@@ -85,22 +120,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
   constexpr bool kSplit = NT <= 128;                        // second accumulator for the small cross terms (see the header)
   constexpr uint32_t kAcc = kSplit ? 2 * NT : NT;           // TMEM columns per accumulator stage (main | small)
   constexpr uint32_t kTmemCols = 2 * kAcc;                  // 64 .. 512, a power of two
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
   unsigned char* a_st = smem_raw;                           // [S][32 KB]
   unsigned char* b_st = smem_raw + (size_t)S * kAStageBytes;    // [S][kBStage]
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_st + (size_t)S * kBStage);
   uint64_t* full_a = bars;                 // [S] 128 producer arrivals
   uint64_t* full_b = bars + S;             // [S] 1 arrival + tx bytes
-  uint64_t* empty = bars + 2 * S;          // [S] tcgen05.commit
+  uint64_t* empty = bars + 2 * S;          // [S] tcgen05.commit of every CTA of the cluster
   uint64_t* acc_full = bars + 3 * S;       // [2] tcgen05.commit after the last chunk of a tile
   uint64_t* acc_empty = bars + 3 * S + 2;  // [2] 128 epilogue arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
       umma::mbar_init(&full_a[s], 128);
       umma::mbar_init(&full_b[s], 1);
-      umma::mbar_init(&empty[s], 1);
+      umma::mbar_init(&empty[s], CL);
     }
     for (int s = 0; s < 2; ++s) {
       umma::mbar_init(&acc_full[s], 1);
@@ -111,25 +148,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
   if (warp == 8) umma::tmem_alloc(tmem_slot, kTmemCols);
   umma::fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // every CTA's barriers exist before a peer multicasts into them
   umma::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
 
+  // Tiles: cluster tile ct -> column tile ct % n_tiles_n, row tiles (ct / n_tiles_n) * CL + rank.  Every CTA of a cluster runs
+  // the same number of rounds; a row tile beyond M is a dummy (the policies load zeros and store nothing for rows >= M).
   const int m_tiles = (P.M + 127) / 128;
-  const int n_tiles = m_tiles * P.n_tiles_n;
+  const int n_ct = ((m_tiles + CL - 1) / CL) * P.n_tiles_n;
+  const int n_clusters = gridDim.x / CL, cid = blockIdx.x / CL;
   const int n_chunks = P.n_chunks;
+  auto row_tile = [&](int ct) { return (ct / P.n_tiles_n) * CL + rank; };
 
   if (warp < 4) {
     // ------------------------------------------------------------------ A producers
     const int r = threadIdx.x;                      // row of the tile
     uint32_t it = 0;                                // global chunk counter -> stage / phase
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int mt = t / P.n_tiles_n;
-      const typename Policy::Row row = Policy::row_begin(P, mt * 128 + r);
+    // The values of chunk kc + 1 (of the next tile after the last chunk) are fetched BEFORE chunk kc is split and stored: one
+    // producer warp per scheduler cannot hide a global-load latency any other way.
+    float xn[32];
+    typename Policy::Row row = Policy::row_begin(P, row_tile(cid) * 128 + r);
+    if (cid < n_ct) Policy::load(P, row, 0, xn);
+    for (int ct = cid; ct < n_ct; ct += n_clusters) {
       for (int kc = 0; kc < n_chunks; ++kc, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         float x[32];
-        Policy::load(P, row, kc, x);                // global loads first: they fly while we wait for the stage
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x[k] = xn[k];
+        if (kc + 1 < n_chunks) {
+          Policy::load(P, row, kc + 1, xn);
+        } else if (ct + n_clusters < n_ct) {
+          row = Policy::row_begin(P, row_tile(ct + n_clusters) * 128 + r);
+          Policy::load(P, row, 0, xn);
+        }
         umma::mbar_wait(&empty[s], ph ^ 1);
         unsigned char* hi = a_st + (size_t)s * kAStageBytes + (r >> 3) * 128 + (r & 7) * 16;
         unsigned char* lo = hi + 128 * kChunk * 4;
@@ -151,10 +203,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
     // ------------------------------------------------------------------ epilogue (warp - 4 = TMEM lane quarter)
     const int r = threadIdx.x - 128;
     uint32_t tl = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
-      const int mt = t / P.n_tiles_n, nt = t % P.n_tiles_n;
+    for (int ct = cid; ct < n_ct; ct += n_clusters, ++tl) {
+      const int nt = ct % P.n_tiles_n;
       const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      const typename Policy::Row row = Policy::row_begin(P, mt * 128 + r);
+      const typename Policy::Row row = Policy::row_begin(P, row_tile(ct) * 128 + r);
       umma::mbar_wait(&acc_full[as], aph);
       umma::fence_after_sync();
       const uint32_t taddr = tmem + as * kAcc + ((uint32_t)((warp - 4) * 32) << 16);
@@ -180,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
     if (lane == 0) {
       constexpr uint32_t idesc = umma::idesc_tf32(128, NT);
       uint32_t it = 0, tl = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tl) {
+      for (int ct = cid; ct < n_ct; ct += n_clusters, ++tl) {
         const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
         umma::mbar_wait(&acc_empty[as], aph ^ 1);   // the epilogue drained this accumulator stage (two tiles ago)
         umma::fence_after_sync();
@@ -205,7 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
                           umma::smem_desc_kmajor(b_s + q * (NT * 32), NT * 16, 128), idesc, (kc | later) ? 1u : 0u);
             }
           }
-          umma::commit(&empty[s]);                  // the stage is free once these MMAs have read it
+          // the stage is free once these MMAs have read it -- in EVERY CTA of the cluster (their loaders write into it)
+          if (CL > 1) commit_multicast(&empty[s], kMask);
+          else umma::commit(&empty[s]);
         }
         umma::commit(&acc_full[as]);                // accumulator complete -> epilogue
       }
@@ -214,16 +268,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
   } else {
     // ------------------------------------------------------------------ B loader (TMA bulk copies)
     if (lane == 0) {
+      constexpr uint32_t kPiece = kBStage / CL;
       uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int nt = t % P.n_tiles_n;
-        const float* src = P.wimg + (size_t)nt * n_chunks * (2 * NT * kChunk);
+      for (int ct = cid; ct < n_ct; ct += n_clusters) {
+        const int nt = ct % P.n_tiles_n;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg + (size_t)nt * n_chunks * (2 * NT * kChunk));
         for (int kc = 0; kc < n_chunks; ++kc, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           umma::mbar_wait(&empty[s], ph ^ 1);
-          umma::mbar_arrive_expect_tx(&full_b[s], kBStage);
-          umma::bulk_g2s(b_st + (size_t)s * kBStage, src + (size_t)kc * (2 * NT * kChunk), kBStage, &full_b[s]);
+          umma::mbar_arrive_expect_tx(&full_b[s], kBStage);       // all CL pieces land here, one of them is ours
+          unsigned char* dst = b_st + (size_t)s * kBStage + (size_t)rank * kPiece;
+          const unsigned char* from = src + (size_t)kc * kBStage + (size_t)rank * kPiece;
+          if (CL > 1) bulk_g2s_multicast(dst, from, kPiece, &full_b[s], kMask);
+          else umma::bulk_g2s(dst, from, kPiece, &full_b[s]);
         }
       }
     }
@@ -231,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
   }
   umma::fence_before_sync();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into its shared memory
   if (warp == 8) umma::tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -250,34 +309,63 @@ inline int sm_count() {
   return n;
 }
 
-template <class Policy>
-int launch(const typename Policy::Params& P, int NT, cudaStream_t st) {
-  const int tiles = ((P.M + 127) / 128) * P.n_tiles_n;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  if (grid <= 0) return IFD_OK;
+inline int g_cluster_size = 2;       // ifd_test_hook(6, n): CTAs per cluster of the GEMM engine (1, 2 or 4)
+
+template <class Policy, int NT, int CL>
+int launch_one(const typename Policy::Params& P, int clusters_wanted, cudaStream_t st) {
   const size_t smem = smem_bytes(NT);
-  switch (NT) {
-    case 32:
-      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 32>, smem));
-      gemm_kernel<Policy, 32><<<grid, kThreads, smem, st>>>(P);
-      break;
-    case 64:
-      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 64>, smem));
-      gemm_kernel<Policy, 64><<<grid, kThreads, smem, st>>>(P);
-      break;
-    case 128:
-      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 128>, smem));
-      gemm_kernel<Policy, 128><<<grid, kThreads, smem, st>>>(P);
-      break;
-    default:
-      IFD_CUDA_TRY(set_max_dyn_smem((const void*)gemm_kernel<Policy, 256>, smem));
-      gemm_kernel<Policy, 256><<<grid, kThreads, smem, st>>>(P);
-      break;
+  const void* fn = (const void*)gemm_kernel<Policy, NT, CL>;
+  IFD_CUDA_TRY(set_max_dyn_smem(fn, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  int max_clusters = sm_count() / CL;
+  if (CL > 1) {                        // how many clusters of this shape the chip holds at once (GPC boundaries), once per kernel
+    static int cached = -1;
+    if (cached < 0) {
+      cfg.gridDim = dim3(sm_count() / CL * CL);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) == cudaSuccess && n > 0) cached = n;
+      else { cudaGetLastError(); cached = max_clusters; }
+    }
+    max_clusters = cached < max_clusters ? cached : max_clusters;
   }
+  const int n = clusters_wanted < max_clusters ? clusters_wanted : max_clusters;
+  cfg.gridDim = dim3(n * CL);
+  IFD_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_kernel<Policy, NT, CL>, P));
   IFD_LAUNCH_CHECK("tc::gemm_kernel");
   return IFD_OK;
 }
 
+template <class Policy, int NT>
+int launch_nt(const typename Policy::Params& P, cudaStream_t st) {
+  const int m_tiles = (P.M + 127) / 128;
+  if (m_tiles <= 0) return IFD_OK;
+  int cl = g_cluster_size;
+  while (cl > 1 && m_tiles < 2 * cl) cl >>= 1;           // tiny problems: no point in padding row tiles
+  const int wanted = ((m_tiles + cl - 1) / cl) * P.n_tiles_n;
+  if (cl >= 4) return launch_one<Policy, NT, 4>(P, wanted, st);
+  if (cl == 2) return launch_one<Policy, NT, 2>(P, wanted, st);
+  return launch_one<Policy, NT, 1>(P, wanted, st);
+}
+
+template <class Policy>
+int launch(const typename Policy::Params& P, int NT, cudaStream_t st) {
+  switch (NT) {
+    case 32: return launch_nt<Policy, 32>(P, st);
+    case 64: return launch_nt<Policy, 64>(P, st);
+    case 128: return launch_nt<Policy, 128>(P, st);
+    default: return launch_nt<Policy, 256>(P, st);
+  }
+}
 
 }  // namespace tc
 }  // namespace ifd

@@ -266,3 +266,7 @@ extern "C" int ifd_group_max(const float* x, int groups, int T, int C, float* ou
   IFD_LAUNCH_CHECK("tc::group_max_kernel");
   return IFD_OK;
 }
+
+namespace ifd {
+void tc_set_cluster(int n) { tc::g_cluster_size = n >= 4 ? 4 : (n >= 2 ? 2 : 1); }
+}  // namespace ifd

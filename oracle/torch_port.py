@@ -161,10 +161,25 @@ def normalize_coordinate(p, padding=0.1, plane="xz"):
     return xy
 
 
-def coordinate2index(x, reso):
-    """common.py:300-315 ('2d')."""
+def normalize_3d_coordinate(p, padding=0.1):
+    """common.py:260-276 (the 'grid' feature volume; in-place clamps as in the 2-D function, constants 10e-4)."""
+    p_nor = p / (1 + padding + 10e-4)
+    p_nor = p_nor + 0.5
+    if p_nor.max() >= 1:
+        p_nor[p_nor >= 1] = 1 - 10e-4
+    if p_nor.min() < 0:
+        p_nor[p_nor < 0] = 0.0
+    return p_nor
+
+
+def coordinate2index(x, reso, coord_type="2d"):
+    """common.py:300-315."""
     x = (x * reso).long()
-    return (x[:, :, 0] + reso * x[:, :, 1])[:, None, :]
+    if coord_type == "2d":
+        index = x[:, :, 0] + reso * x[:, :, 1]
+    else:                                                           # '3d': the grid volume
+        index = x[:, :, 0] + reso * (x[:, :, 1] + reso * x[:, :, 2])
+    return index[:, None, :]
 
 
 def _lin(sd, name, x):
@@ -182,6 +197,11 @@ def _resblock_fc(sd, name, x):
 def convonet_decode(sd, p, c_plane, padding=0.1, n_blocks=5):
     """LocalDecoder.forward (decoder.py:69-95) -> logits [B,K].  c_plane: dict plane -> [B,C,R,R]."""
     c = 0
+    if "grid" in c_plane:                                           # decoder.py:59-67, 72-73: trilinear sample of the volume
+        p_nor = normalize_3d_coordinate(p.clone(), padding=padding)
+        vgrid = 2.0 * p_nor[:, :, None, None].float() - 1.0
+        c = c + F.grid_sample(c_plane["grid"], vgrid, padding_mode="border", align_corners=True,
+                              mode="bilinear").squeeze(-1).squeeze(-1)
     for plane in ("xz", "xy", "yz"):                                # decoder.py:75-80 order
         if plane in c_plane:
             xy = normalize_coordinate(p.clone(), padding=padding, plane=plane)
@@ -285,6 +305,17 @@ def convonet_encode(sd, p, reso=64, padding=0.1, c_dim=32, planes=("xz", "xy", "
         plane = (plane / cnt.clamp_(min=1)).reshape(p.shape[0], c_dim, reso, reso)
         fea[pl] = _unet(sd, plane)
     return fea
+
+
+def convonet_grid_features(c, p, reso=32, padding=0.1):
+    """generate_grid_features up to the 3-D U-Net (encoder/pointnet.py:88-99): scatter_mean of the point features c [B,T,C]
+    into the reso^3 volume -> [B,C,reso,reso,reso] (indexed [z][y][x]: coordinate2index '3d' is x + reso (y + reso z))."""
+    index = coordinate2index(normalize_3d_coordinate(p.clone(), padding=padding), reso, coord_type="3d")
+    src = c.permute(0, 2, 1)
+    idx = index.expand(-1, src.shape[1], -1)
+    vol = src.new_zeros(p.shape[0], src.shape[1], reso ** 3).scatter_add_(-1, idx, src)
+    cnt = torch.zeros_like(vol).scatter_add_(-1, idx, torch.ones_like(src))
+    return (vol / cnt.clamp_(min=1)).reshape(p.shape[0], src.shape[1], reso, reso, reso), index
 
 
 def onet_encode(sd, p):

@@ -6,10 +6,19 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from ifdefense_b200 import models, synth, tc
+from ifdefense_b200 import capi, models, synth, tc
 from oracle import torch_port as tp
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=[1, 2, 4], ids=lambda n: "cluster%d" % n)
+def cluster(request):
+    """CTAs per thread-block cluster of the engine: 1 = no cluster, 2 / 4 = weight chunks TMA-multicast across the cluster."""
+    L = capi.lib()
+    L.ifd_test_hook(6, request.param)
+    yield request.param
+    L.ifd_test_hook(6, 2)
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -23,7 +32,7 @@ def rel_err(got, want, scale):
 
 @pytest.mark.parametrize("M,K,N", [(1, 32, 32), (77, 64, 32), (128, 96, 40), (1000, 3, 64), (4099, 256, 256), (300, 1024, 512),
                                    (513, 70, 100), (20000, 64, 32)])
-def test_linear_vs_float64(M, K, N):
+def test_linear_vs_float64(M, K, N, cluster):
     x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
     got = tc.linear([(x, K, False)], tc.pack(w), N, bias=b)
     want = x.double() @ w.double().T + b.double()
@@ -59,7 +68,7 @@ def test_linear_fused_relu_residual_segments_groups():
 
 @pytest.mark.parametrize("B,H,W,C0,C1,Cout,pool", [(2, 8, 8, 32, 0, 32, False), (3, 16, 16, 64, 64, 64, False), (2, 8, 8, 32, 0, 64, True),
                                                    (1, 64, 64, 32, 0, 32, False), (5, 8, 8, 256, 0, 256, False), (2, 16, 16, 128, 128, 128, False)])
-def test_conv3x3_vs_float64(B, H, W, C0, C1, Cout, pool):
+def test_conv3x3_vs_float64(B, H, W, C0, C1, Cout, pool, cluster):
     Hs, Ws = (2 * H, 2 * W) if pool else (H, W)
     a = rnd(B, Hs, Ws, C0, seed=1)
     b = rnd(B, H, W, C1, seed=2) if C1 else None
@@ -79,7 +88,7 @@ def test_conv3x3_vs_float64(B, H, W, C0, C1, Cout, pool):
     assert err < 2e-6
 
 
-def test_convtranspose_and_unet_vs_torch():
+def test_convtranspose_and_unet_vs_torch(cluster):
     cin, cout, B, H, W = 64, 32, 3, 8, 8
     x = rnd(B, H, W, cin, seed=1)
     w, bias = rnd(cin, cout, 2, 2, seed=2, scale=0.1), rnd(cout, seed=3)
