@@ -59,6 +59,11 @@ SIGNATURES = {
     "ifd_plane_bins": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
     "ifd_scatter_max_gather": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "ifd_scatter_mean_cl": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "ifd_grid_bins": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
+    "ifd_convonet_grid_decode_fwd": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
+    "ifd_convonet_grid_decode_bwd": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _vp, _vp]),
+    "ifd_convonet_grid_opt": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                       ctypes.POINTER(OptParams), _vp, _vp, _c_sz, _vp]),
     "ifd_tc_packed_floats": (_c_sz, [_c_int, ctypes.POINTER(ctypes.c_int), _c_int]),
     "ifd_tc_pack": (_c_int, [_vp, _c_int, ctypes.POINTER(ctypes.c_int), _c_int, _c_int, _vp, _vp]),
     "ifd_tc_linear": (_c_int, [ctypes.POINTER(TcLinearArgs), _vp]),

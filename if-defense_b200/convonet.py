@@ -41,6 +41,43 @@ def planes_to_channels_last(c):
     return out
 
 
+def volume_to_channels_last(vol):
+    """'grid' feature volume [B,C,R,R,R] (what the reference's generate_grid_features returns, indexed [z][y][x]) -> the
+    kernel layout [B,R,R,R,C]; a 5-D channels_last_3d tensor is taken as it is."""
+    if vol.dim() != 5:
+        raise RuntimeError("the grid feature volume must be [B,C,R,R,R]")
+    return vol.detach().float().permute(0, 2, 3, 4, 1).contiguous()
+
+
+class _GridDecodeFn(torch.autograd.Function):
+    """generator.model.decode(p, {'grid': volume}).logits, differentiable w.r.t. p (decoder.py:59-67,72-73)."""
+
+    @staticmethod
+    def forward(ctx, p, vol_cl, wblob, dims, padding):
+        capi.require_gpu()
+        x = p.detach().float().contiguous()
+        B, K, _ = x.shape
+        C, H, nb = dims
+        logits = torch.empty((B, K), dtype=torch.float32, device=x.device)
+        capi.check(capi.lib().ifd_convonet_grid_decode_fwd(capi.ptr(vol_cl), capi.ptr(wblob), capi.ptr(x), B, K, vol_cl.shape[1], C, H,
+                                                           nb, padding, capi.ptr(logits), capi.stream()), "ifd_convonet_grid_decode_fwd")
+        ctx.save_for_backward(x, vol_cl, wblob)
+        ctx.dims, ctx.padding = dims, padding
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        x, vol_cl, wblob = ctx.saved_tensors
+        B, K, _ = x.shape
+        C, H, nb = ctx.dims
+        g = grad_logits.detach().float().contiguous()
+        out = torch.empty_like(x)
+        capi.check(capi.lib().ifd_convonet_grid_decode_bwd(capi.ptr(vol_cl), capi.ptr(wblob), capi.ptr(x), capi.ptr(g), B, K,
+                                                           vol_cl.shape[1], C, H, nb, ctx.padding, capi.ptr(out), capi.stream()),
+                   "ifd_convonet_grid_decode_bwd")
+        return out, None, None, None, None
+
+
 class _DecodeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p, planes_cl, wblob, dims, padding):
@@ -85,6 +122,11 @@ class ConvONetDecoder:
         self.blob = torch.from_numpy(blob).to(self.device) if self.device.type == "cuda" else None
 
     def decode(self, p, c, **kwargs):
+        if isinstance(c, dict) and "grid" in c:
+            if len(c) != 1:
+                raise RuntimeError("a feature volume combined with planes is not supported (no reference config does it)")
+            logits = _GridDecodeFn.apply(p, volume_to_channels_last(c["grid"]), self.blob, self.dims, self.padding)
+            return dist.Bernoulli(logits=logits)
         planes = planes_to_channels_last(c)
         logits = _DecodeFn.apply(p, planes, self.blob, self.dims, self.padding)
         return dist.Bernoulli(logits=logits)
@@ -135,6 +177,8 @@ class Restorer:
         capi.require_gpu()
         x = opt_points.detach().float().cuda().contiguous().clone()
         B, K, _ = x.shape
+        if isinstance(c, dict) and "grid" in c:
+            return self._optimize_points_grid(x, c, rep_weight, iterations, printing, B if B_ref is None else B_ref, return_tensor)
         planes = planes_to_channels_last(c)
         C, H, nb = self.decoder.dims
         R = planes.shape[2]
@@ -165,6 +209,25 @@ class Restorer:
         if return_tensor:
             return x
         return x.cpu().numpy()
+
+    def _optimize_points_grid(self, x, c, rep_weight, iterations, printing, B_ref, return_tensor):
+        """The loop with the 'grid' decoder (c = {'grid': [B,C,R,R,R]}): ifd_convonet_grid_opt."""
+        if len(c) != 1:
+            raise RuntimeError("a feature volume combined with planes is not supported (no reference config does it)")
+        vol = volume_to_channels_last(c["grid"])
+        B, K, _ = x.shape
+        C, H, nb = self.decoder.dims
+        L = capi.lib()
+        P = self.params(B_ref, rep_weight, iterations, want_stats=printing)
+        ws_bytes = L.ifd_convonet_opt_workspace_bytes(B, K)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        stats = torch.zeros((iterations // 100 + 1, 4), dtype=torch.float64, device=x.device) if printing else None
+        capi.check(L.ifd_convonet_grid_opt(capi.ptr(vol), capi.ptr(self.decoder.blob), capi.ptr(x), None, None, B, K, vol.shape[1], C, H,
+                                           nb, ctypes.byref(P), capi.ptr(stats), capi.ptr(ws), ws_bytes, capi.stream()),
+                   "ifd_convonet_grid_opt")
+        if printing:
+            self.last_stats = stats.cpu().numpy()
+        return x if return_tensor else x.cpu().numpy()
 
     def optimize_points_host(self, opt_points_np, planes_nchw_np, rep_weight=500., iterations=200, B_ref=None):
         """End-to-end seam with HOST buffers (numpy in, numpy out): H2D, layout conversion, loop, D2H inside

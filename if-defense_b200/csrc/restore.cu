@@ -18,6 +18,7 @@
 #include "cloud_step.cuh"
 #include "decode_v3.cuh"
 #include "decode_v4.cuh"
+#include "grid_point.cuh"
 #include "topk.cuh"
 
 namespace ifd {
@@ -39,6 +40,7 @@ struct DecodeArgs {
   int B, K, R, n_blocks, wtotal4;
   float denom, target, ginv;
   const LoopJob* job;        // decode v4 only (graph replay)
+  int grid3d;                // 1: `planes` is ONE feature volume [B][R][R][R][C] (the 'grid' variant, grid_point.cuh)
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -101,6 +103,64 @@ __global__ void __launch_bounds__(kDecThreads) convonet_decode_kernel(const Deco
   }
   float gp[3];
   pt.backward(Wb, planes, glogit, a.R, a.n_blocks, gp);
+  if (live) {
+    a.grad_out[(size_t)pi * 3 + 0] = gp[0];
+    a.grad_out[(size_t)pi * 3 + 1] = gp[1];
+    a.grad_out[(size_t)pi * 3 + 2] = gp[2];
+  }
+}
+
+// The 'grid' variant of the decoder (LocalDecoder with plane_type ['grid']: decoder.py:59-67,72-73): thread per point, fp32,
+// weights in shared memory -- the structure of the first-generation plane kernel above with the three bilinear plane samples
+// replaced by one trilinear sample of the feature volume.  No shipped config selects this variant, so it is
+// kept at this simple formulation: correct and parity-tested, not tuned.
+template <int MODE>
+__global__ void __launch_bounds__(kDecThreads) convonet_grid_decode_kernel(const DecodeArgs a) {
+  extern __shared__ float4 smem_w4[];
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.W);
+    for (int i = threadIdx.x; i < a.wtotal4; i += kDecThreads) smem_w4[i] = src[i];
+  }
+  __syncthreads();
+  const float* Wb = reinterpret_cast<const float*>(smem_w4);
+  const int n = a.B * a.K;
+  const int idx = blockIdx.x * kDecThreads + threadIdx.x;
+  const bool live = idx < n;
+  const int pi = live ? idx : n - 1;
+  const float* vol = a.planes + (size_t)(pi / a.K) * a.R * a.R * a.R * H32;
+  const float px = a.xyz[(size_t)pi * 3 + 0], py = a.xyz[(size_t)pi * 3 + 1], pz = a.xyz[(size_t)pi * 3 + 2];
+  GridPoint<H32> pt;
+  const float logit = pt.forward(Wb, vol, px, py, pz, a.R, a.denom, a.n_blocks);
+  if (live && a.logits_out) a.logits_out[pi] = logit;
+  if (MODE == kFwdOnly) return;
+  float glogit;
+  if (MODE == kBwdGiven) {
+    glogit = a.grad_logits[pi];
+  } else {
+    const float sg = sigmoidf_(logit);
+    glogit = (sg - a.target) * a.ginv;
+    if (a.stat_part) {                   // block-uniform branch
+      __shared__ double red[2][kDecThreads / 32];
+      double s0 = warp_sum_d(live ? (double)bce_with_logits(logit, a.target) : 0.0);
+      double s1 = warp_sum_d(live ? (double)sg : 0.0);
+      if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = s0;
+        red[1][threadIdx.x >> 5] = s1;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int w = 0; w < kDecThreads / 32; ++w) {
+          t0 += red[0][w];
+          t1 += red[1][w];
+        }
+        a.stat_part[blockIdx.x * 2 + 0] = t0;
+        a.stat_part[blockIdx.x * 2 + 1] = t1;
+      }
+    }
+  }
+  float gp[3];
+  pt.backward(Wb, vol, glogit, a.R, a.n_blocks, gp);
   if (live) {
     a.grad_out[(size_t)pi * 3 + 0] = gp[0];
     a.grad_out[(size_t)pi * 3 + 1] = gp[1];
@@ -378,6 +438,11 @@ static int check_decoder_cfg(int R, int C, int H, int n_blocks) {
   return IFD_OK;
 }
 
+static float grid_denom(double padding) {
+  // p / (1 + padding + 10e-4) (common.py:269): the Python double is rounded to fp32 when it meets the tensor
+  return (float)(1.0 + padding + 10e-4);
+}
+
 static float plane_denom(double padding) {
   // xy / (1 + padding + 10e-6): the Python double is rounded to fp32 when it meets the tensor (common.py:250)
   return (float)(1.0 + padding + 10e-6);
@@ -389,6 +454,20 @@ static int launch_decode(int mode, DecodeArgs a, cudaStream_t st) {
   const size_t smem = (size_t)a.wtotal4 * sizeof(float4);
   const int n = a.B * a.K;
   const int grid = (n + kDecThreads - 1) / kDecThreads;
+  if (a.grid3d) {
+    if (mode == kFwdOnly) {
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_grid_decode_kernel<kFwdOnly>, smem));
+      convonet_grid_decode_kernel<kFwdOnly><<<grid, kDecThreads, smem, st>>>(a);
+    } else if (mode == kBwdGiven) {
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_grid_decode_kernel<kBwdGiven>, smem));
+      convonet_grid_decode_kernel<kBwdGiven><<<grid, kDecThreads, smem, st>>>(a);
+    } else {
+      IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_grid_decode_kernel<kBce>, smem));
+      convonet_grid_decode_kernel<kBce><<<grid, kDecThreads, smem, st>>>(a);
+    }
+    IFD_LAUNCH_CHECK("convonet_grid_decode_kernel");
+    return IFD_OK;
+  }
   if (mode == kFwdOnly) {
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_kernel<kFwdOnly>, smem));
     convonet_decode_kernel<kFwdOnly><<<grid, kDecThreads, smem, st>>>(a);
@@ -598,17 +677,19 @@ int g_use_graph = 1;   // ifd_test_hook(3, 0 / 1)
 // The loop of optimize_points (opt_defense.py:210-239) as a sequence of launches on `st`.  With `job` the kernels take every
 // buffer pointer from that device record (graph capture); the pointer arguments are then only used for shapes.
 int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, float* m, float* v, bool fresh, int B, int K, int R,
-                 int n_blocks, const ifd_opt_params* P, double* stats_out, void* workspace, const LoopJob* job, cudaStream_t st) {
+                 int n_blocks, const ifd_opt_params* P, double* stats_out, void* workspace, const LoopJob* job, cudaStream_t st,
+                 bool grid3d = false) {
   OptWorkspace w = carve_opt_ws(workspace, B, K);
   int rc;
   if ((rc = opt_begin(m, v, fresh, B, K, P, workspace, st))) return rc;
   DecodeArgs a{};
   a.planes = planes_cl; a.W = dec_weights; a.xyz = xyz; a.grad_out = w.g_occ; a.job = job;
-  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(P->padding);
+  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = grid3d ? grid_denom(P->padding) : plane_denom(P->padding);
+  a.grid3d = grid3d ? 1 : 0;
   a.target = (float)P->occ_target;
   // d/dlogit of (mean over B_ref*K) * K: autograd multiplies K, then divides by the element count
   a.ginv = (float)K / (float)((long long)P->B_ref * K);
-  const int dk = P->decode_kernel == 0 ? 4 : P->decode_kernel;
+  const int dk = grid3d ? 1 : (P->decode_kernel == 0 ? 4 : P->decode_kernel);      // the grid variant has the thread-per-point kernel only
   const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads          // CTAs of the decode kernel (stat partials)
                     : dk == 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
   if (dk >= 3) {
@@ -625,7 +706,7 @@ int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, f
                    : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
       if (rc) return rc;
     }
-    if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1, st, job, fresh))) return rc;
+    if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1 || grid3d, st, job, fresh))) return rc;
   }
   return opt_finish(xyz, B, K, P->normalize_out, st, job);
 }
@@ -981,6 +1062,69 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   }
   return dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
                  : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+}
+
+// ---- the 'grid' (feature volume, trilinear) variant ------------------------------------------------------------------------
+__global__ void grid_bins_kernel(const float* __restrict__ p, int n, int R, float denom, int32_t* __restrict__ bins) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float fR = (float)R;
+  // (p_nor * reso).long(): truncation toward zero of the fp32 product; x + R (y + R z)  (common.py:309-313)
+  const int ix = (int)mul_rn(grid_coord(p[(size_t)e * 3 + 0], denom).u, fR);
+  const int iy = (int)mul_rn(grid_coord(p[(size_t)e * 3 + 1], denom).u, fR);
+  const int iz = (int)mul_rn(grid_coord(p[(size_t)e * 3 + 2], denom).u, fR);
+  bins[e] = ix + R * (iy + R * iz);
+}
+
+extern "C" int ifd_grid_bins(const float* xyz, int B, int T, int R, double padding, int32_t* bins_out, ifd_stream_t stream) {
+  IFD_REQUIRE(xyz && bins_out && B > 0 && T > 0 && R > 0 && R <= 1024, "ifd_grid_bins: bad arguments");
+  const int n = B * T;
+  grid_bins_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(xyz, n, R, grid_denom(padding), bins_out);
+  IFD_LAUNCH_CHECK("grid_bins_kernel");
+  return IFD_OK;
+}
+
+static int grid_decode(int mode, const float* volume_cl, const float* dec_weights, const float* xyz, const float* grad_logits, int B,
+                       int K, int R, int C, int H, int n_blocks, double padding, float* logits_out, float* grad_out, cudaStream_t st) {
+  int rc = check_decoder_cfg(R, C, H, n_blocks);
+  if (rc) return rc;
+  if ((rc = check_ptrs16(volume_cl, dec_weights))) return rc;
+  DecodeArgs a{};
+  a.planes = volume_cl; a.W = dec_weights; a.xyz = xyz; a.grad_logits = grad_logits; a.logits_out = logits_out; a.grad_out = grad_out;
+  a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = grid_denom(padding); a.grid3d = 1;
+  return launch_decode(mode, a, st);
+}
+
+extern "C" int ifd_convonet_grid_decode_fwd(const float* volume_cl, const float* dec_weights, const float* xyz, int B, int K, int R,
+                                            int C, int H, int n_blocks, double padding, float* logits_out, ifd_stream_t stream) {
+  IFD_REQUIRE(volume_cl && dec_weights && xyz && logits_out && B > 0 && K > 0, "ifd_convonet_grid_decode_fwd: bad arguments");
+  return grid_decode(kFwdOnly, volume_cl, dec_weights, xyz, nullptr, B, K, R, C, H, n_blocks, padding, logits_out, nullptr, as_stream(stream));
+}
+
+extern "C" int ifd_convonet_grid_decode_bwd(const float* volume_cl, const float* dec_weights, const float* xyz, const float* grad_logits,
+                                            int B, int K, int R, int C, int H, int n_blocks, double padding, float* grad_xyz_out,
+                                            ifd_stream_t stream) {
+  IFD_REQUIRE(volume_cl && dec_weights && xyz && grad_logits && grad_xyz_out && B > 0 && K > 0, "ifd_convonet_grid_decode_bwd: bad arguments");
+  return grid_decode(kBwdGiven, volume_cl, dec_weights, xyz, grad_logits, B, K, R, C, H, n_blocks, padding, nullptr, grad_xyz_out, as_stream(stream));
+}
+
+extern "C" int ifd_convonet_grid_opt(const float* volume_cl, const float* dec_weights, float* xyz, float* adam_m, float* adam_v, int B,
+                                     int K, int R, int C, int H, int n_blocks, const ifd_opt_params* P, double* stats_out,
+                                     void* workspace, size_t workspace_bytes, ifd_stream_t stream) {
+  IFD_REQUIRE(volume_cl && dec_weights && xyz && P && B > 0 && K > 0, "ifd_convonet_grid_opt: bad arguments");
+  IFD_REQUIRE(P->n_steps >= 0 && P->step0 >= 0 && P->B_ref > 0, "ifd_convonet_grid_opt: bad step counts / B_ref");
+  IFD_REQUIRE((adam_m == nullptr) == (adam_v == nullptr), "ifd_convonet_grid_opt: pass both adam_m and adam_v or neither");
+  IFD_REQUIRE(!(P->step0 > 0 && !adam_m), "ifd_convonet_grid_opt: resuming (step0 > 0) needs adam_m / adam_v");
+  int rc = check_decoder_cfg(R, C, H, n_blocks);
+  if (rc) return rc;
+  if ((rc = check_ptrs16(volume_cl, dec_weights))) return rc;
+  IFD_REQUIRE(workspace, "ifd_convonet_grid_opt: workspace is required");
+  if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_grid_opt: workspace too small");
+  OptWorkspace w = carve_opt_ws(workspace, B, K);
+  float* m = adam_m ? adam_m : w.m;
+  float* v = adam_v ? adam_v : w.v;
+  return enqueue_loop(volume_cl, dec_weights, xyz, m, v, !adam_m || P->step0 == 0, B, K, R, n_blocks, P, stats_out, workspace, nullptr,
+                      as_stream(stream), true);
 }
 
 namespace ifd { void onet_set_engine(int on); void tc_set_cluster(int n); }

@@ -278,6 +278,24 @@ int ifd_convonet_opt_batches(int n_batches, const float* const* planes_cl, const
                              void* workspace, size_t workspace_bytes, ifd_stream_t stream);
 
 
+/* ------------------------------------------------------------------------------------------------
+ * The 'grid' variant of ConvONet: ONE feature volume sampled trilinearly instead of three planes sampled bilinearly
+ * (LocalDecoder.sample_grid_feature, ConvONet/src/conv_onet/models/decoder.py:59-67,72-73; normalize_3d_coordinate,
+ * ConvONet/src/common.py:260-276; LocalPoolPointnet.generate_grid_features, ConvONet/src/encoder/pointnet.py:88-99).
+ * No shipped config selects it (configs/ has no grid_resolution); it is what BASELINE.json's north_star describes.
+ * volume_cl: [B][R][R][R][C] float32 channels-last, indexed [z][y][x] (coordinate2index '3d' = x + R (y + R z)); C = H = 32.
+ * Same arguments and semantics as the plane entry points above; thread-per-point fp32 kernels.
+ * ---------------------------------------------------------------------------------------------- */
+int ifd_grid_bins(const float* xyz, int B, int T, int R, double padding, int32_t* bins_out /* [B][T] */, ifd_stream_t stream);
+int ifd_convonet_grid_decode_fwd(const float* volume_cl, const float* dec_weights, const float* xyz, int B, int K, int R, int C,
+                                 int H, int n_blocks, double padding, float* logits_out, ifd_stream_t stream);
+int ifd_convonet_grid_decode_bwd(const float* volume_cl, const float* dec_weights, const float* xyz, const float* grad_logits,
+                                 int B, int K, int R, int C, int H, int n_blocks, double padding, float* grad_xyz_out,
+                                 ifd_stream_t stream);
+int ifd_convonet_grid_opt(const float* volume_cl, const float* dec_weights, float* xyz, float* adam_m, float* adam_v, int B, int K,
+                          int R, int C, int H, int n_blocks, const ifd_opt_params* params, double* stats_out, void* workspace,
+                          size_t workspace_bytes, ifd_stream_t stream);
+
 /* Host-buffer convenience call (the end-to-end seam): planes in the reference's NCHW layout
  * [3][B][C][R][R], weights, xyz are HOST pointers; does H2D, layout conversion, the loop, D2H of xyz and
  * synchronises.  Device scratch is cached per thread between calls and released by ifd_release_cache(). */

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../if-defense_b200/csrc/convonet_point.cuh"
+#include "../../if-defense_b200/csrc/grid_point.cuh"
 
 using namespace ifd;
 
@@ -39,6 +40,28 @@ void mc_convonet_decode(const float* W, const float* planes_cl, const float* xyz
     const float gl = mode == 1 ? grad_logits[pi] : (sigmoidf_(logit) - target) * ginv;
     float gp[3];
     pt.backward(W, planes, gl, R, n_blocks, gp);
+    grad_out[pi * 3] = gp[0];
+    grad_out[pi * 3 + 1] = gp[1];
+    grad_out[pi * 3 + 2] = gp[2];
+  }
+}
+
+// The 'grid' variant (grid_point.cuh): vol_cl [B][R][R][R][32] channels-last.  mode as above.
+void mc_convonet_grid_decode(const float* W, const float* vol_cl, const float* xyz, int B, int K, int R, int n_blocks,
+                             double padding, int mode, const float* grad_logits, float target, float ginv,
+                             float* logits_out, float* grad_out) {
+  const float denom = (float)(1.0 + padding + 10e-4);
+  const size_t vol_sz = (size_t)R * R * R * 32;
+#pragma omp parallel for schedule(static)
+  for (int pi = 0; pi < B * K; ++pi) {
+    const float* vol = vol_cl + (size_t)(pi / K) * vol_sz;
+    GridPoint<32> pt;
+    const float logit = pt.forward(W, vol, xyz[pi * 3], xyz[pi * 3 + 1], xyz[pi * 3 + 2], R, denom, n_blocks);
+    if (logits_out) logits_out[pi] = logit;
+    if (mode == 0) continue;
+    const float gl = mode == 1 ? grad_logits[pi] : (sigmoidf_(logit) - target) * ginv;
+    float gp[3];
+    pt.backward(W, vol, gl, R, n_blocks, gp);
     grad_out[pi * 3] = gp[0];
     grad_out[pi * 3 + 1] = gp[1];
     grad_out[pi * 3 + 2] = gp[2];
