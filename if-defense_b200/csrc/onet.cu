@@ -10,11 +10,10 @@
 // The ten 256x256 layers per direction are real GEMMs (M = B*K points, N = K = 256): one tcgen05 kernel,
 //   Y[M][256] = prologue(A)[M][256] . W^T  (+ bias, + residual)                       forward
 //   Y[M][256] = (G[M][256] . W) * s_b * [s_b * Xsaved + t_b > 0]  (+ residual)        dgrad through CBN+ReLU
-// A CTA owns 128 rows; thread r owns row r: it reads a 32-column chunk of its row, applies the prologue, splits it
-// into TF32 hi/lo and writes it to TMEM with tcgen05.st (A operand in TMEM, no shared-memory staging); the weight
-// chunk [256 x 32] hi/lo streams from a pre-packed K-major image in L2 into a double-buffered shared-memory slot;
-// twelve tcgen05.mma (3xTF32 x four K=8 steps, M=128, N=256) accumulate into 256 TMEM columns.  Activations of the
-// forward pass are kept in HBM (11 x [M][256] fp32) for the dgrad masks -- 740 MB at B=64, K=1024.
+// Every layer runs on the shared warp-specialised GEMM engine (tc_gemm.cuh: A producers with the CBN + ReLU prologue, weight
+// chunks [256 x 32] hi/lo by TMA bulk copies multicast across a 2-CTA cluster, twelve tcgen05.mma per chunk into one of two
+// TMEM accumulator stages, epilogue warps with bias / residual / dgrad mask).  Activations of the forward pass are kept
+// in HBM (11 x [M][256] fp32, warp-transposed layout, see act_off4) for the dgrad masks -- 740 MB at B=64, K=1024.
 #include "common.cuh"
 #include "ifd_math.cuh"
 #include "tc_gemm.cuh"
@@ -25,13 +24,20 @@ namespace ifd {
 constexpr int kOH = 256;          // hidden size
 constexpr int kOC = 512;          // c_dim
 constexpr int kOnetCbn = 11;      // block{0..4}.bn_{0,1}, bn
-constexpr int kGemmThreads = 128;
 constexpr int kChunk = 32;                              // K columns per pipeline step
 constexpr int kChunkImgFloats = 2 * kOH * kChunk;       // hi + lo of a [256 x 32] chunk
 constexpr int kLayerImgFloats = (kOH / kChunk) * kChunkImgFloats;   // 131072 floats = 512 KB
-constexpr int kNH = kOH / 2;                            // output columns per CTA: the N range is split over blockIdx.y so that
-                                                        // two CTAs (256 TMEM columns each) share an SM
-constexpr int kHalfImgFloats = 2 * kNH * kChunk;        // hi + lo of a [128 x 32] half chunk = 32 KB
+
+// Activation tensors of the chain ([M][256] logically: net_i, h_i, gradients) live in a WARP-TRANSPOSED layout: rows in blocks
+// of 32, and inside a block the 64 float4 column groups one after the other, each holding its 32 rows contiguously:
+//     float offset of (row m, column k) = (((m / 32) * 64 + k / 4) * 32 + m % 32) * 4 + k % 4.
+// The kernels that touch them are thread-per-row (a TMEM lane is a row), and in this layout the 32 lanes of a warp reading
+// "their row's float4 number q" touch 512 contiguous bytes -- 4 L1 wavefronts instead of the 32 a row-major tensor costs
+// (ncu on the row-major version: LSU wavefronts 71 % of peak, tensor pipe 31 %: the layer was bound by its own addressing).
+__host__ __device__ __forceinline__ size_t act_off4(int m, int k4) {          // in float4 units
+  return ((size_t)(m >> 5) * 64 + (size_t)k4) * 32 + (size_t)(m & 31);
+}
+__host__ __device__ inline size_t act_floats(int M) { return (size_t)((M + 31) / 32) * 32 * kOH; }
 
 // ---------------------------------------------------------------------------------------------- packing
 // One layer's weight W[n][k] (row-major [256][256]) -> chunked K-major UMMA images, hi then lo per chunk.
@@ -117,10 +123,10 @@ struct OnetLayerPolicy {
       for (int k = 0; k < 32; ++k) x[k] = 0.0f;
       return;
     }
-    const float4* p4 = reinterpret_cast<const float4*>(P.g.A + (size_t)r.row * kOH + kc * kChunk);
+    const float4* p4 = reinterpret_cast<const float4*>(P.g.A) + act_off4(r.row, kc * 8);      // + 32 per float4 column group
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 v = __ldg(p4 + q);
+      const float4 v = __ldg(p4 + q * 32);
       x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
     if (P.g.pro_s) {                    // CBN (eval mode, folded) + ReLU on read
@@ -139,16 +145,23 @@ struct OnetLayerPolicy {
   static __device__ __forceinline__ void store(const Params& P, const Row& r, int col0, const float (&y_in)[32]) {
     if (r.row >= P.M) return;
     const GemmArgs& a = P.g;
+    const size_t off = act_off4(r.row, col0 >> 2);
     float y[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) y[k] = y_in[k];
+    float4 rv[8];
+    if (a.resid) {                      // plain loads (the dgrad residual buffer is updated in place), issued before any store
+      const float4* r4 = reinterpret_cast<const float4*>(a.resid) + off;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rv[q] = r4[q * 32];
+    }
     if (a.mask_x) {                     // dgrad through relu(s * x + t): scale by s where the pre-activation was positive
-      const float4* x4 = reinterpret_cast<const float4*>(a.mask_x + (size_t)r.row * kOH + col0);
+      const float4* x4 = reinterpret_cast<const float4*>(a.mask_x) + off;
       const float4* s4 = reinterpret_cast<const float4*>(a.mask_s + (size_t)r.b * kOH + col0);
       const float4* t4 = reinterpret_cast<const float4*>(a.mask_t + (size_t)r.b * kOH + col0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 xs = __ldg(x4 + q), s = __ldg(s4 + q), t = __ldg(t4 + q);
+        const float4 xs = __ldg(x4 + q * 32), s = __ldg(s4 + q), t = __ldg(t4 + q);
         y[4 * q + 0] = fmaf(s.x, xs.x, t.x) > 0.0f ? y[4 * q + 0] * s.x : 0.0f;
         y[4 * q + 1] = fmaf(s.y, xs.y, t.y) > 0.0f ? y[4 * q + 1] * s.y : 0.0f;
         y[4 * q + 2] = fmaf(s.z, xs.z, t.z) > 0.0f ? y[4 * q + 2] * s.z : 0.0f;
@@ -164,236 +177,97 @@ struct OnetLayerPolicy {
       }
     }
     if (a.resid) {
-      const float4* r4 = reinterpret_cast<const float4*>(a.resid + (size_t)r.row * kOH + col0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 rv = r4[q];        // plain load: the dgrad residual buffer is updated in place
-        y[4 * q + 0] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
+        y[4 * q + 0] += rv[q].x; y[4 * q + 1] += rv[q].y; y[4 * q + 2] += rv[q].z; y[4 * q + 3] += rv[q].w;
       }
     }
-    float4* o4 = reinterpret_cast<float4*>(a.out + (size_t)r.row * kOH + col0);
+    float4* o4 = reinterpret_cast<float4*>(a.out) + off;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) o4[q] = make_float4(y[4 * q + 0], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+    for (int q = 0; q < 8; ++q) o4[q * 32] = make_float4(y[4 * q + 0], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
   }
 };
 
-__global__ void __launch_bounds__(kGemmThreads, 2) onet_gemm_kernel(const GemmArgs a) {
-  extern __shared__ float4 smem4[];
-  float* bbuf = reinterpret_cast<float*>(smem4);                    // [2][kHalfImgFloats]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bbuf + 2 * kHalfImgFloats);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  const int warp = threadIdx.x >> 5;
-  const int nh = blockIdx.y;                                        // which half of the 256 output columns
-  if (warp == 0) umma::tmem_alloc(tmem_slot, 256);                  // D: columns 0..127, A chunks: 128..255
-  if (threadIdx.x == 32) {
-    umma::mbar_init(&bars[0], 1);
-    umma::mbar_init(&bars[1], 1);
-    umma::fence_mbar_init();
-  }
-  // Weight chunk kc, rows [128 nh, 128 nh + 128) -> slot buf with cp.async (no register staging).  In the packed
-  // K-major image of the full [256 x 32] chunk every 4-wide k group holds its 32 n-groups contiguously (4 KB), so
-  // the half is 16 pieces of 2 KB (8 k groups x {hi, lo}), stored back to back: LBO = 2048 in shared memory.
-  auto load_b = [&](int kc, int buf) {
-    const float4* src = reinterpret_cast<const float4*>(a.img + (size_t)kc * kChunkImgFloats);
-    const uint32_t dst = umma::smem_u32(bbuf + (size_t)buf * kHalfImgFloats);
-    for (int i = threadIdx.x; i < kHalfImgFloats / 4; i += kGemmThreads) {
-      const int piece = i >> 7, within = i & 127;                   // 128 float4 = 2 KB per piece
-      const int sidx = (piece < 8 ? piece * 256 : 2048 + (piece - 8) * 256) + nh * 128 + within;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + sidx) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  load_b(0, 0);
-  __syncthreads();                          // barriers / TMEM slot visible
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_t = tmem + ((uint32_t)(warp * 32) << 16);
-  const int row = blockIdx.x * kGemmThreads + threadIdx.x;
-  const int rowc = min(row, a.M - 1);
-  const int b = rowc / a.K;
-  const float* arow = a.A + (size_t)rowc * kOH;
-  const bool leader = threadIdx.x == 0;
-  uint32_t parity[2] = {0u, 0u};
-  constexpr uint32_t idesc = umma::idesc_tf32(128, kNH);
-
-  float4 nx[8];                             // next chunk of this thread's row, loaded one iteration ahead
-#pragma unroll
-  for (int q = 0; q < 8; ++q) nx[q] = __ldg(reinterpret_cast<const float4*>(arow) + q);
-
-#pragma unroll 1
-  for (int kc = 0; kc < kOH / kChunk; ++kc) {
-    const int buf = kc & 1;
-    float x[32];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      x[4 * q + 0] = nx[q].x; x[4 * q + 1] = nx[q].y; x[4 * q + 2] = nx[q].z; x[4 * q + 3] = nx[q].w;
-    }
-    if (kc + 1 < kOH / kChunk) {
-      const float4* p4 = reinterpret_cast<const float4*>(arow + (kc + 1) * kChunk);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) nx[q] = __ldg(p4 + q);
-    }
-    if (a.pro_s) {
-      const float4* s4 = reinterpret_cast<const float4*>(a.pro_s + (size_t)b * kOH + kc * kChunk);
-      const float4* t4 = reinterpret_cast<const float4*>(a.pro_t + (size_t)b * kOH + kc * kChunk);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 s = __ldg(s4 + q), t = __ldg(t4 + q);
-        x[4 * q + 0] = fmaxf(fmaf(s.x, x[4 * q + 0], t.x), 0.0f);
-        x[4 * q + 1] = fmaxf(fmaf(s.y, x[4 * q + 1], t.y), 0.0f);
-        x[4 * q + 2] = fmaxf(fmaf(s.z, x[4 * q + 2], t.z), 0.0f);
-        x[4 * q + 3] = fmaxf(fmaf(s.w, x[4 * q + 3], t.w), 0.0f);
-      }
-    }
-    if (kc + 1 < kOH / kChunk) {            // prefetch the next weight chunk into the other slot
-      if (kc >= 1) {                        // MMA kc-1 read that slot (and its A columns): it must have completed
-        umma::mbar_wait(&bars[buf ^ 1], parity[buf ^ 1]);
-        parity[buf ^ 1] ^= 1;
-        umma::fence_after_sync();
-      }
-      load_b(kc + 1, buf ^ 1);
-    }
-    uint32_t u[32];
-    const uint32_t a_hi = lane_t + kNH + buf * 64, a_lo = a_hi + 32;
-#pragma unroll
-    for (int k = 0; k < 32; ++k) u[k] = umma::tf32_hi_fast(x[k]);
-    umma::tmem_st32(a_hi, u);
-#pragma unroll
-    for (int k = 0; k < 32; ++k) u[k] = __float_as_uint(x[k] - __uint_as_float(u[k]));   // exact residual, top 11 bits used
-    umma::tmem_st32(a_lo, u);
-    umma::tmem_wait_st();
-    // this chunk's weights (all but the group just committed) have landed
-    if (kc + 1 < kOH / kChunk) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    umma::fence_proxy_async();
-    umma::fence_before_sync();
-    __syncthreads();
-    if (leader) {
-      umma::fence_after_sync();
-      const uint32_t ta_hi = tmem + kNH + buf * 64, ta_lo = ta_hi + 32;
-      const uint32_t sb = umma::smem_u32(bbuf + (size_t)buf * kHalfImgFloats);
-#pragma unroll
-      for (int part = 0; part < 3; ++part) {        // lo.hi, hi.lo, hi.hi
-        const uint32_t ta = part == 0 ? ta_lo : ta_hi;
-        const uint32_t bs = sb + (part == 1 ? (uint32_t)(kNH * kChunk * 4) : 0u);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)
-          umma::mma_tf32_ts(tmem, ta + s * 8, umma::smem_desc_kmajor(bs + s * 2 * (kNH / 8) * 128, (kNH / 8) * 128, 128), idesc,
-                            (kc | part | s) ? 1u : 0u);
-      }
-      umma::commit(&bars[buf]);
-    }
-    __syncwarp();
-  }
-  // the last commit covers every earlier MMA
-  umma::mbar_wait(&bars[1], parity[1]);
-  umma::fence_after_sync();
-
-  float* orow = a.out + (size_t)rowc * kOH;
-  const bool live = row < a.M;
-#pragma unroll 1
-  for (int cl = 0; cl < kNH / 32; ++cl) {
-    const int cg = nh * (kNH / 32) + cl;            // 32-column group of the full row
-    uint32_t d[32];
-    umma::tmem_ld32(lane_t + cl * 32, d);
-    float y[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(d[k]);
-    if (a.mask_x) {                     // dgrad through relu(s * x + t): scale by s where the pre-activation was positive
-      const float4* x4 = reinterpret_cast<const float4*>(a.mask_x + (size_t)rowc * kOH + cg * 32);
-      const float4* s4 = reinterpret_cast<const float4*>(a.mask_s + (size_t)b * kOH + cg * 32);
-      const float4* t4 = reinterpret_cast<const float4*>(a.mask_t + (size_t)b * kOH + cg * 32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 xs = __ldg(x4 + q), s = __ldg(s4 + q), t = __ldg(t4 + q);
-        y[4 * q + 0] = fmaf(s.x, xs.x, t.x) > 0.0f ? y[4 * q + 0] * s.x : 0.0f;
-        y[4 * q + 1] = fmaf(s.y, xs.y, t.y) > 0.0f ? y[4 * q + 1] * s.y : 0.0f;
-        y[4 * q + 2] = fmaf(s.z, xs.z, t.z) > 0.0f ? y[4 * q + 2] * s.z : 0.0f;
-        y[4 * q + 3] = fmaf(s.w, xs.w, t.w) > 0.0f ? y[4 * q + 3] * s.w : 0.0f;
-      }
-    }
-    if (a.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(a.bias + cg * 32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 bv = __ldg(b4 + q);
-        y[4 * q + 0] += bv.x; y[4 * q + 1] += bv.y; y[4 * q + 2] += bv.z; y[4 * q + 3] += bv.w;
-      }
-    }
-    if (a.resid) {
-      const float4* r4 = reinterpret_cast<const float4*>(a.resid + (size_t)rowc * kOH + cg * 32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 rv = r4[q];     // plain load: the dgrad residual buffer is updated in place by this kernel
-        y[4 * q + 0] += rv.x; y[4 * q + 1] += rv.y; y[4 * q + 2] += rv.z; y[4 * q + 3] += rv.w;
-      }
-    }
-    if (live) {
-      float4* o4 = reinterpret_cast<float4*>(orow + cg * 32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) o4[q] = make_float4(y[4 * q + 0], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-    }
-  }
-  umma::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 256);
-}
-
 // ---------------------------------------------------------------------------------------------- thin layers
+// All thread-per-row on the warp-transposed activation layout (a warp = one block of 32 rows: every access is 512 contiguous bytes).
+
 // net0[m][n] = Wp[n][:] . p_m + bp[n]        (fc_p: Conv1d(3, 256, 1))
 __global__ void onet_fcp_kernel(const float* __restrict__ xyz, const float* __restrict__ Wp, const float* __restrict__ bp,
                                 int M, float* __restrict__ out) {
-  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (size_t)M * kOH) return;
-  const int m = (int)(e / kOH), n = (int)(e % kOH);
-  float v = bp[n];
-  v = fmaf(Wp[n * 3 + 0], xyz[(size_t)m * 3 + 0], v);
-  v = fmaf(Wp[n * 3 + 1], xyz[(size_t)m * 3 + 1], v);
-  v = fmaf(Wp[n * 3 + 2], xyz[(size_t)m * 3 + 2], v);
-  out[e] = v;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float px = xyz[(size_t)m * 3 + 0], py = xyz[(size_t)m * 3 + 1], pz = xyz[(size_t)m * 3 + 2];
+  float4* o4 = reinterpret_cast<float4*>(out) + act_off4(m, 0);
+#pragma unroll 4
+  for (int q = 0; q < kOH / 4; ++q) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = 4 * q + j;
+      float t = __ldg(bp + n);
+      t = fmaf(__ldg(Wp + n * 3 + 0), px, t);
+      t = fmaf(__ldg(Wp + n * 3 + 1), py, t);
+      t = fmaf(__ldg(Wp + n * 3 + 2), pz, t);
+      v[j] = t;
+    }
+    o4[q * 32] = make_float4(v[0], v[1], v[2], v[3]);
+  }
 }
 
-// One warp per row: logit = w_out . relu(s_f * net + t_f) + b_out ; then either store the logit (forward seam), or
-// turn it into the gradient of the loss w.r.t. net:  g_net = glogit * w_out * [pre > 0] * s_f  with
-// glogit = grad_logits[m] (seam) or (sigmoid(logit) - target) * ginv (loop).
+// logit = w_out . relu(s_f * net + t_f) + b_out ; then either store the logit (forward seam), or turn it into the gradient
+// of the loss w.r.t. net:  g_net = glogit * w_out * [pre > 0] * s_f  with glogit = grad_logits[m] (seam) or
+// (sigmoid(logit) - target) * ginv (loop).  The dot product runs over n = 0 .. 255 in order (one thread, one chain).
 __global__ void onet_head_kernel(const float* __restrict__ net, const float* __restrict__ s, const float* __restrict__ t,
                                  const float* __restrict__ wout, const float* __restrict__ bout, int M, int K,
                                  float* __restrict__ logits_out, const float* __restrict__ grad_logits, int bce, float target,
                                  float ginv, float* __restrict__ gnet_out, double* __restrict__ stat_part) {
-  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp_in_block = threadIdx.x >> 5;
   double s0 = 0.0, s1 = 0.0;
   if (m < M) {
     const int b = m / K;
-    const float* row = net + (size_t)m * kOH;
-    const float* sb = s + (size_t)b * kOH;
-    const float* tb = t + (size_t)b * kOH;
-    float pre[8], acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int n = lane + 32 * i;
-      pre[i] = fmaf(sb[n], row[n], tb[n]);
-      acc = fmaf(wout[n], fmaxf(pre[i], 0.0f), acc);
+    const float4* row4 = reinterpret_cast<const float4*>(net) + act_off4(m, 0);
+    const float4* sb4 = reinterpret_cast<const float4*>(s + (size_t)b * kOH);
+    const float4* tb4 = reinterpret_cast<const float4*>(t + (size_t)b * kOH);
+    const float4* w4 = reinterpret_cast<const float4*>(wout);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < kOH / 4; ++q) {
+      const float4 x = __ldg(row4 + q * 32), sv = __ldg(sb4 + q), tv = __ldg(tb4 + q), wv = __ldg(w4 + q);
+      acc = fmaf(wv.x, fmaxf(fmaf(sv.x, x.x, tv.x), 0.0f), acc);
+      acc = fmaf(wv.y, fmaxf(fmaf(sv.y, x.y, tv.y), 0.0f), acc);
+      acc = fmaf(wv.z, fmaxf(fmaf(sv.z, x.z, tv.z), 0.0f), acc);
+      acc = fmaf(wv.w, fmaxf(fmaf(sv.w, x.w, tv.w), 0.0f), acc);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     const float logit = acc + bout[0];
-    if (logits_out && lane == 0) logits_out[m] = logit;
+    if (logits_out) logits_out[m] = logit;
     if (gnet_out) {
       const float sg = sigmoidf_(logit);
       const float gl = bce ? (sg - target) * ginv : grad_logits[m];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int n = lane + 32 * i;
-        gnet_out[(size_t)m * kOH + n] = pre[i] > 0.0f ? gl * wout[n] * sb[n] : 0.0f;
+      float4* g4 = reinterpret_cast<float4*>(gnet_out) + act_off4(m, 0);
+#pragma unroll 4
+      for (int q = 0; q < kOH / 4; ++q) {
+        const float4 x = __ldg(row4 + q * 32), sv = __ldg(sb4 + q), tv = __ldg(tb4 + q), wv = __ldg(w4 + q);
+        float4 o;
+        o.x = fmaf(sv.x, x.x, tv.x) > 0.0f ? gl * wv.x * sv.x : 0.0f;
+        o.y = fmaf(sv.y, x.y, tv.y) > 0.0f ? gl * wv.y * sv.y : 0.0f;
+        o.z = fmaf(sv.z, x.z, tv.z) > 0.0f ? gl * wv.z * sv.z : 0.0f;
+        o.w = fmaf(sv.w, x.w, tv.w) > 0.0f ? gl * wv.w * sv.w : 0.0f;
+        g4[q * 32] = o;
       }
-      if (stat_part && lane == 0) {
+      if (stat_part) {
         s0 = (double)bce_with_logits(logit, target);
         s1 = (double)sg;
       }
     }
   }
-  if (stat_part) {                       // block-uniform
+  if (stat_part) {                       // block-uniform: deterministic block sums
     __shared__ double red[2][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
     if (lane == 0) {
       red[0][warp_in_block] = s0;
       red[1][warp_in_block] = s1;
@@ -411,32 +285,27 @@ __global__ void onet_head_kernel(const float* __restrict__ net, const float* __r
   }
 }
 
-// g_p[m][d] = sum_n Wp[n][d] * g_net0[m][n]      (one warp per row)
+// g_p[m][d] = sum_n Wp[n][d] * g_net0[m][n]
 __global__ void onet_fcp_bwd_kernel(const float* __restrict__ gnet, const float* __restrict__ Wp, int M, float* __restrict__ gp) {
-  const int lane = threadIdx.x & 31;
-  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
-  const float* row = gnet + (size_t)m * kOH;
+  const float4* row4 = reinterpret_cast<const float4*>(gnet) + act_off4(m, 0);
   float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll 4
+  for (int q = 0; q < kOH / 4; ++q) {
+    const float4 g = __ldg(row4 + q * 32);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int n = lane + 32 * i;
-    const float g = row[n];
-    g0 = fmaf(Wp[n * 3 + 0], g, g0);
-    g1 = fmaf(Wp[n * 3 + 1], g, g1);
-    g2 = fmaf(Wp[n * 3 + 2], g, g2);
+    for (int j = 0; j < 4; ++j) {
+      const int n = 4 * q + j;
+      g0 = fmaf(__ldg(Wp + n * 3 + 0), gv[j], g0);
+      g1 = fmaf(__ldg(Wp + n * 3 + 1), gv[j], g1);
+      g2 = fmaf(__ldg(Wp + n * 3 + 2), gv[j], g2);
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    g0 += __shfl_xor_sync(0xffffffffu, g0, o);
-    g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-    g2 += __shfl_xor_sync(0xffffffffu, g2, o);
-  }
-  if (lane == 0) {
-    gp[(size_t)m * 3 + 0] = g0;
-    gp[(size_t)m * 3 + 1] = g1;
-    gp[(size_t)m * 3 + 2] = g2;
-  }
+  gp[(size_t)m * 3 + 0] = g0;
+  gp[(size_t)m * 3 + 1] = g1;
+  gp[(size_t)m * 3 + 2] = g2;
 }
 
 }  // namespace ifd
@@ -467,25 +336,18 @@ OnetWs carve_onet(void* base, int B, int K) {
   w.img = (float*)take((size_t)2 * 10 * kLayerImgFloats * 4);
   w.s = (float*)take((size_t)kOnetCbn * B * kOH * 4);
   w.t = (float*)take((size_t)kOnetCbn * B * kOH * 4);
-  w.act = (float*)take((size_t)11 * M * kOH * 4);
-  w.g0 = (float*)take(M * kOH * 4);
-  w.g1 = (float*)take(M * kOH * 4);
-  w.stat = (double*)take(((M + 7) / 8) * 2 * sizeof(double));
+  const size_t MH = act_floats((int)M);       // rows padded to whole 32-row blocks of the warp-transposed layout
+  w.act = (float*)take((size_t)11 * MH * 4);
+  w.g0 = (float*)take(MH * 4);
+  w.g1 = (float*)take(MH * 4);
+  w.stat = (double*)take(((M + 255) / 256) * 2 * sizeof(double));
   w.bytes = off;
   return w;
 }
-int g_onet_engine = 1;     // ifd_test_hook(5, 0 / 1): 1 = the warp-specialised GEMM engine, 0 = the first-generation kernel
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
-  if (g_onet_engine) {
-    OnetLayerParams P{};
-    P.M = a.M; P.n_chunks = kOH / kChunk; P.n_tiles_n = 1; P.wimg = a.img; P.g = a;
-    return tc::launch<OnetLayerPolicy>(P, 256, st);
-  }
-  const size_t smem = (size_t)2 * kHalfImgFloats * 4 + 64;
-  IFD_CUDA_TRY(set_max_dyn_smem((const void*)onet_gemm_kernel, smem));
-  onet_gemm_kernel<<<dim3((a.M + kGemmThreads - 1) / kGemmThreads, 2), kGemmThreads, smem, st>>>(a);
-  IFD_LAUNCH_CHECK("onet_gemm_kernel");
-  return IFD_OK;
+  OnetLayerParams P{};
+  P.M = a.M; P.n_chunks = kOH / kChunk; P.n_tiles_n = 1; P.wimg = a.img; P.g = a;
+  return tc::launch<OnetLayerPolicy>(P, 256, st);
 }
 }  // namespace
 
@@ -543,8 +405,8 @@ namespace {
 // forward through the decoder; activations land in w.act.  Returns through logits_out (optional).
 int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K, cudaStream_t st) {
   const int M = B * K;
-  const size_t MH = (size_t)M * kOH;
-  onet_fcp_kernel<<<(unsigned)((MH + 255) / 256), 256, 0, st>>>(xyz, W, W + kOH * 3, M, w.act);
+  const size_t MH = act_floats(M);
+  onet_fcp_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xyz, W, W + kOH * 3, M, w.act);
   IFD_LAUNCH_CHECK("onet_fcp_kernel");
   for (int blk = 0; blk < 5; ++blk) {
     float* net = w.act + (size_t)(2 * blk) * MH;
@@ -572,7 +434,7 @@ int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K
 // dgrad from g_net5 (in w.g0) down to grad_xyz
 int onet_backward(const float* W, const OnetWs& w, int B, int K, float* grad_xyz, cudaStream_t st) {
   const int M = B * K;
-  const size_t MH = (size_t)M * kOH;
+  const size_t MH = act_floats(M);
   float* gnet = w.g0;
   float* gtmp = w.g1;
   for (int blk = 4; blk >= 0; --blk) {
@@ -593,7 +455,7 @@ int onet_backward(const float* W, const OnetWs& w, int B, int K, float* grad_xyz
     c.out = gnet;                                   // each thread reads and writes only its own row chunk
     if ((rc = launch_gemm(c, st))) return rc;
   }
-  onet_fcp_bwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(gnet, W, M, grad_xyz);
+  onet_fcp_bwd_kernel<<<(M + 255) / 256, 256, 0, st>>>(gnet, W, M, grad_xyz);
   IFD_LAUNCH_CHECK("onet_fcp_bwd_kernel");
   return IFD_OK;
 }
@@ -610,7 +472,7 @@ extern "C" int ifd_onet_decode_fwd(const float* dec_weights, const float* xyz, i
   int rc = onet_forward(dec_weights, w, xyz, B, K, st);
   if (rc) return rc;
   const int M = B * K;
-  onet_head_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.act + (size_t)10 * M * kOH, w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+  onet_head_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.act + (size_t)10 * act_floats(M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
                                                dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, logits_out, nullptr, 0, 0.f,
                                                0.f, nullptr, nullptr);
   IFD_LAUNCH_CHECK("onet_head_kernel");
@@ -627,7 +489,7 @@ extern "C" int ifd_onet_decode_bwd(const float* dec_weights, const float* xyz, c
   int rc = onet_forward(dec_weights, w, xyz, B, K, st);
   if (rc) return rc;
   const int M = B * K;
-  onet_head_kernel<<<(M + 7) / 8, 256, 0, st>>>(w.act + (size_t)10 * M * kOH, w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+  onet_head_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.act + (size_t)10 * act_floats(M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
                                                dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, nullptr, grad_logits, 0, 0.f,
                                                0.f, w.g0, nullptr);
   IFD_LAUNCH_CHECK("onet_head_kernel");
@@ -667,13 +529,13 @@ extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz
   float* g_occ = opt_ws_gocc(conv_ws, B, K);
   const int M = B * K;
   const float ginv = (float)K / (float)((long long)P->B_ref * K);
-  const int n_dec = (M + 7) / 8;
+  const int n_dec = (M + 255) / 256;
   for (int i = 0; i < P->n_steps; ++i) {
     const bool stat = P->want_stats && stats_out && (i % 100 == 0);
     {
       ProfileScope ps(0, st);
       if ((rc = onet_forward(dec_weights, w, xyz, B, K, st))) return rc;
-      onet_head_kernel<<<n_dec, 256, 0, st>>>(w.act + (size_t)10 * M * kOH, w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+      onet_head_kernel<<<n_dec, 256, 0, st>>>(w.act + (size_t)10 * act_floats(M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
                                               dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, nullptr, nullptr, 1,
                                               (float)P->occ_target, ginv, w.g0, stat ? w.stat : nullptr);
       IFD_LAUNCH_CHECK("onet_head_kernel");
@@ -684,6 +546,3 @@ extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz
   return opt_finish(xyz, B, K, P->normalize_out, st, nullptr);
 }
 
-namespace ifd {
-void onet_set_engine(int on) { g_onet_engine = on ? 1 : 0; }
-}  // namespace ifd

@@ -1127,9 +1127,8 @@ extern "C" int ifd_convonet_grid_opt(const float* volume_cl, const float* dec_we
                       as_stream(stream), true);
 }
 
-namespace ifd { void onet_set_engine(int on); void tc_set_cluster(int n); }
+namespace ifd { void tc_set_cluster(int n); }
 extern "C" void ifd_test_hook(int key, int value) {
-  if (key == 5) onet_set_engine(value);
   if (key == 6) tc_set_cluster(value);
   if (key == 1) g_inbox_cap = value < 0 ? 0 : (value > kCsInbox ? kCsInbox : value);
   if (key == 2) g_lanes = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);

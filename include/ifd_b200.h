@@ -416,7 +416,6 @@ int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t st
  * parts).  Measurement knob: 3 / 4 lanes gave +1.6 / +2.4 % over 2 at B = 64 and were not adopted.
  * key 3: 0 = enqueue the loop of ifd_convonet_opt as direct launches, 1 (default) = replay the cached CUDA graph (same bits).
  * key 4: cluster barrier in front of cloud_step_kernel's first remote store: 0 none, 1 release / acquire, 2 (default) relaxed.
- * key 5: ONet decoder layers on 1 (default) the warp-specialised GEMM engine, 0 the first-generation kernel.
  * key 6: CTAs per thread-block cluster of the GEMM engine (1, 2 (default) or 4): weight chunks are TMA-multicast across it. */
 void ifd_test_hook(int key, int value);
 

@@ -381,3 +381,4 @@ def test_graph_replay_equals_direct_launches(conv, dec, planes):
     finally:
         L.ifd_test_hook(3, 1)
     assert np.array_equal(e, f)
+
