@@ -32,6 +32,7 @@ class TcLinearArgs(ctypes.Structure):
     _fields_ = [
         ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("n_seg", ctypes.c_int32),
         ("a_ptr", ctypes.c_void_p * 3), ("a_ld", ctypes.c_int32 * 3), ("a_width", ctypes.c_int32 * 3), ("a_relu", ctypes.c_int32 * 3),
+        ("a_blocked", ctypes.c_int32 * 3), ("out_blocked", ctypes.c_int32),
         ("a_group", ctypes.c_int32 * 3),
         ("wimg", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("resid", ctypes.c_void_p), ("ld_resid", ctypes.c_int32),
         ("relu_out", ctypes.c_int32), ("out", ctypes.c_void_p), ("ld_out", ctypes.c_int32),
@@ -68,7 +69,8 @@ SIGNATURES = {
     "ifd_tc_pack": (_c_int, [_vp, _c_int, ctypes.POINTER(ctypes.c_int), _c_int, _c_int, _vp, _vp]),
     "ifd_tc_linear": (_c_int, [ctypes.POINTER(TcLinearArgs), _vp]),
     "ifd_group_max": (_c_int, [_vp, _c_int, _c_int, _c_int, _vp, _vp]),
-    "ifd_tc_conv3x3": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _c_int, _vp, _vp]),
+    "ifd_tc_blocked_floats": (_c_sz, [ctypes.c_longlong, _c_int]),
+    "ifd_tc_conv3x3": (_c_int, [_vp, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _c_int, _c_int, _vp, _c_int, _vp]),
     "ifd_mc_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
     "ifd_mc_count": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _c_d, _vp, _c_sz,
                               ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), _vp]),

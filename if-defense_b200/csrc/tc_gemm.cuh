@@ -55,6 +55,12 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
       : "memory");
 }
+// Warp-transposed ("blocked") row layout for tensors the engine reads and writes thread-per-row: rows in blocks of 32, inside a
+// block the C / 4 float4 column groups one after the other, each holding its 32 rows contiguously.  The 32 lanes of a warp that
+// access "their row's float4 number q" then touch 512 contiguous bytes (4 L1 wavefronts) instead of 32 separate lines.
+// Buffers hold ceil(M / 32) * 32 rows.  Offset in float4 units:
+__host__ __device__ __forceinline__ size_t blk_off4(size_t m, int c4, int C4) { return ((m >> 5) * (size_t)C4 + (size_t)c4) * 32 + (m & 31); }
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
 }

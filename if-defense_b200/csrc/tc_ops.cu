@@ -31,6 +31,8 @@ struct LinearParams {
   const float* wimg;
   const float* a_ptr[3];     // up to three K segments, concatenated in this order
   int a_ld[3], a_w[3], a_relu[3], a_chunk0[3];      // row stride, width, ReLU on read, first chunk of the segment
+  int a_blocked[3];          // 1: the segment is stored in the warp-transposed layout (tc_gemm.cuh, blk_off4), width % 4 == 0
+  int out_blocked;           // 1: `out` (N % 4 == 0; with the pixel-shuffle epilogue: [B * 2H * 2W][cout]) is warp-transposed
   int a_group[3];            // > 0: the segment has one row per GROUP of a_group consecutive rows (a per-cloud vector that the
                              // reference expands over the cloud's points: ONet/im2mesh/encoder/pointnet.py:103-104)
   int n_seg;
@@ -51,6 +53,20 @@ struct LinearPolicy {
     if (P.n_seg > 1 && kc >= P.a_chunk0[1]) seg = 1;
     if (P.n_seg > 2 && kc >= P.a_chunk0[2]) seg = 2;
     const int k0 = (kc - P.a_chunk0[seg]) * kChunk;
+    if (P.a_blocked[seg]) {
+      const int C4 = P.a_w[seg] >> 2;
+      const float4* p4 = reinterpret_cast<const float4*>(P.a_ptr[seg]) + blk_off4((size_t)r.row, k0 >> 2, C4);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = (k0 >> 2) + q < C4 ? __ldg(p4 + q * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+      }
+      if (P.a_relu[seg]) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x[k] = fmaxf(x[k], 0.0f);
+      }
+      return;
+    }
     const int arow = P.a_group[seg] > 0 ? r.row / P.a_group[seg] : r.row;
     const float* p = P.a_ptr[seg] + (size_t)arow * P.a_ld[seg] + k0;
     const int w = P.a_w[seg] - k0;
@@ -74,11 +90,14 @@ struct LinearPolicy {
       const int q = col0 / P.shuffle_cout, co = col0 % P.shuffle_cout;
       const int hw = P.shuffle_H * P.shuffle_W;
       const int b = r.row / hw, yy = (r.row % hw) / P.shuffle_W, xx = r.row % P.shuffle_W;
-      float* o = P.out + ((((size_t)b * 2 * P.shuffle_H + 2 * yy + (q >> 1)) * 2 * P.shuffle_W) + 2 * xx + (q & 1)) * P.shuffle_cout + co;
+      const size_t opix = (((size_t)b * 2 * P.shuffle_H + 2 * yy + (q >> 1)) * 2 * P.shuffle_W) + 2 * xx + (q & 1);
+      float4* o4 = P.out_blocked ? reinterpret_cast<float4*>(P.out) + blk_off4(opix, co >> 2, P.shuffle_cout >> 2)
+                                 : reinterpret_cast<float4*>(P.out + opix * P.shuffle_cout + co);
+      const int ostep = P.out_blocked ? 32 : 1;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float4 bv = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + co) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(o)[g] = make_float4(y[4 * g] + bv.x, y[4 * g + 1] + bv.y, y[4 * g + 2] + bv.z, y[4 * g + 3] + bv.w);
+        o4[g * ostep] = make_float4(y[4 * g] + bv.x, y[4 * g + 1] + bv.y, y[4 * g + 2] + bv.z, y[4 * g + 3] + bv.w);
       }
       return;
     }
@@ -95,6 +114,13 @@ struct LinearPolicy {
     if (P.relu_out) {
 #pragma unroll
       for (int k = 0; k < 32; ++k) y[k] = fmaxf(y[k], 0.0f);
+    }
+    if (P.out_blocked) {
+      float4* o4 = reinterpret_cast<float4*>(P.out) + blk_off4((size_t)r.row, col0 >> 2, P.N >> 2);
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (4 * g < n_here) o4[g * 32] = make_float4(y[4 * g], y[4 * g + 1], y[4 * g + 2], y[4 * g + 3]);
+      return;
     }
     float* o = P.out + (size_t)r.row * P.ld_out + col0;
     if (n_here == 32 && (P.ld_out & 3) == 0) {
@@ -115,6 +141,7 @@ struct ConvParams {
   const float* src0;       // [B][H][W][C0], or [B][2H][2W][C0] when pool
   const float* src1;       // [B][H][W][C1] second half of the channel concatenation, or null
   int C0, C1, H, W, pool, cpt;      // cpt = (C0 + C1) / 32 chunks per tap
+  int blk0, blk1, blk_out;          // 1: src0 / src1 / out are in the warp-transposed layout (tc_gemm.cuh, blk_off4)
   const float* bias;
   int relu_out, N;
   float* out;              // [B][H][W][N]
@@ -126,39 +153,52 @@ struct ConvPolicy {
     const int hw = P.H * P.W;
     return Row{row, row / hw, (row % hw) / P.W, row % P.W};
   }
+  // 32 channels c .. c + 31 of pixel `pix` of a [n_pix][C] tensor in either layout
+  static __device__ __forceinline__ void load_px(const float* __restrict__ src, size_t pix, int C, int c, int blocked, float (&x)[32]) {
+    const float4* p4 = blocked ? reinterpret_cast<const float4*>(src) + blk_off4(pix, c >> 2, C >> 2)
+                               : reinterpret_cast<const float4*>(src + pix * C + c);
+    const int step = blocked ? 32 : 1;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = __ldg(p4 + q * step);
+      x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+  }
   static __device__ __forceinline__ void load(const Params& P, const Row& r, int kc, float (&x)[32]) {
     const int tap = kc / P.cpt, c = (kc % P.cpt) * kChunk;
     const int yy = r.y + tap / 3 - 1, xx = r.x + tap % 3 - 1;
     if (r.row >= P.M || yy < 0 || yy >= P.H || xx < 0 || xx >= P.W) return zero32(x);
     if (P.pool) {            // F.max_pool2d(x, 2, 2) of the level above, taken on read
       const int W2 = 2 * P.W;
-      const float* p = P.src0 + (((size_t)r.b * 2 * P.H + 2 * yy) * W2 + 2 * xx) * P.C0 + c;
+      const size_t p00 = ((size_t)r.b * 2 * P.H + 2 * yy) * W2 + 2 * xx;
       float t[32];
-      load32(p, x);
-      load32(p + P.C0, t);
+      load_px(P.src0, p00, P.C0, c, P.blk0, x);
+      load_px(P.src0, p00 + 1, P.C0, c, P.blk0, t);
 #pragma unroll
       for (int k = 0; k < 32; ++k) x[k] = fmaxf(x[k], t[k]);
-      load32(p + (size_t)W2 * P.C0, t);
+      load_px(P.src0, p00 + W2, P.C0, c, P.blk0, t);
 #pragma unroll
       for (int k = 0; k < 32; ++k) x[k] = fmaxf(x[k], t[k]);
-      load32(p + (size_t)W2 * P.C0 + P.C0, t);
+      load_px(P.src0, p00 + W2 + 1, P.C0, c, P.blk0, t);
 #pragma unroll
       for (int k = 0; k < 32; ++k) x[k] = fmaxf(x[k], t[k]);
       return;
     }
     const size_t pix = ((size_t)r.b * P.H + yy) * P.W + xx;
-    if (c < P.C0) load32(P.src0 + pix * P.C0 + c, x);
-    else load32(P.src1 + pix * P.C1 + (c - P.C0), x);
+    if (c < P.C0) load_px(P.src0, pix, P.C0, c, P.blk0, x);
+    else load_px(P.src1, pix, P.C1, c - P.C0, P.blk1, x);
   }
   static __device__ __forceinline__ void store(const Params& P, const Row& r, int col0, const float (&y)[32]) {
     if (r.row >= P.M || col0 >= P.N) return;
-    float* o = P.out + (size_t)r.row * P.N + col0;
+    float4* o4 = P.blk_out ? reinterpret_cast<float4*>(P.out) + blk_off4((size_t)r.row, col0 >> 2, P.N >> 2)
+                           : reinterpret_cast<float4*>(P.out + (size_t)r.row * P.N + col0);
+    const int step = P.blk_out ? 32 : 1;
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const float4 bv = __ldg(reinterpret_cast<const float4*>(P.bias + col0) + g);
       float4 v = make_float4(y[4 * g] + bv.x, y[4 * g + 1] + bv.y, y[4 * g + 2] + bv.z, y[4 * g + 3] + bv.w);
       if (P.relu_out) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-      reinterpret_cast<float4*>(o)[g] = v;
+      o4[g * step] = v;
     }
   }
 };
@@ -180,6 +220,11 @@ __global__ void group_max_kernel(const float* __restrict__ x, int T, int C, floa
 using namespace ifd;
 
 static int seg_chunks(int w) { return (w + tc::kChunk - 1) / tc::kChunk; }
+
+extern "C" size_t ifd_tc_blocked_floats(long long M, int C) {
+  if (M <= 0 || C <= 0 || (C & 3)) return 0;
+  return (size_t)((M + 31) / 32) * 32 * (size_t)C;
+}
 
 extern "C" size_t ifd_tc_packed_floats(int N, const int* seg_widths, int n_seg) {
   if (N <= 0 || !seg_widths || n_seg < 1 || n_seg > 3) return 0;
@@ -228,12 +273,15 @@ extern "C" int ifd_tc_linear(const ifd_tc_linear_args* a, ifd_stream_t stream) {
     IFD_REQUIRE(((uintptr_t)a->a_ptr[s] & 15) == 0 || (a->a_ld[s] & 3) != 0, "ifd_tc_linear: A segments must be 16-byte aligned");
     P.a_ptr[s] = a->a_ptr[s]; P.a_ld[s] = a->a_ld[s]; P.a_w[s] = a->a_width[s]; P.a_relu[s] = a->a_relu[s]; P.a_chunk0[s] = c0;
     P.a_group[s] = a->a_group[s] > 0 ? a->a_group[s] : 0;
+    P.a_blocked[s] = a->a_blocked[s] ? 1 : 0;
+    IFD_REQUIRE(!P.a_blocked[s] || ((a->a_width[s] & 3) == 0 && !P.a_group[s]), "ifd_tc_linear: a blocked segment needs width % 4 == 0 and no grouping");
     c0 += seg_chunks(a->a_width[s]);
   }
   P.n_seg = a->n_seg; P.n_chunks = c0;
   P.bias = a->bias; P.resid = a->resid; P.ld_resid = a->ld_resid; P.relu_out = a->relu_out;
-  P.out = a->out; P.ld_out = a->ld_out;
-  IFD_REQUIRE(a->ld_out >= a->N || a->shuffle_cout > 0, "ifd_tc_linear: ld_out < N");
+  P.out = a->out; P.ld_out = a->ld_out; P.out_blocked = a->out_blocked ? 1 : 0;
+  IFD_REQUIRE(!P.out_blocked || ((a->N & 3) == 0 && !a->resid), "ifd_tc_linear: a blocked output needs N % 4 == 0 and no residual");
+  IFD_REQUIRE(a->ld_out >= a->N || a->shuffle_cout > 0 || a->out_blocked, "ifd_tc_linear: ld_out < N");
   IFD_REQUIRE(((uintptr_t)a->wimg & 15) == 0 && ((uintptr_t)a->out & 15) == 0, "ifd_tc_linear: wimg / out must be 16-byte aligned");
   if (a->shuffle_cout > 0) {
     IFD_REQUIRE(a->shuffle_cout % 32 == 0 && a->N == 4 * a->shuffle_cout && a->shuffle_H > 0 && a->shuffle_W > 0 &&
@@ -245,7 +293,7 @@ extern "C" int ifd_tc_linear(const ifd_tc_linear_args* a, ifd_stream_t stream) {
 }
 
 extern "C" int ifd_tc_conv3x3(const float* src0, int C0, const float* src1, int C1, int B, int H, int W, int pool, const float* wimg,
-                              const float* bias, int relu_out, int Cout, float* out, ifd_stream_t stream) {
+                              const float* bias, int relu_out, int Cout, float* out, int layout, ifd_stream_t stream) {
   IFD_REQUIRE(src0 && wimg && bias && out && B > 0 && H > 0 && W > 0 && Cout > 0, "ifd_tc_conv3x3: bad arguments");
   IFD_REQUIRE(C0 > 0 && C0 % 32 == 0 && C1 >= 0 && C1 % 32 == 0 && Cout % 32 == 0, "ifd_tc_conv3x3: channel counts must be multiples of 32");
   IFD_REQUIRE((C1 == 0) == (src1 == nullptr) && !(pool && C1), "ifd_tc_conv3x3: bad source combination");
@@ -255,6 +303,7 @@ extern "C" int ifd_tc_conv3x3(const float* src0, int C0, const float* src1, int 
   const int NT = tc::pick_nt(Cout);
   P.M = B * H * W; P.N = Cout; P.n_tiles_n = (Cout + NT - 1) / NT; P.wimg = wimg;
   P.src0 = src0; P.src1 = src1; P.C0 = C0; P.C1 = C1; P.H = H; P.W = W; P.pool = pool ? 1 : 0;
+  P.blk0 = layout & 1; P.blk1 = (layout >> 1) & 1; P.blk_out = (layout >> 2) & 1;
   P.cpt = (C0 + C1) / 32; P.n_chunks = 9 * P.cpt;
   P.bias = bias; P.relu_out = relu_out; P.out = out;
   return tc::launch<tc::ConvPolicy>(P, NT, as_stream(stream));

@@ -146,25 +146,28 @@ class UNet(nn.Module):
         if not hasattr(self, "_tc_cache"):
             self._tc_cache = _PackedCache()
         pk = self._tc_cache.get(self, lambda: self._pack(tc))
+        # every intermediate feature map lives in the engine's warp-transposed layout (tc.Blocked): only the engine touches them,
+        # and its thread-per-pixel accesses are coalesced there; input and output stay plain channels-last
         skips = []
         for i, d in enumerate(self.down_convs):
             (w1, b1), (w2, b2) = pk["down"][i]
-            x = tc.conv3x3(x, w1, b1, d.conv1.out_channels, pool=i > 0)
-            x = tc.conv3x3(x, w2, b2, d.conv2.out_channels)
+            x = tc.conv3x3(x, w1, b1, d.conv1.out_channels, pool=i > 0, blocked_out=True)
+            x = tc.conv3x3(x, w2, b2, d.conv2.out_channels, blocked_out=True)
             skips.append(x)
         for i, u in enumerate(self.up_convs):
             (wt, bt), (w1, b1), (w2, b2) = pk["up"][i]
-            B, H, W, cin = x.shape
-            cout = u.upconv.out_channels
-            up = tc.linear([(x.view(B * H * W, cin), cin, False)], wt, 4 * cout, bias=bt, shuffle=(cout, H, W))
-            x = tc.conv3x3(up, w1, b1, cout, src1=skips[-(i + 2)])
-            x = tc.conv3x3(x, w2, b2, cout)
-        B, H, W, c = x.shape
+            B, H, W = x.dims
+            cin, cout = x.C, u.upconv.out_channels
+            up = tc.Blocked(B * 4 * H * W, cout, x.buf.device, dims=(B, 2 * H, 2 * W))
+            tc.linear([(x, cin, False)], wt, 4 * cout, bias=bt, shuffle=(cout, H, W), out=up)
+            x = tc.conv3x3(up, w1, b1, cout, src1=skips[-(i + 2)], blocked_out=True)
+            x = tc.conv3x3(x, w2, b2, cout, blocked_out=True)
+        B, H, W = x.dims
         wf, bf = pk["final"]
         ncls = self.conv_final.out_channels
         if out is None:
-            out = torch.empty((B, H, W, ncls), dtype=torch.float32, device=x.device)
-        tc.linear([(x.view(B * H * W, c), c, False)], wf, ncls, bias=bf, out=out.view(B * H * W, ncls))
+            out = torch.empty((B, H, W, ncls), dtype=torch.float32, device=x.buf.device)
+        tc.linear([(x, x.C, False)], wf, ncls, bias=bf, out=out.view(B * H * W, ncls))
         return out
 
     def forward(self, x):

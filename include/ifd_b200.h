@@ -180,6 +180,8 @@ typedef struct ifd_tc_linear_args {
   int32_t a_ld[3];           /* row strides in floats */
   int32_t a_width[3];        /* columns used of each segment (= the widths given to ifd_tc_pack) */
   int32_t a_relu[3];         /* 1: the segment passes through ReLU on read (fc(relu(x))) */
+  int32_t a_blocked[3];      /* 1: the segment is in the warp-transposed layout (see ifd_tc_blocked_floats), width % 4 == 0 */
+  int32_t out_blocked;       /* 1: out is in the warp-transposed layout (N % 4 == 0, no resid) */
   int32_t a_group[3];        /* > 0: the segment holds one row per group of a_group consecutive rows (a per-cloud vector
                                 expanded over the cloud's points on read); 0: one row per output row */
   const float* wimg;         /* packed weights */
@@ -195,6 +197,13 @@ typedef struct ifd_tc_linear_args {
 } ifd_tc_linear_args;
 int ifd_tc_linear(const ifd_tc_linear_args* args, ifd_stream_t stream);
 
+/* The engine reads and writes tensors thread-per-row; intermediate tensors that only the engine touches (the U-Net's feature
+ * maps) can therefore live in a WARP-TRANSPOSED layout in which those accesses are coalesced: rows (pixels) in blocks of 32,
+ * inside a block the C / 4 float4 column groups one after the other, each holding its 32 rows contiguously.  A tensor of M
+ * rows x C columns (C % 4 == 0) occupies ifd_tc_blocked_floats(M, C) floats; element (m, c) sits at float offset
+ * (((m / 32) * (C / 4) + c / 4) * 32 + m % 32) * 4 + c % 4. */
+size_t ifd_tc_blocked_floats(long long M, int C);
+
 /* out[g][c] = max_t x[g * T + t][c]: the global max-pool of ResnetPointnet (ONet/im2mesh/encoder/pointnet.py:103,110). */
 int ifd_group_max(const float* x, int groups, int T, int C, float* out, ifd_stream_t stream);
 
@@ -202,9 +211,10 @@ int ifd_group_max(const float* x, int groups, int T, int C, float* out, ifd_stre
  * [src0 | src1] (torch.cat((from_up, from_down), 1), unet.py:187; src1 = NULL, C1 = 0 for a single input) of
  * [B][H][W][C] tensors; with pool != 0 the input is F.max_pool2d(src0, 2, 2) of a [B][2H][2W][C0] tensor, taken on read
  * (unet.py:151).  wimg = ifd_tc_pack of the weight as [Cout][9 * (C0 + C1)] with k = (ky * 3 + kx) * (C0 + C1) + ci.
- * Channel counts are multiples of 32.  out [B][H][W][Cout]. */
+ * Channel counts are multiples of 32.  out [B][H][W][Cout].  layout: bit 0 / 1 / 2 = src0 / src1 / out are in the
+ * warp-transposed layout (rows = pixels in [b][y][x] order) instead of plain channels-last. */
 int ifd_tc_conv3x3(const float* src0, int C0, const float* src1, int C1, int B, int H, int W, int pool, const float* wimg,
-                   const float* bias, int relu_out, int Cout, float* out, ifd_stream_t stream);
+                   const float* bias, int relu_out, int Cout, float* out, int layout, ifd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * The restoration loop

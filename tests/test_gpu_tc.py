@@ -86,6 +86,11 @@ def test_conv3x3_vs_float64(B, H, W, C0, C1, Cout, pool, cluster):
     err = float(((got.double() - want).abs() / scale).max())
     print("conv K = %d: max error / sum|a||w| = %.2e, max abs error %.2e" % (9 * (C0 + C1), err, float((got.double() - want).abs().max())))
     assert err < 2e-6
+    # the same convolution on feature maps in the engine's warp-transposed layout: the same bits
+    ab = tc.Blocked.from_rows(a)
+    bb = tc.Blocked.from_rows(b) if b is not None else None
+    gotb = tc.conv3x3(ab, tc.pack(w.permute(0, 2, 3, 1).reshape(Cout, -1)), bias, Cout, src1=bb, pool=pool, relu=True, blocked_out=True)
+    assert gotb.dims == (B, H, W) and torch.equal(gotb.to_rows().view(B, H, W, Cout), got)
 
 
 def test_convtranspose_and_unet_vs_torch(cluster):
@@ -96,6 +101,10 @@ def test_convtranspose_and_unet_vs_torch(cluster):
                     shuffle=(cout, H, W))
     want = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), stride=2).permute(0, 2, 3, 1)
     assert got.shape == (B, 2 * H, 2 * W, cout) and float((got.double() - want).abs().max()) < 1e-5
+    upb = tc.Blocked(B * 4 * H * W, cout, x.device, dims=(B, 2 * H, 2 * W))
+    tc.linear([(tc.Blocked.from_rows(x), cin, False)], tc.pack(w.permute(2, 3, 1, 0).reshape(4 * cout, cin)), 4 * cout, bias=bias,
+              shuffle=(cout, H, W), out=upb)
+    assert torch.equal(upb.to_rows().view(B, 2 * H, 2 * W, cout), got)
     # the whole U-Net of the shipped config (depth 4, 32 -> 256 channels) against the float64 torch forward
     torch.manual_seed(0)
     net = models.UNet(32, in_channels=32, depth=4, start_filts=32).cuda().eval()
