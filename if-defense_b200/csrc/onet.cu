@@ -12,8 +12,9 @@
 //   Y[M][256] = (G[M][256] . W) * s_b * [s_b * Xsaved + t_b > 0]  (+ residual)        dgrad through CBN+ReLU
 // Every layer runs on the shared warp-specialised GEMM engine (tc_gemm.cuh: A producers with the CBN + ReLU prologue, weight
 // chunks [256 x 32] hi/lo by TMA bulk copies multicast across a 2-CTA cluster, twelve tcgen05.mma per chunk into one of two
-// TMEM accumulator stages, epilogue warps with bias / residual / dgrad mask).  Activations of the forward pass are kept
-// in HBM (11 x [M][256] fp32, warp-transposed layout, see act_off4) for the dgrad masks -- 740 MB at B=64, K=1024.
+// TMEM accumulator stages, epilogue warps with bias / residual / dgrad mask).  The forward pass keeps three activation tensors
+// ([M][256] fp32, warp-transposed layout, see act_off4: net ping, h, net pong) and, for the dgrad, one sign bit per CBN
+// pre-activation (10 layers x 32 B per row = 21 MB at B=64, K=1024, instead of the 740 MB of the activations themselves).
 #include "common.cuh"
 #include "ifd_math.cuh"
 #include "tc_gemm.cuh"
@@ -95,9 +96,10 @@ struct GemmArgs {
   const float* img;      // packed weight images of this layer / direction
   const float* bias;     // [256] or nullptr
   const float* resid;    // [M][256] or nullptr
-  const float* mask_x;   // dgrad epilogue: saved forward activation [M][256] (nullptr: plain epilogue)
-  const float* mask_s;   // [B][256]
-  const float* mask_t;   // [B][256]
+  uint32_t* mask_out;    // forward prologue: sign bits of the CBN pre-activations it forms, one word per (row, 32-column chunk):
+                         // word of (row m, chunk c) at ((m / 32) * 8 + c) * 32 + m % 32  (nullptr: not recorded)
+  const uint32_t* mask_bits;   // dgrad epilogue: those bits of the layer being differentiated (nullptr: plain epilogue)
+  const float* mask_s;   // [B][256] the CBN scale that goes with them
   float* out;            // [M][256]
   int M, K;              // rows, points per cloud
 };
@@ -132,14 +134,21 @@ struct OnetLayerPolicy {
     if (P.g.pro_s) {                    // CBN (eval mode, folded) + ReLU on read
       const float4* s4 = reinterpret_cast<const float4*>(P.g.pro_s + (size_t)r.b * kOH + kc * kChunk);
       const float4* t4 = reinterpret_cast<const float4*>(P.g.pro_t + (size_t)r.b * kOH + kc * kChunk);
+      uint32_t m = 0;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 s = __ldg(s4 + q), t = __ldg(t4 + q);
-        x[4 * q + 0] = fmaxf(fmaf(s.x, x[4 * q + 0], t.x), 0.0f);
-        x[4 * q + 1] = fmaxf(fmaf(s.y, x[4 * q + 1], t.y), 0.0f);
-        x[4 * q + 2] = fmaxf(fmaf(s.z, x[4 * q + 2], t.z), 0.0f);
-        x[4 * q + 3] = fmaxf(fmaf(s.w, x[4 * q + 3], t.w), 0.0f);
+        const float p0 = fmaf(s.x, x[4 * q + 0], t.x), p1 = fmaf(s.y, x[4 * q + 1], t.y);
+        const float p2 = fmaf(s.z, x[4 * q + 2], t.z), p3 = fmaf(s.w, x[4 * q + 3], t.w);
+        m |= (p0 > 0.0f ? 1u : 0u) << (4 * q) | (p1 > 0.0f ? 1u : 0u) << (4 * q + 1) | (p2 > 0.0f ? 1u : 0u) << (4 * q + 2) |
+             (p3 > 0.0f ? 1u : 0u) << (4 * q + 3);
+        x[4 * q + 0] = fmaxf(p0, 0.0f);
+        x[4 * q + 1] = fmaxf(p1, 0.0f);
+        x[4 * q + 2] = fmaxf(p2, 0.0f);
+        x[4 * q + 3] = fmaxf(p3, 0.0f);
       }
+      // the dgrad needs nothing of this activation but these signs: 32 bytes per row and layer instead of the 1 KB row itself
+      if (P.g.mask_out) P.g.mask_out[((size_t)(r.row >> 5) * 8 + kc) * 32 + (r.row & 31)] = m;
     }
   }
   static __device__ __forceinline__ void store(const Params& P, const Row& r, int col0, const float (&y_in)[32]) {
@@ -155,17 +164,16 @@ struct OnetLayerPolicy {
 #pragma unroll
       for (int q = 0; q < 8; ++q) rv[q] = r4[q * 32];
     }
-    if (a.mask_x) {                     // dgrad through relu(s * x + t): scale by s where the pre-activation was positive
-      const float4* x4 = reinterpret_cast<const float4*>(a.mask_x) + off;
+    if (a.mask_bits) {                  // dgrad through relu(s * x + t): scale by s where the pre-activation was positive
+      const uint32_t m = __ldg(a.mask_bits + ((size_t)(r.row >> 5) * 8 + (col0 >> 5)) * 32 + (r.row & 31));
       const float4* s4 = reinterpret_cast<const float4*>(a.mask_s + (size_t)r.b * kOH + col0);
-      const float4* t4 = reinterpret_cast<const float4*>(a.mask_t + (size_t)r.b * kOH + col0);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 xs = __ldg(x4 + q * 32), s = __ldg(s4 + q), t = __ldg(t4 + q);
-        y[4 * q + 0] = fmaf(s.x, xs.x, t.x) > 0.0f ? y[4 * q + 0] * s.x : 0.0f;
-        y[4 * q + 1] = fmaf(s.y, xs.y, t.y) > 0.0f ? y[4 * q + 1] * s.y : 0.0f;
-        y[4 * q + 2] = fmaf(s.z, xs.z, t.z) > 0.0f ? y[4 * q + 2] * s.z : 0.0f;
-        y[4 * q + 3] = fmaf(s.w, xs.w, t.w) > 0.0f ? y[4 * q + 3] * s.w : 0.0f;
+        const float4 s = __ldg(s4 + q);
+        y[4 * q + 0] = ((m >> (4 * q + 0)) & 1u) ? y[4 * q + 0] * s.x : 0.0f;
+        y[4 * q + 1] = ((m >> (4 * q + 1)) & 1u) ? y[4 * q + 1] * s.y : 0.0f;
+        y[4 * q + 2] = ((m >> (4 * q + 2)) & 1u) ? y[4 * q + 2] * s.z : 0.0f;
+        y[4 * q + 3] = ((m >> (4 * q + 3)) & 1u) ? y[4 * q + 3] * s.w : 0.0f;
       }
     }
     if (a.bias) {
@@ -318,7 +326,8 @@ struct OnetWs {
   float* img;      // [2 dirs][10 layers][kLayerImgFloats]
   float* s;        // [11][B][256]
   float* t;
-  float* act;      // [11][M][256]: net_0, h_0, net_1, h_1, ..., net_4, h_4, net_5
+  float* act;      // [3][M][256] (warp-transposed): net ping, h, net pong -- the dgrad needs only sign bits of them
+  uint32_t* mask;  // [10 layers][M / 32][8 chunks][32 rows]: sign bits of the CBN pre-activation each layer's prologue forms
   float* g0;       // [M][256] gradient ping
   float* g1;       // [M][256] gradient pong
   double* stat;    // [M/8 blocks][2]
@@ -337,7 +346,8 @@ OnetWs carve_onet(void* base, int B, int K) {
   w.s = (float*)take((size_t)kOnetCbn * B * kOH * 4);
   w.t = (float*)take((size_t)kOnetCbn * B * kOH * 4);
   const size_t MH = act_floats((int)M);       // rows padded to whole 32-row blocks of the warp-transposed layout
-  w.act = (float*)take((size_t)11 * MH * 4);
+  w.act = (float*)take((size_t)3 * MH * 4);
+  w.mask = (uint32_t*)take((size_t)10 * (MH / kOH) * 8 * 4);
   w.g0 = (float*)take(MH * 4);
   w.g1 = (float*)take(MH * 4);
   w.stat = (double*)take(((M + 255) / 256) * 2 * sizeof(double));
@@ -402,21 +412,25 @@ extern "C" int ifd_onet_prepare(const float* dec_weights, const float* c, int B,
 }
 
 namespace {
-// forward through the decoder; activations land in w.act.  Returns through logits_out (optional).
-int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K, cudaStream_t st) {
+// forward through the decoder.  net ping-pongs between act slots 0 and 2 (net_5 ends in slot 2, see onet_net5), h lives in slot 1;
+// the sign bits of every CBN pre-activation go to w.mask[layer] when `masks` (the dgrad needs nothing else of the activations).
+inline float* onet_net5(const OnetWs& w, int M) { return w.act + (size_t)2 * act_floats(M); }
+inline uint32_t* onet_mask(const OnetWs& w, int M, int layer) { return w.mask + (size_t)layer * (act_floats(M) / kOH) * 8; }
+int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K, bool masks, cudaStream_t st) {
   const int M = B * K;
   const size_t MH = act_floats(M);
   onet_fcp_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xyz, W, W + kOH * 3, M, w.act);
   IFD_LAUNCH_CHECK("onet_fcp_kernel");
   for (int blk = 0; blk < 5; ++blk) {
-    float* net = w.act + (size_t)(2 * blk) * MH;
-    float* h = w.act + (size_t)(2 * blk + 1) * MH;
-    float* net_next = w.act + (size_t)(2 * blk + 2) * MH;
+    float* net = w.act + (size_t)((blk & 1) ? 2 : 0) * MH;
+    float* h = w.act + MH;
+    float* net_next = w.act + (size_t)((blk & 1) ? 0 : 2) * MH;
     GemmArgs a{};
     a.M = M; a.K = K;
     a.A = net; a.pro_s = w.s + (size_t)(2 * blk) * B * kOH; a.pro_t = w.t + (size_t)(2 * blk) * B * kOH;
     a.img = w.img + (size_t)(2 * blk) * kLayerImgFloats;
     a.bias = W + kOffFc + (2 * blk) * kFcFloats + (size_t)kOH * kOH;
+    a.mask_out = masks ? onet_mask(w, M, 2 * blk) : nullptr;
     a.out = h;
     int rc = launch_gemm(a, st);
     if (rc) return rc;
@@ -425,6 +439,7 @@ int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K
     c.A = h; c.pro_s = w.s + (size_t)(2 * blk + 1) * B * kOH; c.pro_t = w.t + (size_t)(2 * blk + 1) * B * kOH;
     c.img = w.img + (size_t)(2 * blk + 1) * kLayerImgFloats;
     c.bias = W + kOffFc + (2 * blk + 1) * kFcFloats + (size_t)kOH * kOH;
+    c.mask_out = masks ? onet_mask(w, M, 2 * blk + 1) : nullptr;
     c.resid = net;
     c.out = net_next;
     if ((rc = launch_gemm(c, st))) return rc;
@@ -434,23 +449,20 @@ int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K
 // dgrad from g_net5 (in w.g0) down to grad_xyz
 int onet_backward(const float* W, const OnetWs& w, int B, int K, float* grad_xyz, cudaStream_t st) {
   const int M = B * K;
-  const size_t MH = act_floats(M);
   float* gnet = w.g0;
   float* gtmp = w.g1;
   for (int blk = 4; blk >= 0; --blk) {
-    const float* net = w.act + (size_t)(2 * blk) * MH;
-    const float* h = w.act + (size_t)(2 * blk + 1) * MH;
     GemmArgs a{};                                   // g_h = (g_net . W1) * s1 * [cbn1(h) > 0]
     a.M = M; a.K = K; a.A = gnet;
     a.img = w.img + ((size_t)10 + 2 * blk + 1) * kLayerImgFloats;
-    a.mask_x = h; a.mask_s = w.s + (size_t)(2 * blk + 1) * B * kOH; a.mask_t = w.t + (size_t)(2 * blk + 1) * B * kOH;
+    a.mask_bits = onet_mask(w, M, 2 * blk + 1); a.mask_s = w.s + (size_t)(2 * blk + 1) * B * kOH;
     a.out = gtmp;
     int rc = launch_gemm(a, st);
     if (rc) return rc;
     GemmArgs c{};                                   // g_net = g_net + (g_h . W0) * s0 * [cbn0(net) > 0]   (in place on gnet)
     c.M = M; c.K = K; c.A = gtmp;
     c.img = w.img + ((size_t)10 + 2 * blk) * kLayerImgFloats;
-    c.mask_x = net; c.mask_s = w.s + (size_t)(2 * blk) * B * kOH; c.mask_t = w.t + (size_t)(2 * blk) * B * kOH;
+    c.mask_bits = onet_mask(w, M, 2 * blk); c.mask_s = w.s + (size_t)(2 * blk) * B * kOH;
     c.resid = gnet;
     c.out = gnet;                                   // each thread reads and writes only its own row chunk
     if ((rc = launch_gemm(c, st))) return rc;
@@ -469,10 +481,10 @@ extern "C" int ifd_onet_decode_fwd(const float* dec_weights, const float* xyz, i
   if (workspace_bytes < ifd_onet_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_onet_decode_fwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   OnetWs w = carve_onet(workspace, B, K);
-  int rc = onet_forward(dec_weights, w, xyz, B, K, st);
+  int rc = onet_forward(dec_weights, w, xyz, B, K, false, st);
   if (rc) return rc;
   const int M = B * K;
-  onet_head_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.act + (size_t)10 * act_floats(M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+  onet_head_kernel<<<(M + 255) / 256, 256, 0, st>>>(onet_net5(w, M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
                                                dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, logits_out, nullptr, 0, 0.f,
                                                0.f, nullptr, nullptr);
   IFD_LAUNCH_CHECK("onet_head_kernel");
@@ -486,10 +498,10 @@ extern "C" int ifd_onet_decode_bwd(const float* dec_weights, const float* xyz, c
   if (workspace_bytes < ifd_onet_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_onet_decode_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   OnetWs w = carve_onet(workspace, B, K);
-  int rc = onet_forward(dec_weights, w, xyz, B, K, st);
+  int rc = onet_forward(dec_weights, w, xyz, B, K, true, st);
   if (rc) return rc;
   const int M = B * K;
-  onet_head_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.act + (size_t)10 * act_floats(M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+  onet_head_kernel<<<(M + 255) / 256, 256, 0, st>>>(onet_net5(w, M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
                                                dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, nullptr, grad_logits, 0, 0.f,
                                                0.f, w.g0, nullptr);
   IFD_LAUNCH_CHECK("onet_head_kernel");
@@ -534,8 +546,8 @@ extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz
     const bool stat = P->want_stats && stats_out && (i % 100 == 0);
     {
       ProfileScope ps(0, st);
-      if ((rc = onet_forward(dec_weights, w, xyz, B, K, st))) return rc;
-      onet_head_kernel<<<n_dec, 256, 0, st>>>(w.act + (size_t)10 * act_floats(M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
+      if ((rc = onet_forward(dec_weights, w, xyz, B, K, true, st))) return rc;
+      onet_head_kernel<<<n_dec, 256, 0, st>>>(onet_net5(w, M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
                                               dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, nullptr, nullptr, 1,
                                               (float)P->occ_target, ginv, w.g0, stat ? w.stat : nullptr);
       IFD_LAUNCH_CHECK("onet_head_kernel");
