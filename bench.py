@@ -433,6 +433,15 @@ def main():
         case = synth.make_case(B, K=K, seed=100 * rank + j, device="cuda", sd=sd)
         sd = case.sd
         planes_cl = convonet.planes_to_channels_last({k: v.cuda() for k, v in case.c.items()})
+        if os.environ.get("IFD_EXP_MORTON"):     # experiment: points of a cloud in Morton order
+            import numpy as np
+            q = np.clip(((case.p0.numpy() / 1.1 + 0.5) * 1024).astype(np.int64), 0, 1023)
+            def part(v):
+                v = (v | (v << 16)) & 0x30000ff; v = (v | (v << 8)) & 0x300f00f; v = (v | (v << 4)) & 0x30c30c3; v = (v | (v << 2)) & 0x9249249
+                return v
+            code = part(q[..., 0]) | (part(q[..., 1]) << 1) | (part(q[..., 2]) << 2)
+            order = torch.from_numpy(np.argsort(code, axis=1))
+            case.p0 = torch.gather(case.p0, 1, order[..., None].expand(-1, -1, 3)).contiguous()
         batches.append((case, planes_cl, case.p0.cuda()))
     dec = convonet.ConvONetDecoder(sd, padding=0.1)
     C, H, nb = dec.dims

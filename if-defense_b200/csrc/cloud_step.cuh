@@ -135,27 +135,51 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
   // ---- all global reads happen here, coalesced over the flat [K][3] arrays (both CTAs read the whole cloud)
   const size_t cloud3 = (size_t)b * K * 3;
   float* xs = reinterpret_cast<float*>(&S.inbox[0][0]);        // xyz staging (the inbox is not in use yet)
-  for (int e = i; e < 3 * K; e += kCsThreads) {
-    xs[e] = g_xyz[cloud3 + e];
-    S.gmv[0][e] = g_gocc[cloud3 + e];
-    S.gmv[1][e] = a.zero_mv ? 0.0f : g_m[cloud3 + e];
-    S.gmv[2][e] = a.zero_mv ? 0.0f : g_v[cloud3 + e];
-  }
-  if (live && a.warm) {                                        // previous lists -> 16-bit rows
-    const int4* pv = reinterpret_cast<const int4*>(g_nbr + ((size_t)b * K + i) * kCsKK);
-    const int4 p0 = pv[0], p1 = pv[1];
-    const int prev[kCsKK] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-    uint32_t w[4];
+  // (every load is issued before the first shared-memory store: the kernel starts with a cold L1, so what this phase costs is
+  // L2 round trips -- one, not one per array and iteration; ncu had 22 % of the kernel's warp time on this loop)
+  {
+    static_assert(3 * kCsMaxK == 3 * kCsThreads, "three elements per thread and array");
+    float rx[3], rg[3], rm[3], rv[3];
+    int4 p0 = make_int4(0, 0, 0, 0), p1 = p0;
+    const bool have_mv = !a.zero_mv;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const int e0 = (unsigned)prev[2 * s] < (unsigned)K ? prev[2 * s] : i;
-      const int e1 = (unsigned)prev[2 * s + 1] < (unsigned)K ? prev[2 * s + 1] : i;
-      w[s] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+    for (int u = 0; u < 3; ++u) {
+      const int e = i + u * kCsThreads;
+      const bool in = e < 3 * K;
+      rx[u] = in ? __ldcg(g_xyz + cloud3 + e) : 0.0f;
+      rg[u] = in ? __ldcg(g_gocc + cloud3 + e) : 0.0f;
+      rm[u] = (in && have_mv) ? __ldcg(g_m + cloud3 + e) : 0.0f;
+      rv[u] = (in && have_mv) ? __ldcg(g_v + cloud3 + e) : 0.0f;
     }
-    *reinterpret_cast<uint4*>(&S.nbr[i][0]) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (live && a.warm) {
+      const int4* pv = reinterpret_cast<const int4*>(g_nbr + ((size_t)b * K + i) * kCsKK);
+      p0 = __ldcg(pv);
+      p1 = __ldcg(pv + 1);
+    }
+    for (int c = i; c < kCsCells + 4; c += kCsThreads) S.cell[c] = 0;      // (independent work under the load latency)
+    S.inbox_cnt[i] = 0;
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int e = i + u * kCsThreads;
+      if (e < 3 * K) {
+        xs[e] = rx[u];
+        S.gmv[0][e] = rg[u];
+        S.gmv[1][e] = rm[u];
+        S.gmv[2][e] = rv[u];
+      }
+    }
+    if (live && a.warm) {                                      // previous lists -> 16-bit rows
+      const int prev[kCsKK] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int e0 = (unsigned)prev[2 * s] < (unsigned)K ? prev[2 * s] : i;
+        const int e1 = (unsigned)prev[2 * s + 1] < (unsigned)K ? prev[2 * s + 1] : i;
+        w[s] = (uint32_t)e0 | ((uint32_t)e1 << 16);
+      }
+      *reinterpret_cast<uint4*>(&S.nbr[i][0]) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
   }
-  for (int c = i; c < kCsCells + 4; c += kCsThreads) S.cell[c] = 0;
-  S.inbox_cnt[i] = 0;
   if (i == 0) {
     S.nhub = 0;
     S.split_cell = kCsCells;

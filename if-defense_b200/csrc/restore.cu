@@ -18,6 +18,7 @@
 #include "cloud_step.cuh"
 #include "decode_v3.cuh"
 #include "decode_v4.cuh"
+#include "decode_v5.cuh"
 #include "grid_point.cuh"
 #include "topk.cuh"
 
@@ -448,6 +449,8 @@ static float plane_denom(double padding) {
   return (float)(1.0 + padding + 10e-6);
 }
 
+constexpr int kDefaultDecode = 5;      // decode_kernel == 0
+
 static int launch_decode(int mode, DecodeArgs a, cudaStream_t st) {
   const int wtotal = ConvDecLayout<H32>::total(a.n_blocks);
   a.wtotal4 = (wtotal + 3) / 4;
@@ -495,20 +498,6 @@ static int launch_decode_v2(const DecodeArgs& a, cudaStream_t st) {
   return IFD_OK;
 }
 
-static int launch_decode_v3(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
-  DecodeV3Args v{};
-  v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
-  v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
-  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv;
-  const size_t smem = DecodeV3Smem::bytes(a.n_blocks);
-  if (smem > 227 * 1024) return fail(IFD_ERR_UNSUPPORTED, "decode v3 supports n_blocks <= 6");
-  if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v3: plane array too large for 32-bit texel indices");
-  IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v3_kernel, smem));
-  convonet_decode_v3_kernel<<<(v.n + kV3Pts - 1) / kV3Pts, kV3Threads, smem, st>>>(v);
-  IFD_LAUNCH_CHECK("convonet_decode_v3_kernel");
-  return IFD_OK;
-}
-
 static int launch_decode_v4(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
   DecodeV3Args v{};
   v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
@@ -519,6 +508,19 @@ static int launch_decode_v4(const DecodeArgs& a, const float* wimg, cudaStream_t
   IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v4_kernel, smem));
   convonet_decode_v4_kernel<<<(v.n + kV4Pts - 1) / kV4Pts, kV4Threads, smem, st>>>(v);
   IFD_LAUNCH_CHECK("convonet_decode_v4_kernel");
+  return IFD_OK;
+}
+
+static int launch_decode_v5(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
+  DecodeV3Args v{};
+  v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
+  v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
+  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv; v.job = a.job;
+  const size_t smem = DecodeV5Smem::bytes(a.n_blocks);
+  if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v5: plane array too large for 32-bit texel indices");
+  IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v5_kernel, smem));
+  convonet_decode_v5_kernel<<<(v.n + kV4Pts - 1) / kV4Pts, kV4Threads, smem, st>>>(v);
+  IFD_LAUNCH_CHECK("convonet_decode_v5_kernel");
   return IFD_OK;
 }
 
@@ -689,12 +691,13 @@ int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, f
   a.target = (float)P->occ_target;
   // d/dlogit of (mean over B_ref*K) * K: autograd multiplies K, then divides by the element count
   a.ginv = (float)K / (float)((long long)P->B_ref * K);
-  const int dk = grid3d ? 1 : (P->decode_kernel == 0 ? 4 : P->decode_kernel);      // the grid variant has the thread-per-point kernel only
+  const int dk = grid3d ? 1 : (P->decode_kernel == 0 ? kDefaultDecode : P->decode_kernel);      // the grid variant has the thread-per-point kernel only
   const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads          // CTAs of the decode kernel (stat partials)
-                    : dk == 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
-  if (dk >= 3) {
+                    : dk >= 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
+  if (dk >= 4) {
     const int nl = 3 * n_blocks;
-    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, job);
+    if (dk == 5) convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, job);
+    else convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, job);
     IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
   }
   for (int i = 0; i < P->n_steps; ++i) {
@@ -702,8 +705,8 @@ int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, f
     a.stat_part = stat ? w.dec_part : nullptr;
     {
       ProfileScope ps(0, st);
-      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
-                   : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
+                   : launch_decode_v2(a, st);
       if (rc) return rc;
     }
     if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1 || grid3d, st, job, fresh))) return rc;
@@ -784,6 +787,7 @@ int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, con
   if (!hit) {
     // attributes first (cudaFuncSetAttribute is not a stream operation, but keep the capture free of anything else)
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v4_kernel, DecodeV4Smem::bytes(n_blocks)));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v5_kernel, DecodeV5Smem::bytes(n_blocks)));
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
     const long long before = launch_counter_ref();
     IFD_CUDA_TRY(cudaStreamBeginCapture(g.cap, cudaStreamCaptureModeThreadLocal));
@@ -926,14 +930,14 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   OptWorkspace w = carve_opt_ws(workspace, B, K);
   float* m = adam_m ? adam_m : w.m;
   float* v = adam_v ? adam_v : w.v;
-  const int dk = P->decode_kernel == 0 ? 4 : P->decode_kernel;
-  if (dk < 1 || dk > 4) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0..4");
-  if (dk == 4 && (unsigned long long)3 * B * R * R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v4: plane array too large for 32-bit texel indices");
+  const int dk = P->decode_kernel == 0 ? kDefaultDecode : P->decode_kernel;
+  if (dk < 1 || dk > 5 || dk == 3) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0, 1, 2, 4 or 5");
+  if (dk >= 4 && (unsigned long long)3 * B * R * R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v4 / v5: plane array too large for 32-bit texel indices");
   const bool stats = P->want_stats && stats_out;
   // The common case -- a fresh run of the production kernels without diagnostics -- replays ONE cached CUDA graph of the
   // whole loop (pack, n_steps x {decode, cloud_step}, normalise): the kernels read their buffers from a LoopJob record, so
   // the graph does not depend on the pointers and the host enqueues two operations instead of ~400.
-  if (g_use_graph && dk == 4 && !stats && !adam_m && P->step0 == 0 && P->n_steps >= 4 && opt_tail_fused(K, P) && !profile_on()) {
+  if (g_use_graph && dk >= 4 && !stats && !adam_m && P->step0 == 0 && P->n_steps >= 4 && opt_tail_fused(K, P) && !profile_on()) {
     LoopJob job{planes_cl, dec_weights, w.wimg, xyz, w.g_occ, m, v, w.nbr};
     return launch_loop_graph(job, B, K, R, n_blocks, P, st);
   }
@@ -1046,8 +1050,8 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   if ((rc = check_ptrs16(planes_cl, dec_weights))) return rc;
   IFD_REQUIRE(workspace, "ifd_convonet_decode_bce_grad: workspace is required");
   if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_decode_bce_grad: workspace too small");
-  const int dk = decode_kernel == 0 ? 4 : decode_kernel;
-  if (dk < 1 || dk > 4) return fail(IFD_ERR_INVALID, "decode_kernel must be 0..4");
+  const int dk = decode_kernel == 0 ? kDefaultDecode : decode_kernel;
+  if (dk < 1 || dk > 5 || dk == 3) return fail(IFD_ERR_INVALID, "decode_kernel must be 0, 1, 2, 4 or 5");
   cudaStream_t st = as_stream(stream);
   OptWorkspace w = carve_opt_ws(workspace, B, K);
   DecodeArgs a{};
@@ -1055,13 +1059,14 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   a.B = B; a.K = K; a.R = R; a.n_blocks = n_blocks; a.denom = plane_denom(padding);
   a.target = (float)occ_target;
   a.ginv = (float)K / (float)((long long)B_ref * K);
-  if (dk >= 3) {
+  if (dk >= 4) {
     const int nl = 3 * n_blocks;
-    convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, nullptr);
+    if (dk == 5) convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, nullptr);
+    else convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, nullptr);
     IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
   }
-  return dk == 1 ? launch_decode(kBce, a, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
-                 : dk == 3 ? launch_decode_v3(a, w.wimg, st) : launch_decode_v2(a, st);
+  return dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
+                 : launch_decode_v2(a, st);
 }
 
 // ---- the 'grid' (feature volume, trilinear) variant ------------------------------------------------------------------------

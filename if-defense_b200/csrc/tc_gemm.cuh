@@ -44,17 +44,7 @@ __host__ __device__ constexpr size_t smem_bytes(int NT) {
   return (size_t)stages_for(NT) * (kAStageBytes + b_stage_bytes(NT)) + 256;
 }
 
-// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, one elected thread issues
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
-}
+using umma::mma_tf32_ss;       // D[tmem] (+)= A[smem] . B[smem]^T
 // Warp-transposed ("blocked") row layout for tensors the engine reads and writes thread-per-row: rows in blocks of 32, inside a
 // block the C / 4 float4 column groups one after the other, each holding its 32 rows contiguously.  The 32 lanes of a warp that
 // access "their row's float4 number q" then touch 512 contiguous bytes (4 L1 wavefronts) instead of 32 separate lines.
