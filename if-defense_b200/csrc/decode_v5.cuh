@@ -131,6 +131,13 @@ __device__ __forceinline__ void v5_c_big(uint32_t tile_taddr, uint32_t img_saddr
   for (int s = 0; s < 4; ++s)
     umma::mma_tf32_ts(tile_taddr, c_hi + s * 8, umma::smem_desc_kmajor(img_saddr + s * 1024, 512, 128), idesc, 1u);
 }
+// Sign bits of 32 values as a mask (bit 31 - k = sign of v[k]): four independent funnel-shift chains of eight, then one merge.
+struct V5Signs {
+  uint32_t q[4];
+  __device__ __forceinline__ void clear() { q[0] = q[1] = q[2] = q[3] = 0u; }
+  __device__ __forceinline__ void push(int k, float v) { q[k >> 3] = __funnelshift_l(__float_as_uint(v), q[k >> 3], 1); }
+  __device__ __forceinline__ uint32_t mask() const { return (q[0] << 24) | (q[1] << 16) | (q[2] << 8) | q[3]; }
+};
 // every thread of the 128-thread group, around the leader's MMAs
 __device__ __forceinline__ void v5_round_begin(int group) {
   umma::fence_before_sync();
@@ -206,6 +213,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     else if (row < n_layers + 4) v = Wb[(row - n_layers) * 32 + c];          // fc_p W^T rows 0..2, then fc_p.b
     else if (row == n_layers + 4) v = Wb[L::out_w(nb) + c];
     else v = c == 0 ? Wb[L::out_b(nb)] : 0.0f;
+    if (row < n_layers && v == 0.0f) v = -0.0f;     // a zero bias is kept as -0: see the sign-bit masks of the forward pass
     vec[i] = v;
   }
   // ---------------- own point (slot = thread) and its geometry
@@ -291,6 +299,11 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     umma::commit(bar);
   }
   v5_round_end(d, lane_taddr, bar, parity);
+  // The residual stream and the hidden pre-activations are carried NEGATED (nnet = -net, exact: rounding is symmetric), because
+  // then "pre-activation > 0" is the sign bit of the stored value and a 32-bit ReLU mask costs one funnel shift per element
+  // instead of compare + select + or (ncu: 470 instructions per thread and round trip, 80 of them for the masks).  Zeros: every
+  // sum below is formed as (-a) + (-b) with zero biases stored as -0, so a true zero comes out as +0 (sign clear = "not > 0",
+  // the reference's relu'(0) = 0), never as -0.  Bit 31 - k of a mask belongs to element k.
   {
     const float* bc = vec;
 #pragma unroll
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
       v = fmaf(fcp[0 * 32 + o], p0, v);
       v = fmaf(fcp[1 * 32 + o], p1, v);
       v = fmaf(fcp[2 * 32 + o], p2, v);
-      net[o] = v + (__uint_as_float(d[o]) + bc[o]);            // net = fc_p(p) + fc_c[0](c)
+      net[o] = __fadd_rn(-v, __fadd_rn(-__uint_as_float(d[o]), -bc[o]));            // -(fc_p(p) + fc_c[0](c))
     }
   }
 #pragma unroll 1
@@ -308,13 +321,14 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     begin_stage(st);
     const float* b0 = vec + (3 * blk + 1) * 32;
     const float* b1 = vec + (3 * blk + 2) * 32;
-    uint32_t m = 0;
+    V5Signs sg4;
+    sg4.clear();
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      m |= (net[k] > 0.0f ? 1u : 0u) << k;
-      x[k] = fmaxf(net[k], 0.0f);
+      sg4.push(k, net[k]);
+      x[k] = fmaxf(-net[k], 0.0f);
     }
-    mask_a[blk] = m;
+    mask_a[blk] = sg4.mask();
     v5_put_a(x, d, lane_taddr);
     v5_round_begin(group);
     if (leader) {
@@ -324,14 +338,14 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
       umma::commit(bar);
     }
     v5_round_end(d, lane_taddr, bar, parity);
-    m = 0;
+    sg4.clear();
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      const float h = __uint_as_float(d[k]) + b0[k];         // h = fc_0(relu(net))
-      m |= (h > 0.0f ? 1u : 0u) << k;
-      x[k] = fmaxf(h, 0.0f);
+      const float nh = __fadd_rn(-__uint_as_float(d[k]), -b0[k]);         // -h,  h = fc_0(relu(net))
+      sg4.push(k, nh);
+      x[k] = fmaxf(-nh, 0.0f);
     }
-    mask_h[blk] = m;
+    mask_h[blk] = sg4.mask();
     v5_put_a(x, d, lane_taddr);
     v5_round_begin(group);
     const bool more = blk + 1 < nb;
@@ -349,20 +363,23 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     if (more) {
       const float* bc = vec + (3 * blk + 3) * 32;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) net[k] = (net[k] + (__uint_as_float(d[k]) + b1[k])) + bc[k];   // + fc_1(relu(h)) + fc_c[blk + 1](c)
+      for (int k = 0; k < 32; ++k)      // net + fc_1(relu(h)) + fc_c[blk + 1](c), negated
+        net[k] = __fadd_rn(__fadd_rn(net[k], __fadd_rn(-__uint_as_float(d[k]), -b1[k])), -bc[k]);
     } else {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) net[k] += __uint_as_float(d[k]) + b1[k];
+      for (int k = 0; k < 32; ++k) net[k] = __fadd_rn(net[k], __fadd_rn(-__uint_as_float(d[k]), -b1[k]));
     }
   }
   const float* wo = vec + (n_layers + 4) * 32;
   float logit = vec[(n_layers + 5) * 32];
-  uint32_t mask_f = 0;
+  V5Signs sgf;
+  sgf.clear();
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
-    mask_f |= (net[k] > 0.0f ? 1u : 0u) << k;
-    logit = fmaf(wo[k], fmaxf(net[k], 0.0f), logit);
+    sgf.push(k, net[k]);
+    logit = fmaf(wo[k], fmaxf(-net[k], 0.0f), logit);
   }
+  const uint32_t mask_f = sgf.mask();
   const float sg = sigmoidf_(logit);
   const float glogit = (sg - a.target) * a.ginv;
   if (a.stat_part) {
@@ -395,7 +412,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   //                  fc_1[blk]^T (same A operand) into columns 96..127 and added to `feat` in the shadow of the next round trip.
   float (&gnet)[32] = net;
 #pragma unroll
-  for (int k = 0; k < 32; ++k) gnet[k] = ((mask_f >> k) & 1u) ? glogit * wo[k] : 0.0f;
+  for (int k = 0; k < 32; ++k) gnet[k] = ((mask_f >> (31 - k)) & 1u) ? glogit * wo[k] : 0.0f;
 #pragma unroll 1
   for (int blk = nb - 1; blk >= 0; --blk) {
     const int st = nb + 1 + (nb - 1 - blk);
@@ -416,7 +433,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     v5_round_end(d, lane_taddr, bar, parity);
     const uint32_t mh = mask_h[blk], ma = mask_a[blk];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) x[k] = ((mh >> k) & 1u) ? __uint_as_float(d[k]) : 0.0f;      // gh
+    for (int k = 0; k < 32; ++k) x[k] = ((mh >> (31 - k)) & 1u) ? __uint_as_float(d[k]) : 0.0f;      // gh
     v5_put_a(x, d, lane_taddr);
     v5_round_begin(group);
     if (leader) {
@@ -436,7 +453,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     }
     v5_round_end(d, lane_taddr, bar, parity);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) gnet[k] += ((ma >> k) & 1u) ? __uint_as_float(d[k]) : 0.0f;
+    for (int k = 0; k < 32; ++k) gnet[k] += ((ma >> (31 - k)) & 1u) ? __uint_as_float(d[k]) : 0.0f;
   }
   {
     const int st = 2 * nb + 1;
