@@ -255,15 +255,17 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     feat[(j4 * 4 + 3) * kV4Stride + gslot] = c.w;
   }
   begin_stage(0);                      // (also publishes feat, vec, the TMEM slot and the mbarriers)
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tile_taddr = tmem_base + group * kV5TileCols;                         // lane 0 of the tile
+  // warp-uniform copies of everything the MMA issue reads (umma::elect_one: the operands must sit in uniform registers)
+  const int warp_u = (int)umma::warp_bcast((uint32_t)warp), group_u = warp_u >> 2;
+  const uint32_t tmem_base = umma::warp_bcast(*tmem_slot);
+  const uint32_t tile_taddr = tmem_base + group_u * kV5TileCols;                       // lane 0 of the tile
   const uint32_t lane_taddr = tile_taddr + ((uint32_t)((warp & 3) * 32) << 16);        // this warp's lane quarter
   const uint32_t wimg_saddr = umma::smem_u32(wimg);
-  unsigned char* clo = reinterpret_cast<unsigned char*>(feat) + (size_t)group * (128 * 32 * 4);   // c_lo image of this tile
+  unsigned char* clo = reinterpret_cast<unsigned char*>(feat) + (size_t)group_u * (128 * 32 * 4);   // c_lo image of this tile
   const uint32_t clo_saddr = umma::smem_u32(clo);
-  uint64_t* bar = &bars[group];
+  uint64_t* bar = &bars[group_u];
   uint32_t parity = 0;
-  const bool leader = (threadIdx.x & 127) == 0;
+  const bool lead_warp = (warp_u & 3) == 0;                                            // first warp of the tile issues its MMAs
   auto stage_img = [&](int t, int i) { return wimg_saddr + (uint32_t)(t & 1) * (kV4StageFloats * 4) + (uint32_t)i * (kV3ImgFloats * 4); };
 
   // ---------------- MLP forward: thread = point
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   umma::fence_proxy_async();           // generic-proxy stores -> visible to the tensor core's async proxy
   umma::tmem_wait_st();
   v5_round_begin(group);
-  if (leader) {
+  if (lead_warp && umma::elect_one()) {
     umma::fence_after_sync();
     v5_c_small(tile_taddr, clo_saddr, stage_img(0, 0), 0u);
     v5_c_big(tile_taddr, stage_img(0, 0));
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     mask_a[blk] = sg4.mask();
     v5_put_a(x, d, lane_taddr);
     v5_round_begin(group);
-    if (leader) {
+    if (lead_warp && umma::elect_one()) {
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 0), 0u, 0u);
       v5_chain_big(tile_taddr, stage_img(st, 0), 0u);
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     v5_put_a(x, d, lane_taddr);
     v5_round_begin(group);
     const bool more = blk + 1 < nb;
-    if (leader) {
+    if (lead_warp && umma::elect_one()) {
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 1), 0u, 0u);
       if (more) {
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     const bool with_c = blk + 1 < nb;
     v5_put_a(gnet, d, lane_taddr);
     v5_round_begin(group);
-    if (leader) {
+    if (lead_warp && umma::elect_one()) {
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 0), 0u, 0u);                                      // . W1[blk]
       v5_chain_big(tile_taddr, stage_img(st, 0), 0u);
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     for (int k = 0; k < 32; ++k) x[k] = ((mh >> (31 - k)) & 1u) ? __uint_as_float(d[k]) : 0.0f;      // gh
     v5_put_a(x, d, lane_taddr);
     v5_round_begin(group);
-    if (leader) {
+    if (lead_warp && umma::elect_one()) {
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 1), 0u, 0u);                                      // . W0[blk]
       v5_chain_big(tile_taddr, stage_img(st, 1), 0u);
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     begin_stage(st);
     v5_put_a(gnet, d, lane_taddr);
     v5_round_begin(group);
-    if (leader) {
+    if (lead_warp && umma::elect_one()) {
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 0), kV5ColX, 0u);                                 // . Wc[0]
       v5_chain_big(tile_taddr, stage_img(st, 0), kV5ColX);

@@ -225,14 +225,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop and waits on the barriers; one ELECTED lane issues (umma::elect_one: with warp-uniform
+    // operands the twelve MMAs of a chunk are twelve SASS instructions, not twelve ELECT / R2UR / BRA.U.ANY loops).
+    {
       constexpr uint32_t idesc = umma::idesc_tf32(128, NT);
+      const uint32_t tmem_u = umma::warp_bcast(tmem);
+      const uint32_t cid_u = umma::warp_bcast((uint32_t)cid), ncl_u = umma::warp_bcast((uint32_t)n_clusters);
       uint32_t it = 0, tl = 0;
-      for (int ct = cid; ct < n_ct; ct += n_clusters, ++tl) {
+      for (uint32_t ct = cid_u; ct < (uint32_t)n_ct; ct += ncl_u, ++tl) {
         const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
         umma::mbar_wait(&acc_empty[as], aph ^ 1);   // the epilogue drained this accumulator stage (two tiles ago)
         umma::fence_after_sync();
-        const uint32_t d_t = tmem + as * kAcc;
+        const uint32_t d_t = tmem_u + as * kAcc;
         for (int kc = 0; kc < n_chunks; ++kc, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
@@ -241,26 +245,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
           umma::fence_after_sync();
           const uint32_t sa = umma::smem_u32(a_st + (size_t)s * kAStageBytes);
           const uint32_t sb = umma::smem_u32(b_st + (size_t)s * kBStage);
+          if (umma::elect_one()) {
 #pragma unroll
-          for (int part = 0; part < 3; ++part) {    // lo.hi, hi.lo, hi.hi (small terms first)
-            const uint32_t a_s = sa + (part == 0 ? 128 * kChunk * 4 : 0);
-            const uint32_t b_s = sb + (part == 1 ? NT * kChunk * 4 : 0);
-            const uint32_t d_p = (kSplit && part < 2) ? d_t + NT : d_t;
+            for (int part = 0; part < 3; ++part) {    // lo.hi, hi.lo, hi.hi (small terms first)
+              const uint32_t a_s = sa + (part == 0 ? 128 * kChunk * 4 : 0);
+              const uint32_t b_s = sb + (part == 1 ? NT * kChunk * 4 : 0);
+              const uint32_t d_p = (kSplit && part < 2) ? d_t + NT : d_t;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint32_t later = kSplit ? (part == 1 ? 1u : (uint32_t)q) : (uint32_t)(part | q);    // 0 only for the first MMA into an accumulator
-              mma_tf32_ss(d_p, umma::smem_desc_kmajor(a_s + q * 4096, 2048, 128),
-                          umma::smem_desc_kmajor(b_s + q * (NT * 32), NT * 16, 128), idesc, (kc | later) ? 1u : 0u);
+              for (int q = 0; q < 4; ++q) {
+                const uint32_t later = kSplit ? (part == 1 ? 1u : (uint32_t)q) : (uint32_t)(part | q);    // 0 only for the first MMA into an accumulator
+                mma_tf32_ss(d_p, umma::smem_desc_kmajor(a_s + q * 4096, 2048, 128),
+                            umma::smem_desc_kmajor(b_s + q * (NT * 32), NT * 16, 128), idesc, (kc | later) ? 1u : 0u);
+              }
             }
+            // the stage is free once these MMAs have read it -- in EVERY CTA of the cluster (their loaders write into it)
+            if (CL > 1) commit_multicast(&empty[s], kMask);
+            else umma::commit(&empty[s]);
+            if (kc + 1 == n_chunks) umma::commit(&acc_full[as]);    // accumulator complete -> epilogue
           }
-          // the stage is free once these MMAs have read it -- in EVERY CTA of the cluster (their loaders write into it)
-          if (CL > 1) commit_multicast(&empty[s], kMask);
-          else umma::commit(&empty[s]);
+          __syncwarp();
         }
-        umma::commit(&acc_full[as]);                // accumulator complete -> epilogue
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ B loader (TMA bulk copies)
     if (lane == 0) {

@@ -70,6 +70,25 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- single-thread issue without the divergence tax ------------------------------------------------------------------------
+// tcgen05.mma / commit are per-thread instructions.  Issued under `if (threadIdx.x == leader)` ptxas must assume any subset of
+// lanes may be active and wraps EVERY instruction in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (12-20 SASS instructions per
+// MMA, measured); for the N = 32 MMAs of the decode chain that loop, not the tensor pipe, set the issue rate.  The pattern
+// ptxas understands: a WARP-UNIFORM branch selects the issuing warp (uniform values come from warp_bcast), elect_one() picks
+// the lane -- the operands then live in uniform registers and the MMAs issue back to back.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_bcast(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- descriptors -----------------------------------------------------------------------------------
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (sm_100 version bits = 1).  In 16-byte units the
 // canonical layout is ((8,n),2):((1,SBO),LBO): 8 rows x 16 B contiguous per core matrix, `lbo` bytes between
