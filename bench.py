@@ -44,7 +44,7 @@ B, K, ITERS = 64, 1024, 200                    # configs[1]: batch=64 x 1024 pts
 WORKLOAD = "ConvONet-Opt batch=64x1024 pts, 200 iters (201 Adam steps), 3 planes 64^2 x 32 ch"
 ALG_BYTES_PER_PT_STEP = 1560                   # 3 planes x 4 texels x 32 ch x 4 B + xyz r/w
 ALG_FLOP_PER_PT_STEP = 61952                   # decoder fwd + dgrad
-DECODE_KERNEL = "convonet_decode_v4_kernel"
+DECODE_KERNEL = "convonet_decode_v5_kernel"
 
 
 NCU_SUMMARIES = ("r02_ncu_full_summary.txt", "r01_final_ncu_full_summary.txt")     # newest first
@@ -71,7 +71,7 @@ def ncu_value(sec, key):
         return None
 
 
-def ncu_traffic(kernel="convonet_decode_v4_kernel"):
+def ncu_traffic(kernel=DECODE_KERNEL):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full summary
     (profiles/, cold-cache replay), or None."""
     sec, _ = ncu_section(kernel)
@@ -433,15 +433,6 @@ def main():
         case = synth.make_case(B, K=K, seed=100 * rank + j, device="cuda", sd=sd)
         sd = case.sd
         planes_cl = convonet.planes_to_channels_last({k: v.cuda() for k, v in case.c.items()})
-        if os.environ.get("IFD_EXP_MORTON"):     # experiment: points of a cloud in Morton order
-            import numpy as np
-            q = np.clip(((case.p0.numpy() / 1.1 + 0.5) * 1024).astype(np.int64), 0, 1023)
-            def part(v):
-                v = (v | (v << 16)) & 0x30000ff; v = (v | (v << 8)) & 0x300f00f; v = (v | (v << 4)) & 0x30c30c3; v = (v | (v << 2)) & 0x9249249
-                return v
-            code = part(q[..., 0]) | (part(q[..., 1]) << 1) | (part(q[..., 2]) << 2)
-            order = torch.from_numpy(np.argsort(code, axis=1))
-            case.p0 = torch.gather(case.p0, 1, order[..., None].expand(-1, -1, 3)).contiguous()
         batches.append((case, planes_cl, case.p0.cuda()))
     dec = convonet.ConvONetDecoder(sd, padding=0.1)
     C, H, nb = dec.dims
@@ -576,9 +567,11 @@ def main():
                 "traffic_source": "profiles/%s (ncu --set full, bytes per launch, cold-cache replay)" % dsrc,
                 "ms_per_launch": dec_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "l1tex_bytes_per_launch": None if l1_sectors is None else 32.0 * l1_sectors, "lts_bytes_per_launch": lts_bytes,
-                "observed_limiter": "latency: L2->SM gather + the 30 dependent tcgen05 round trips of the MLP chain (DRAM runs at a "
-                                    "few % of peak because the planes stay L2-resident); 'hbm' is the roofline CLASS SURVEY.md 8(d) "
-                                    "assigns to the gather, the denominator of frac, not the observed limiter",
+                "observed_limiter": "two gather phases that run at the L2 -> SM limit (204 MB of sectors in ~20 us = ~10 TB/s against the "
+                                    "~12 TB/s the L2 slices deliver chip-wide) around the 22 dependent tcgen05 round trips of the MLP "
+                                    "chain (latency / issue bound); DRAM runs at a few % of peak because the planes stay L2-resident. "
+                                    "'hbm' is the roofline CLASS SURVEY.md 8(d) assigns to the gather -- the denominator of frac -- not "
+                                    "the observed limiter",
                 "fp32_tflops_achieved": ALG_FLOP_PER_PT_STEP * B * K / (dec_ms * 1e-3) / 1e12,
                 "kernel_time_share": {"decode": kms[0] / total_k, "knn_repulsion_adam (cloud_step)": kms[1] / total_k,
                                       "adam (separate, legacy tail only)": kms[2] / total_k},
@@ -607,7 +600,7 @@ def main():
     if rank == 0 and not args.no_onet:
         onet = onet_leg(L)
         if roofs is not None:
-            roofs.append(dict(onet["decoder_gemm"], kernel="onet_gemm_kernel x 20 per Adam step (ONet-Opt leg)"))
+            roofs.append(dict(onet["decoder_gemm"], kernel="tc::gemm_kernel<OnetLayerPolicy, 256> x 20 per Adam step (ONet-Opt leg)"))
     if rank == 0 and not args.no_cpu_baseline:
         import torch as _t
         cores = os.cpu_count() or 1
