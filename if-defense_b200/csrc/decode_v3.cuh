@@ -1,7 +1,7 @@
 // decode_v3.cuh -- ConvONet decode with the ResNet-MLP on the 5th-generation tensor cores: the building blocks (weight images,
 // bilinear geometry packed for shuffles, one layer as a tcgen05 round trip, self test).  The kernels that use them are
-// decode_v4.cuh / decode_v5.cuh; the first kernel of this generation (512-point CTAs, all images resident, one CTA per SM)
-// produced the same bits as v4 and was retired in round 2.
+// decode_v5.cuh; the earlier kernels of this generation (v3: 512-point CTAs, all images resident, one CTA per SM; v4: 256-point
+// CTAs, two per SM, 30 dependent round trips) were retired in round 2.
 //
 // Why: ncu on decode v2 (profiles/r01_v2_*) shows the SIMT formulation pinned between the FMA pipe (45 %) and
 // the shared-memory pipe (41 % wavefronts for the warp-broadcast weight loads), two warps per scheduler and
@@ -28,27 +28,6 @@ namespace ifd {
 
 constexpr int kV3ImgFloats = 2048;                 // one layer, one direction: hi (1024) + lo (1024)
 constexpr int kV3TileCols = 96;                    // D | A_hi | A_lo
-
-// blob (kernel layout, W^T [in][out] per layer) -> UMMA images.  out: [2 dirs][n_layers][hi|lo][1024] floats.
-__global__ void convonet_pack_umma_kernel(const float* __restrict__ Wb_arg, int n_layers, float* __restrict__ out_arg,
-                                          const LoopJob* __restrict__ job) {
-  using L = ConvDecLayout<32>;
-  const float* __restrict__ Wb = job ? job->W : Wb_arg;
-  float* __restrict__ out = job ? const_cast<float*>(job->Wimg) : out_arg;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_layers * 1024) return;
-  const int l = e >> 10, i = (e >> 5) & 31, o = e & 31;        // WT[i][o] = W[o][i]
-  const float w = Wb[L::kBlk0 + l * L::kLayer + i * 32 + o];
-  const float hi = __uint_as_float(umma::tf32_hi(w)), lo = __uint_as_float(umma::tf32_lo(w));
-  // forward: B[n = o][k = i]
-  float* f = out + ((size_t)0 * n_layers + l) * kV3ImgFloats;
-  f[umma::img_offset(o, i, 32) / 4] = hi;
-  f[1024 + umma::img_offset(o, i, 32) / 4] = lo;
-  // backward (dgrad): B[n = i][k = o]
-  float* b = out + ((size_t)1 * n_layers + l) * kV3ImgFloats;
-  b[umma::img_offset(i, o, 32) / 4] = hi;
-  b[1024 + umma::img_offset(i, o, 32) / 4] = lo;
-}
 
 // Bilinear geometry of one point, packed for warp shuffles: the lane that OWNS a point (slot = thread) computes the
 // three axes once (normalize_coordinate's division and clamps, grid_sample's unnormalise / clip / floor), and the

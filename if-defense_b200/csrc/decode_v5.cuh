@@ -1,5 +1,6 @@
-// decode_v5.cuh -- decode v4 with the fc_c layers taken OFF the dependent chain: 22 tensor-core round trips per point and
-// Adam step instead of 30.
+// decode_v5.cuh -- the production ConvONet decode: gather + ResNet-MLP on tcgen05 (building blocks: decode_v3.cuh) in 256-point
+// CTAs, two per SM, weight images streamed per stage by TMA bulk copies -- and, new against the retired v4 kernel, the fc_c
+// layers taken OFF the dependent chain: 22 tensor-core round trips per point and Adam step instead of 30.
 //
 // LocalDecoder.forward (ConvONet/src/conv_onet/models/decoder.py:82-98) is, per ResNet block i,
 //     net = net + fc_c[i](c);  h = fc_0[i](relu(net));  net = net + fc_1[i](relu(h))
@@ -19,10 +20,15 @@
 // fc_p, weight stages by TMA bulk copy, two CTAs per SM) is v4's.  The association of the residual sum differs from v4
 // ((net + dx) + fc_c  ->  net + (dx + fc_c), formed in the fp32 accumulator), so v5 and v4 agree to rounding, not bitwise.
 #pragma once
-#include "decode_v4.cuh"
+#include "decode_v3.cuh"
 
 namespace ifd {
 
+constexpr int kV4Threads = 256;                    // (names kept from the retired v4 kernel, whose CTA shape this is)
+constexpr int kV4Pts = 256;
+constexpr int kV4Stride = kV4Pts + 1;
+constexpr int kV4StageFloats = 3 * kV3ImgFloats;   // one stage buffer: up to 3 images x (hi + lo) = 24 KB
+constexpr uint32_t kV4TmemCols = 256;
 constexpr int kV5TileCols = 128;                   // D | A_hi | A_lo | c_hi (forward) / D_gc (backward)
 constexpr int kV5ColA = 32, kV5ColX = 96;
 
@@ -152,7 +158,10 @@ __device__ __forceinline__ void v5_round_end(uint32_t (&d)[32], uint32_t taddr, 
 }
 
 struct DecodeV5Smem {
-  static __host__ __device__ size_t bytes(int n_blocks) { return DecodeV4Smem::bytes(n_blocks); }
+  static __host__ __device__ size_t bytes(int n_blocks) {      // stage buffers | feat / c_lo | gpart | barriers | bias / fc_p / fc_out table
+    return (size_t)2 * kV4StageFloats * 4 + (size_t)32 * kV4Stride * 4 + (size_t)kV4Pts * 16 + 256 +
+           (size_t)(3 * n_blocks + 6) * 32 * 4;
+  }
 };
 
 __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const DecodeV3Args a) {

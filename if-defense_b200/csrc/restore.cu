@@ -17,7 +17,6 @@
 #include "decode_v2.cuh"
 #include "cloud_step.cuh"
 #include "decode_v3.cuh"
-#include "decode_v4.cuh"
 #include "decode_v5.cuh"
 #include "grid_point.cuh"
 #include "topk.cuh"
@@ -498,19 +497,6 @@ static int launch_decode_v2(const DecodeArgs& a, cudaStream_t st) {
   return IFD_OK;
 }
 
-static int launch_decode_v4(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
-  DecodeV3Args v{};
-  v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
-  v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
-  v.denom = a.denom; v.target = a.target; v.ginv = a.ginv; v.job = a.job;
-  const size_t smem = DecodeV4Smem::bytes(a.n_blocks);
-  if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v4: plane array too large for 32-bit texel indices");
-  IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v4_kernel, smem));
-  convonet_decode_v4_kernel<<<(v.n + kV4Pts - 1) / kV4Pts, kV4Threads, smem, st>>>(v);
-  IFD_LAUNCH_CHECK("convonet_decode_v4_kernel");
-  return IFD_OK;
-}
-
 static int launch_decode_v5(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
   DecodeV3Args v{};
   v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
@@ -696,17 +682,15 @@ int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, f
                     : dk >= 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
   if (dk >= 4) {
     const int nl = 3 * n_blocks;
-    if (dk == 5) convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, job);
-    else convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, job);
-    IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
+    convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, job);
+    IFD_LAUNCH_CHECK("convonet_pack_umma_v5_kernel");
   }
   for (int i = 0; i < P->n_steps; ++i) {
     const bool stat = P->want_stats && stats_out && (i % 100 == 0);
     a.stat_part = stat ? w.dec_part : nullptr;
     {
       ProfileScope ps(0, st);
-      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
-                   : launch_decode_v2(a, st);
+      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : launch_decode_v2(a, st);
       if (rc) return rc;
     }
     if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1 || grid3d, st, job, fresh))) return rc;
@@ -786,7 +770,6 @@ int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, con
     if (memcmp(&e.key, &key, sizeof key) == 0) hit = &e;
   if (!hit) {
     // attributes first (cudaFuncSetAttribute is not a stream operation, but keep the capture free of anything else)
-    IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v4_kernel, DecodeV4Smem::bytes(n_blocks)));
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v5_kernel, DecodeV5Smem::bytes(n_blocks)));
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
     const long long before = launch_counter_ref();
@@ -931,8 +914,8 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   float* m = adam_m ? adam_m : w.m;
   float* v = adam_v ? adam_v : w.v;
   const int dk = P->decode_kernel == 0 ? kDefaultDecode : P->decode_kernel;
-  if (dk < 1 || dk > 5 || dk == 3) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0, 1, 2, 4 or 5");
-  if (dk >= 4 && (unsigned long long)3 * B * R * R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v4 / v5: plane array too large for 32-bit texel indices");
+  if (dk != 1 && dk != 2 && dk != 5) return fail(IFD_ERR_INVALID, "ifd_convonet_opt: decode_kernel must be 0, 1, 2 or 5");
+  if (dk >= 4 && (unsigned long long)3 * B * R * R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v5: plane array too large for 32-bit texel indices");
   const bool stats = P->want_stats && stats_out;
   // The common case -- a fresh run of the production kernels without diagnostics -- replays ONE cached CUDA graph of the
   // whole loop (pack, n_steps x {decode, cloud_step}, normalise): the kernels read their buffers from a LoopJob record, so
@@ -1051,7 +1034,7 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   IFD_REQUIRE(workspace, "ifd_convonet_decode_bce_grad: workspace is required");
   if (workspace_bytes < ifd_convonet_opt_workspace_bytes(B, K)) return fail(IFD_ERR_WORKSPACE, "ifd_convonet_decode_bce_grad: workspace too small");
   const int dk = decode_kernel == 0 ? kDefaultDecode : decode_kernel;
-  if (dk < 1 || dk > 5 || dk == 3) return fail(IFD_ERR_INVALID, "decode_kernel must be 0, 1, 2, 4 or 5");
+  if (dk != 1 && dk != 2 && dk != 5) return fail(IFD_ERR_INVALID, "decode_kernel must be 0, 1, 2 or 5");
   cudaStream_t st = as_stream(stream);
   OptWorkspace w = carve_opt_ws(workspace, B, K);
   DecodeArgs a{};
@@ -1061,12 +1044,10 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
   a.ginv = (float)K / (float)((long long)B_ref * K);
   if (dk >= 4) {
     const int nl = 3 * n_blocks;
-    if (dk == 5) convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, nullptr);
-    else convonet_pack_umma_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, nl, w.wimg, nullptr);
-    IFD_LAUNCH_CHECK("convonet_pack_umma_kernel");
+    convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, nullptr);
+    IFD_LAUNCH_CHECK("convonet_pack_umma_v5_kernel");
   }
-  return dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : dk == 4 ? launch_decode_v4(a, w.wimg, st)
-                 : launch_decode_v2(a, st);
+  return dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : launch_decode_v2(a, st);
 }
 
 // ---- the 'grid' (feature volume, trilinear) variant ------------------------------------------------------------------------

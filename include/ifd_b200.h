@@ -241,12 +241,12 @@ typedef struct ifd_opt_params {
   int32_t decode_kernel; /* which decode kernel the loop launches -- 0: the production default (= 5);
                             1: v1, thread-per-point fp32 SIMT (the step-level seam; from-scratch kNN every step);
                             2: v2, fp32 SIMT, cooperative gather, 2 points/thread, FFMA2, generic layer bodies;
-                            3: retired (the first tensor-core kernel: 512-point CTAs, one per SM; same bits as 4);
-                            4: v4, ResNet-MLP on tcgen05 tensor cores (3xTF32, A in TMEM, fp32-class accuracy), 256-point
-                               CTAs with the weight images streamed per ResNet block by TMA bulk copies, two CTAs per SM;
-                            5: v5, v4 with the fc_c layers taken off the dependent chain (their products ride in the
-                               accumulator of the preceding fc_1 / in a second accumulator of the dgrad): 22 tensor-core
-                               round trips per step instead of 30; equal to v4 up to the association of one fp32 sum */
+                            3, 4: retired (earlier tensor-core kernels: 512- / 256-point CTAs with 30 dependent tensor-core
+                               round trips per step);
+                            5: v5, ResNet-MLP on tcgen05 tensor cores (3xTF32, A in TMEM, fp32-class accuracy), 256-point
+                               CTAs, two per SM, weight images streamed per stage by TMA bulk copies, the fc_c layers off
+                               the dependent chain (their products ride in the accumulator of the preceding fc_1 / in a
+                               second accumulator of the dgrad): 22 tensor-core round trips per step */
   int32_t tail_kernel;   /* what follows the decode in a step -- 0: the production default, one fused kernel per cloud
                             (grid kNN + repulsion gather + Adam, K <= 1024, knn_k <= 7); 1: first-generation kernels
                             (brute-force kNN + exact long accumulator, separate Adam), any K <= 12000 */

@@ -134,19 +134,17 @@ def test_bce_grad_seam_all_kernels(conv, conv_sd, conv_planes, dec, planes):
     scale = np.abs(want).max()
     errs = {}
     grads = {}
-    for kernel in (1, 2, 4, 5):
+    for kernel in (1, 2, 5):
         g = grads[kernel] = bce_grad(dec, planes, conv["p0"], kernel)
         errs[kernel] = np.abs(g - want).max() / scale
     print("bce-grad max error / max|grad| per kernel:", errs)
     assert errs[1] < 2e-6 and errs[2] < 2e-6
-    assert errs[4] < 2e-5 and errs[5] < 2e-5      # 3xTF32 tensor-core path: fp32-class, ~2^-21 per product term
-    # v5 = v4 with fc_c off the chain: one fp32 sum per block is associated differently, nothing else
-    assert np.abs(grads[4] - grads[5]).max() / scale < 2e-5
+    assert errs[5] < 1e-5                         # 3xTF32 tensor-core path: fp32-class (vs a float64 evaluation: 2.8e-6, the fp32 kernels 3.0e-6)
 
 
-@pytest.mark.parametrize("tck", [4, 5])
+@pytest.mark.parametrize("tck", [5])
 def test_tensor_core_decode_kernel(conv, dec, planes, tck):
-    """decode v4 / v5 (ResNet-MLP on tcgen05, 3xTF32).  Its gradient is as close to a float64 evaluation as the
+    """decode v5 (ResNet-MLP on tcgen05, 3xTF32).  Its gradient is as close to a float64 evaluation as the
     fp32 reference's own (test_bce_grad_seam_all_kernels, tools/grad_probe.py), but pre-activations carry
     ~2^-21 instead of ~2^-24 relative noise, so a ReLU sitting within that noise of zero flips its sign mask
     about 8x more often than between two fp32 implementations (about one point in 500 per evaluation on these
@@ -177,7 +175,7 @@ def test_tensor_core_decode_kernel(conv, dec, planes, tck):
 
 
 def test_tensor_core_201_steps_statistical(conv, dec, planes):
-    x, st = run_opt(dec, planes, conv["p0"], 201, stats=True, decode_kernel=4)
+    x, st = run_opt(dec, planes, conv["p0"], 201, stats=True, decode_kernel=5)
     ref = conv["final_201_raw"]
     d = np.abs(x - ref)
     # measured on a B200 (profiles/r02_parity_record.json, fixture 2 x 256): median 5.5e-5, p99 1.6e-3, max 1.9e-2, 62.5 % within
