@@ -457,14 +457,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- the timed path: K steps (batches) through ifd_convonet_opt_batches -- the loops of two consecutive batches run
-    #      side by side on two streams (one launch fills 128 of the 148 SMs); every step still restores its own batch
+    # ---- the timed path: K steps (batches) through ifd_convonet_opt_batches -- the loops of up to four consecutive batches run
+    #      side by side (no launch of a loop fills the machine); every step still restores its own batch
     n_max = max(args.steps, W)
     xs = [torch.empty_like(x) for _ in range(n_max)]
-    lanes = int(os.environ.get("IFD_LANES", "2"))          # experiment knob: loops side by side (default 2)
-    if lanes != 2:
-        L.ifd_test_hook(2, lanes)
-    ws2_bytes = max(lanes, 2) * ((ws_bytes + 255) // 256 * 256)
+    if os.environ.get("IFD_LANES"):                         # experiment knob: loops side by side (library default: 4)
+        L.ifd_test_hook(2, int(os.environ["IFD_LANES"]))
+    if os.environ.get("IFD_TAIL_CTAS"):                     # experiment knob: CTAs per cloud of the fused tail (default: by context)
+        L.ifd_test_hook(5, int(os.environ["IFD_TAIL_CTAS"]))
+    ws2_bytes = int(L.ifd_convonet_opt_batches_workspace_bytes(B, K))
     ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device="cuda")
 
     def run_steps(j0, n):
@@ -550,7 +551,14 @@ def main():
         kms = (ctypes.c_double * 4)()
         kn = (ctypes.c_longlong * 4)()
         L.ifd_profile_read(kms, kn)
+        L.ifd_test_hook(5, 1)                  # the one-CTA form of the tail, which the side-by-side timed region uses
+        step(W, gather=False)
+        kms1 = (ctypes.c_double * 4)()
+        kn1 = (ctypes.c_longlong * 4)()
+        L.ifd_profile_read(kms1, kn1)
+        L.ifd_test_hook(5, 0)
         L.ifd_profile_enable(0)
+        tail_solo_ms = kms1[1] / max(kn1[1], 1)     # (ifd_profile_read starts a new record)
         hbm_peak, peak_src = peaks()
         dec_ms = kms[0] / max(kn[0], 1)
         tail_ms = kms[1] / max(kn[1], 1)
@@ -584,7 +592,7 @@ def main():
         pair_flops = 8.0 * B * K * K
         cs_ach = pair_flops / (tail_ms * 1e-3) / 1e12
         roof_tail = {"bound": "fp32-alu/smem", "kernel": "cloud_step_kernel (grid kNN-5 + repulsion fwd/bwd + Adam, one cluster per cloud)",
-                     "ms_per_launch": tail_ms, "achieved": cs_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": cs_ach / fp32_peak,
+                     "ms_per_launch": tail_ms, "ms_per_launch_one_cta_form": tail_solo_ms, "achieved": cs_ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": cs_ach / fp32_peak,
                      "peak_source": "nominal: 148 SMs x 128 FMA/clk x 2 x %.0f MHz" % sm_mhz,
                      "algorithmic_flops_per_launch": pair_flops, "algorithmic_bytes_per_launch": 84 * B * K,
                      "hbm_frac": 84 * B * K / (tail_ms * 1e-3) / 1e9 / hbm_peak,
@@ -594,7 +602,9 @@ def main():
                          "threads_per_inst": ncu_value(csec, "smsp__thread_inst_executed_per_inst_executed.ratio"),
                          "warps_active_pct": ncu_value(csec, "sm__warps_active.avg.pct_of_peak_sustained_active")},
                      "note": "achieved counts the K^2 pair keys of the brute-force definition; the kernel evaluates ~25 candidates per "
-                             "query through a per-step uniform grid, so it is bound by barriers and divergence, not by the FMA pipe"}
+                             "query through a per-step uniform grid, so it is bound by barriers and divergence, not by the FMA pipe. "
+                             "ms_per_launch: a loop running alone (2-CTA cluster per cloud); the side-by-side timed region uses the "
+                             "one-CTA form (ms_per_launch_one_cta_form: longer per launch, half the SMs)"}
         roofs = [roof, roof_tail]
 
     if rank == 0 and not args.no_onet:
@@ -629,7 +639,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "clouds_per_gpu_per_step": B, "B_ref": B,
                        "l2": "inputs rotate over %d distinct batches per rank (%.0f MB of planes) > 126 MB L2" % (NB, NB * 100.7),
-                       "concurrency": "loops of two consecutive steps run side by side on two streams (ifd_convonet_opt_batches)",
+                       "concurrency": "loops of up to four consecutive steps run side by side on internal streams (ifd_convonet_opt_batches), each one cached CUDA graph; one-CTA tail in that mode",
                        "parallelism": "clouds sharded over %d GPU(s), all_gather of restored clouds per step" % world},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "rooflines": roofs, "onet": onet,
             "cpu_baseline": cpu,

@@ -147,21 +147,21 @@ class Restorer:
     def __init__(self, decoder, threshold=0.2, lr=1e-3, decode_kernel=0, side_by_side=True):
         """decode_kernel: 0 = production default (tcgen05 tensor-core MLP, 3xTF32); 2 = fp32 SIMT kernels, for
         bit-level trajectory comparisons with an fp32 reference (see include/ifd_b200.h, ifd_opt_params).
-        side_by_side: a batch of >= 128 clouds is cut into equal parts whose loops run next to each other on two streams
-        (ifd_convonet_opt_batches with the batch's B_ref: the same bits, the launches of one loop fill the SMs the other
-        leaves idle)."""
+        side_by_side: a batch of >= 96 clouds is cut into equal parts of at most 64 clouds whose loops run next to each other
+        (ifd_convonet_opt_batches with the batch's B_ref: the same bits, the launches of one loop fill the SMs the others
+        leave idle); an int forces the number of parts."""
         self.decoder, self.threshold, self.lr = decoder, float(threshold), float(lr)
         self.decode_kernel = int(decode_kernel)
         self.side_by_side = side_by_side
         self.last_stats = None
 
     def _parts(self, B):
-        if not self.side_by_side or B < 128:
+        if not self.side_by_side or B < 96:
             return 1
         if isinstance(self.side_by_side, int) and not isinstance(self.side_by_side, bool):
             return self.side_by_side if B % self.side_by_side == 0 else 1
-        for n in range(2, 9):
-            if B % n == 0 and B // n <= 96:
+        for n in range(2, 9):                 # parts of at most 64 clouds: 192 -> 3 x 64, 164 -> 4 x 41, 128 -> 2 x 64
+            if B % n == 0 and B // n <= 64:
                 return n
         return 1
 

@@ -171,15 +171,19 @@ extern "C" int ifd_convonet_opt_host(const float* planes_nchw_host, const float*
 
 // ---------------------------------------------------------------------------------------------------------------
 // Many batches, pipelined: what defend_point_cloud (ConvONet/opt_defense.py:272-312) does batch after batch, with the
-// host<->device copies overlapped with the loops, and the loops of two consecutive batches running side by side (two
-// run streams, two buffer slots, copy streams for H2D and D2H).
+// host<->device copies overlapped with the loops, and the loops of up to four consecutive batches running side by side (one
+// run stream per loop, one buffer slot more than loops in flight, copy streams for H2D and D2H).
 // Every batch still pays its own H2D of planes + init points and D2H of the restored cloud.
 namespace ifd {
+int opt_lanes();                    // restore.cu: loops side by side (ifd_test_hook(2, n), default 4)
+void opt_side_by_side(int on);      // restore.cu: the loops enqueued next run next to others (selects the one-CTA tail)
+constexpr int kPipeRun = 4;         // run streams (>= opt_lanes())
+constexpr int kPipeSlots = kPipeRun + 1;     // buffer slots: one more than loops in flight, for the upload / download of the next
 struct PipeCache {
   void* dev = nullptr;
   size_t bytes = 0;
-  cudaStream_t h2d = nullptr, run[2] = {nullptr, nullptr}, d2h = nullptr;
-  cudaEvent_t ready[3] = {nullptr, nullptr, nullptr}, done[3] = {nullptr, nullptr, nullptr}, freed[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t h2d = nullptr, run[kPipeRun] = {}, d2h = nullptr;
+  cudaEvent_t ready[kPipeSlots] = {}, done[kPipeSlots] = {}, freed[kPipeSlots] = {};
 };
 static thread_local PipeCache g_pipe;
 static thread_local int g_pipe_device = -1;
@@ -191,10 +195,9 @@ static int ensure_pipe(size_t dev_bytes) {
   g_pipe_device = dev;
   if (!g_pipe.h2d) {
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.h2d, cudaStreamNonBlocking));
-    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[0], cudaStreamNonBlocking));
-    IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[1], cudaStreamNonBlocking));
+    for (int r = 0; r < kPipeRun; ++r) IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.run[r], cudaStreamNonBlocking));
     IFD_CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.d2h, cudaStreamNonBlocking));
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < kPipeSlots; ++s) {
       IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.ready[s], cudaEventDisableTiming));
       IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.done[s], cudaEventDisableTiming));
       IFD_CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.freed[s], cudaEventDisableTiming));
@@ -226,58 +229,71 @@ extern "C" int ifd_convonet_opt_host_batches(int n_batches, const float* const* 
   const size_t xyz_al = align_up(xyz_bytes, 256);
   const size_t w_bytes = align_up(nw * sizeof(float), 256);
   const size_t ws_bytes = align_up(ifd_convonet_opt_workspace_bytes(B, K), 256);
-  const size_t total = w_bytes + 2 * ws_bytes + 3 * (2 * plane_bytes + xyz_al);
+  const int lanes = opt_lanes() < 1 ? 1 : (opt_lanes() > kPipeRun ? kPipeRun : opt_lanes());
+  const int slots = lanes + 1;
+  const size_t total = w_bytes + (size_t)lanes * ws_bytes + (size_t)slots * (2 * plane_bytes + xyz_al);
   int rc = ensure_pipe(total);
   if (rc) return rc;
   char* base = (char*)g_pipe.dev;
   float* d_w = (float*)base; base += w_bytes;
-  void* d_ws[2];                            // one workspace per slot: the loops of two batches run side by side
-  d_ws[0] = base; base += ws_bytes;
-  d_ws[1] = base; base += ws_bytes;
-  float *d_nchw[3], *d_cl[3], *d_xyz[3];    // three buffer slots: two batches run while the third is uploaded / downloaded
-  for (int s = 0; s < 3; ++s) {
+  void* d_ws[kPipeRun];                     // one workspace per run stream: the loops of `lanes` batches run side by side
+  for (int r = 0; r < lanes; ++r) {
+    d_ws[r] = base;
+    base += ws_bytes;
+  }
+  float *d_nchw[kPipeSlots], *d_cl[kPipeSlots], *d_xyz[kPipeSlots];    // `lanes` batches run while one more is uploaded / downloaded
+  for (int s = 0; s < slots; ++s) {
     d_nchw[s] = (float*)base; base += plane_bytes;
     d_cl[s] = (float*)base; base += plane_bytes;
     d_xyz[s] = (float*)base; base += xyz_al;
   }
   IFD_CUDA_TRY(cudaMemcpyAsync(d_w, dec_weights_host, nw * sizeof(float), cudaMemcpyHostToDevice, g_pipe.h2d));
-  for (int j = 0; j < n_batches; ++j) {
-    const int s = j % 3, r = j & 1;           // buffer slot, run stream
-    if (j >= 3) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.freed[s], 0));       // slot s drained (loop + D2H of j-3)
-    IFD_CUDA_TRY(cudaMemcpyAsync(d_nchw[s], planes_nchw_host[j], (size_t)3 * B * C * R * R * sizeof(float), cudaMemcpyHostToDevice,
-                                 g_pipe.h2d));
-    IFD_CUDA_TRY(cudaMemcpyAsync(d_xyz[s], xyz_host[j], xyz_bytes, cudaMemcpyHostToDevice, g_pipe.h2d));
-    if ((rc = ifd_planes_nchw_to_cl(d_nchw[s], d_cl[s], 3 * B, C, R, g_pipe.h2d))) return rc;
-    IFD_CUDA_TRY(cudaEventRecord(g_pipe.ready[s], g_pipe.h2d));
-    // two run streams: a decode or tail launch occupies 128 of the 148 SMs (one CTA per SM), the other batch's
-    // launches fill the rest and every gap between dependent launches
-    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.run[r], g_pipe.ready[s], 0));
+  opt_side_by_side(lanes > 1 && n_batches > 1);
+  for (int j = 0; j < n_batches && rc == IFD_OK; ++j) {
+    const int s = j % slots, r = j % lanes;   // buffer slot, run stream
+    cudaError_t e = cudaSuccess;
+    if (j >= slots) e = cudaStreamWaitEvent(g_pipe.h2d, g_pipe.freed[s], 0);       // slot s drained (loop + D2H of j - slots)
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_nchw[s], planes_nchw_host[j], (size_t)3 * B * C * R * R * sizeof(float), cudaMemcpyHostToDevice, g_pipe.h2d);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_xyz[s], xyz_host[j], xyz_bytes, cudaMemcpyHostToDevice, g_pipe.h2d);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "ifd_convonet_opt_host_batches: upload"); break; }
+    if ((rc = ifd_planes_nchw_to_cl(d_nchw[s], d_cl[s], 3 * B, C, R, g_pipe.h2d))) break;
+    e = cudaEventRecord(g_pipe.ready[s], g_pipe.h2d);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_pipe.run[r], g_pipe.ready[s], 0);
+    if (e != cudaSuccess) { rc = cuda_fail(e, "ifd_convonet_opt_host_batches: hand-over"); break; }
     if ((rc = ifd_convonet_opt(d_cl[s], d_w, d_xyz[s], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr, d_ws[r], ws_bytes,
                                g_pipe.run[r])))
-      return rc;
-    IFD_CUDA_TRY(cudaEventRecord(g_pipe.done[s], g_pipe.run[r]));
-    IFD_CUDA_TRY(cudaStreamWaitEvent(g_pipe.d2h, g_pipe.done[s], 0));
-    IFD_CUDA_TRY(cudaMemcpyAsync(xyz_host[j], d_xyz[s], xyz_bytes, cudaMemcpyDeviceToHost, g_pipe.d2h));
-    IFD_CUDA_TRY(cudaEventRecord(g_pipe.freed[s], g_pipe.d2h));
+      break;
+    e = cudaEventRecord(g_pipe.done[s], g_pipe.run[r]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g_pipe.d2h, g_pipe.done[s], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(xyz_host[j], d_xyz[s], xyz_bytes, cudaMemcpyDeviceToHost, g_pipe.d2h);
+    if (e == cudaSuccess) e = cudaEventRecord(g_pipe.freed[s], g_pipe.d2h);
+    if (e != cudaSuccess) rc = cuda_fail(e, "ifd_convonet_opt_host_batches: download");
   }
-  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.d2h));
-  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.run[0]));
-  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.run[1]));
-  IFD_CUDA_TRY(cudaStreamSynchronize(g_pipe.h2d));
-  return IFD_OK;
+  opt_side_by_side(0);
+  // drain on every exit path: the buffers are cached and the next call reuses them
+  cudaError_t es = cudaStreamSynchronize(g_pipe.d2h);
+  for (int r = 0; r < lanes; ++r) {
+    const cudaError_t er = cudaStreamSynchronize(g_pipe.run[r]);
+    if (es == cudaSuccess) es = er;
+  }
+  const cudaError_t eh = cudaStreamSynchronize(g_pipe.h2d);
+  if (es == cudaSuccess) es = eh;
+  if (rc == IFD_OK && es != cudaSuccess) rc = cuda_fail(es, "ifd_convonet_opt_host_batches: synchronize");
+  return rc;
 }
 
 namespace ifd {
 void release_pipe() {
   if (g_pipe.dev) cudaFree(g_pipe.dev);
-  for (int s = 0; s < 3; ++s) {
+  for (int s = 0; s < kPipeSlots; ++s) {
     if (g_pipe.ready[s]) cudaEventDestroy(g_pipe.ready[s]);
     if (g_pipe.done[s]) cudaEventDestroy(g_pipe.done[s]);
     if (g_pipe.freed[s]) cudaEventDestroy(g_pipe.freed[s]);
   }
   if (g_pipe.h2d) cudaStreamDestroy(g_pipe.h2d);
-  if (g_pipe.run[0]) cudaStreamDestroy(g_pipe.run[0]);
-  if (g_pipe.run[1]) cudaStreamDestroy(g_pipe.run[1]);
+  for (int r = 0; r < kPipeRun; ++r)
+    if (g_pipe.run[r]) cudaStreamDestroy(g_pipe.run[r]);
   if (g_pipe.d2h) cudaStreamDestroy(g_pipe.d2h);
   g_pipe = PipeCache();
 }

@@ -114,7 +114,11 @@ __device__ __forceinline__ bool cs_row_has(const uint16_t* row, int k, int who) 
   return hit;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudStepArgs a) {
+// CL = 2: the cluster form described above.  CL = 1: one CTA owns the whole cloud (no helpers at K = 1024, no DSMEM, the
+// cluster barriers become __syncthreads): a longer walk per thread, but half the SMs per launch -- what matters when the
+// loops of two batches share the GPU (ifd_test_hook(5, 1)).
+template <int CL>
+__device__ __forceinline__ void cloud_step_body(const CloudStepArgs& a) {
   extern __shared__ __align__(16) unsigned char cs_raw[];
   // graph replay: the buffers of THIS launch are in the job record.  (Plain locals on purpose: copying the argument struct
   // and overwriting its pointer members made nvcc 12.9 drop the assignment of `xyz` -- the kernel then kept using the
@@ -126,9 +130,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
   int32_t* const g_nbr = a.job ? a.job->nbr : a.nbr;
   CloudStepSmem& S = *reinterpret_cast<CloudStepSmem*>(cs_raw);
   cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
-  const int half = (int)cluster.block_rank();                  // which side of the split this CTA owns
-  CloudStepSmem& P = *cluster.map_shared_rank(&S, half ^ 1);   // the peer CTA's shared memory
-  const int b = blockIdx.x >> 1, i = threadIdx.x, K = a.K, k = a.k;
+  const int half = CL == 2 ? (int)cluster.block_rank() : 0;    // which side of the split this CTA owns
+  CloudStepSmem& P = CL == 2 ? *cluster.map_shared_rank(&S, half ^ 1) : S;   // the peer CTA's shared memory
+  auto cluster_sync = [&]() {
+    if (CL == 2) cluster.sync();
+    else __syncthreads();
+  };
+  const int b = CL == 2 ? blockIdx.x >> 1 : blockIdx.x, i = threadIdx.x, K = a.K, k = a.k;
   const int lane = i & 31, warp = i >> 5;
   bool live = i < K;
 
@@ -191,8 +199,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
   // the first remote store -- the grid build and the kNN walk hide the barrier latency.  No memory ordering is needed from
   // this pair (the rows written remotely, `nbrn`, are not initialised by their owner; the inbox counters are only pushed
   // to after the full cluster.sync below), so the arrive is relaxed.
-  if (a.bar_mode == 1) cluster.barrier_arrive();
-  else if (a.bar_mode == 2) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  if (CL == 2) {
+    if (a.bar_mode == 1) cluster.barrier_arrive();
+    else if (a.bar_mode == 2) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  }
   float4 me0 = make_float4(0.f, 0.f, 0.f, 0.f);        // point i (load order); re-assigned in cell order below
   if (live) {
     const float x = xs[3 * i + 0], y = xs[3 * i + 1], z = xs[3 * i + 2];
@@ -302,7 +312,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
 
   // ---- from here on thread t owns the t-th point in CELL order: the lanes of a warp are spatial neighbours, so
   //      their range queries walk (nearly) the same rows and candidates -- coherent loops, broadcast loads
-  const int rank0 = half == 0 ? 0 : S.split_rank, rank1 = half == 0 ? S.split_rank : K;
+  const int rank0 = (CL == 1 || half == 0) ? 0 : S.split_rank, rank1 = (CL == 2 && half == 0) ? S.split_rank : K;
   const int n_own = rank1 - rank0;
   live = i < n_own;
   // Two threads per query wherever the CTA has threads to spare (the split is at the median, so about half of them
@@ -420,8 +430,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
         }
     }
   }
-  if (a.bar_mode == 1) cluster.barrier_wait();          // the peer has started (see the arrive above)
-  else if (a.bar_mode == 2) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  if (CL == 2) {
+    if (a.bar_mode == 1) cluster.barrier_wait();          // the peer has started (see the arrive above)
+    else if (a.bar_mode == 2) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  }
   if (live) {
     uint32_t w[4];
 #pragma unroll
@@ -432,12 +444,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
     }
     const uint4 row16 = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4*>(&S.nbrn[p][0]) = row16;           // this CTA's copy
-    *reinterpret_cast<uint4*>(&P.nbrn[p][0]) = row16;           // the peer's copy (distributed shared memory)
+    if (CL == 2) *reinterpret_cast<uint4*>(&P.nbrn[p][0]) = row16;           // the peer's copy (distributed shared memory)
     int4* pv = reinterpret_cast<int4*>(g_nbr + ((size_t)b * K + p) * kCsKK);   // warm start of the next step
     pv[0] = make_int4(top.id[0], top.id[1], top.id[2], top.id[3]);
     pv[1] = make_int4(top.id[4], top.id[5], top.id[6], top.id[7]);
   }
-  cluster.sync();                       // both CTAs now hold all K lists
+  cluster_sync();                       // both CTAs now hold all K lists
 
   // ---- own edges: pair terms, mutual test, inbox pushes
   double ax = 0.0, ay = 0.0, az = 0.0;
@@ -459,7 +471,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
           ay += (double)(-gy);
           az += (double)(-gz);
         } else {
-          CloudStepSmem& O = ((int)S.cid[j] >= S.split_cell) == (half == 1) ? S : P;     // the CTA that owns j
+          CloudStepSmem& O = (CL == 1 || ((int)S.cid[j] >= S.split_cell) == (half == 1)) ? S : P;     // the CTA that owns j
           const uint32_t slot = atomicAdd(&O.inbox_cnt[j], 1u);
           if (slot < (uint32_t)a.inbox_cap) O.inbox[j][slot] = (uint16_t)p;
         }
@@ -468,7 +480,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
     ay += (double)sy;
     az += (double)sz;
   }
-  cluster.sync();                       // all pushes (local and remote) have landed
+  cluster_sync();                       // all pushes (local and remote) have landed
   float* ls = reinterpret_cast<float*>(&S.cell[0]);             // the grid is no longer needed: per-point loss staging
   ls[i] = 0.0f;
 
@@ -577,9 +589,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud
       for (int w = 0; w < kCsThreads / 32; ++w) t += S.red[6][w];
       if (half == 1) P.peer_loss = t;
     }
-    cluster.sync();
+    cluster_sync();
     if (i == 0 && half == 0) a.loss_part[b] = t + S.peer_loss;
   }
 }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCsThreads, 1) cloud_step_kernel(const CloudStepArgs a) {
+  cloud_step_body<2>(a);
+}
+__global__ void __launch_bounds__(kCsThreads, 1) cloud_step_solo_kernel(const CloudStepArgs a) { cloud_step_body<1>(a); }
 
 }  // namespace ifd

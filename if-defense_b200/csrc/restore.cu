@@ -573,6 +573,24 @@ float* opt_ws_v(void* ws, int B, int K) { return carve_opt_ws(ws, B, K).v; }
 
 static int g_inbox_cap = kCsInbox;   // ifd_test_hook(1, cap)
 static int g_bar_mode = 2;           // ifd_test_hook(4, mode): CloudStepArgs::bar_mode
+// CTAs per cloud of the fused tail.  The cluster pair finishes a launch sooner (43 vs 57 us at B = 64) but holds two SMs per
+// cloud -- and a tail CTA takes a whole SM's registers, nothing shares an SM with it.  A loop that runs ALONE wants the pair; loops
+// that run side by side (ifd_convonet_opt_batches, the host pipeline) want the one-CTA form, which leaves the other loops' decode
+// launches twice the SMs: 4549 -> 4870 clouds/s with two loops, 5436 with four (B = 64 x 1024, one B200).
+static int g_tail_ctas = 0;          // ifd_test_hook(5, n): 0 = by context (default), 1 = one CTA, 2 = cluster pair
+static thread_local int t_side_by_side = 0;      // set by the multi-batch entry points around their ifd_convonet_opt calls
+static int tail_ctas() { return g_tail_ctas ? g_tail_ctas : (t_side_by_side ? 1 : 2); }
+static int launch_cloud_step(const CloudStepArgs& c, int B, cudaStream_t st) {
+  if (tail_ctas() == 1) {
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_solo_kernel, sizeof(CloudStepSmem)));
+    cloud_step_solo_kernel<<<B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
+  } else {
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
+    cloud_step_kernel<<<2 * B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
+  }
+  IFD_LAUNCH_CHECK("cloud_step_kernel");
+  return IFD_OK;
+}
 
 // The fused per-cloud tail (cloud_step.cuh) handles one point per thread; larger clouds and k + 1 > 8 use the
 // first-generation kernels (knn_repulsion_kernel + adam_kernel), as does tail_kernel == 1.
@@ -616,9 +634,8 @@ int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int
     c.job = job; c.zero_mv = (fresh && i == 0 && P->step0 == 0) ? 1 : 0;
     {
       ProfileScope ps(1, st);
-      IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
-      cloud_step_kernel<<<2 * B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
-      IFD_LAUNCH_CHECK("cloud_step_kernel");
+      int rc_cs = launch_cloud_step(c, B, st);
+      if (rc_cs) return rc_cs;
     }
     if (stat) {
       stats_kernel<<<1, 32, 0, st>>>(dec_part, n_dec, w.loss_part, B, 1, K, P->knn_k, (float)P->rep_weight,
@@ -763,7 +780,7 @@ int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, con
 
   GraphKey key;
   memset(&key, 0, sizeof key);
-  key.B = B; key.K = K; key.R = R; key.n_blocks = n_blocks; key.slot = slot; key.inbox_cap = g_inbox_cap * 4 + g_bar_mode;
+  key.B = B; key.K = K; key.R = R; key.n_blocks = n_blocks; key.slot = slot; key.inbox_cap = (g_inbox_cap * 4 + g_bar_mode) * 4 + tail_ctas();
   memcpy(&key.P, P, sizeof(ifd_opt_params));
   GraphEntry* hit = nullptr;
   for (GraphEntry& e : g.entries)
@@ -772,6 +789,7 @@ int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, con
     // attributes first (cudaFuncSetAttribute is not a stream operation, but keep the capture free of anything else)
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v5_kernel, DecodeV5Smem::bytes(n_blocks)));
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
+    IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_solo_kernel, sizeof(CloudStepSmem)));
     const long long before = launch_counter_ref();
     IFD_CUDA_TRY(cudaStreamBeginCapture(g.cap, cudaStreamCaptureModeThreadLocal));
     // shapes only: every pointer the kernels use comes from the record of this slot
@@ -945,15 +963,13 @@ extern "C" int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const
   c.omb1 = (float)(1.0 - P->beta1); c.b2 = (float)P->beta2; c.omb2 = (float)(1.0 - P->beta2); c.adam_eps = (float)P->adam_eps;
   c.sc.neg_step_size = (float)(-(P->lr / (1.0 - pow(P->beta1, t))));
   c.sc.bc2_sqrt = (float)sqrt(1.0 - pow(P->beta2, t));
-  IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_kernel, sizeof(CloudStepSmem)));
-  cloud_step_kernel<<<2 * B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
-  IFD_LAUNCH_CHECK("cloud_step_kernel");
-  return IFD_OK;
+  return launch_cloud_step(c, B, st);
 }
 
-// A sequence of batches on device buffers, two at a time: one decode or tail launch occupies 128 of the 148 SMs (one CTA
-// per SM, B = 64), so the loops of two batches side by side keep the remaining SMs -- and every gap between dependent
-// launches -- busy.  Forks from `stream` into two internal streams and joins back into it.
+// A sequence of batches on device buffers, up to four at a time: every launch of a loop depends on the one before it and neither
+// kernel fills the machine (a decode launch: 128 SMs at B = 64 and latency-bound phases; a one-CTA tail: 64 SMs), so the loops
+// of several batches side by side keep the remaining SMs -- and every gap between dependent launches -- busy.  Forks from
+// `stream` into internal streams and joins back into it.
 namespace {
 constexpr int kMaxLanes = 4;
 struct PairStreams {
@@ -961,7 +977,7 @@ struct PairStreams {
   cudaEvent_t fork = nullptr, join[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   int device = -1;                  // the device the streams and events belong to
 };
-int g_lanes = 2;   // loops side by side; ifd_test_hook(2, n) (the workspace must then hold n parts)
+int g_lanes = 4;   // loops side by side; ifd_test_hook(2, n); callers size the workspace with ifd_convonet_opt_batches_workspace_bytes
 thread_local PairStreams g_pair;
 int ensure_pair() {
   int dev = 0;
@@ -1008,11 +1024,13 @@ extern "C" int ifd_convonet_opt_batches(int n_batches, const float* const* plane
   cudaStream_t st = as_stream(stream);
   IFD_CUDA_TRY(cudaEventRecord(g_pair.fork, st));
   for (int i = 0; i < lanes; ++i) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pair.s[i], g_pair.fork, 0));
+  t_side_by_side = (lanes > 1 && n_batches > 1) ? 1 : 0;
   for (int j = 0; j < n_batches && rc == IFD_OK; ++j) {
     const int s = j % lanes;
     rc = ifd_convonet_opt(planes_cl[j], dec_weights, xyz[j], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr,
                           (char*)workspace + (size_t)s * one, one, g_pair.s[s]);
   }
+  t_side_by_side = 0;
   // join on every exit path: whatever was enqueued on the lanes must be ordered before the caller's later work on `stream`
   // (the caller may free or reuse the workspace right after an error)
   for (int i = 0; i < lanes; ++i) {
@@ -1022,6 +1040,11 @@ extern "C" int ifd_convonet_opt_batches(int n_batches, const float* const* plane
   }
   return rc;
 }
+
+namespace ifd {
+int opt_lanes() { return g_lanes; }
+void opt_side_by_side(int on) { t_side_by_side = on ? 1 : 0; }
+}  // namespace ifd
 
 extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float* dec_weights, const float* xyz, int B, int K,
                                             int R, int C, int H, int n_blocks, double padding, double occ_target, int B_ref,
@@ -1120,6 +1143,7 @@ extern "C" void ifd_test_hook(int key, int value) {
   if (key == 2) g_lanes = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);
   if (key == 3) g_use_graph = value ? 1 : 0;
   if (key == 4) g_bar_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
+  if (key == 5) g_tail_ctas = value == 1 ? 1 : (value == 2 ? 2 : 0);
 }
 
 extern "C" int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream) {

@@ -280,10 +280,11 @@ int ifd_opt_tail_step(float* xyz, float* adam_m, float* adam_v, const float* g_o
 
 /* The same for a sequence of batches on DEVICE buffers (the loop of defend_point_cloud over batches, opt_defense.py:
  * 272-312, with the encoder outputs already in kernel layout): batch j uses planes_cl[j] / xyz[j] (in place), all of B
- * clouds.  The loops of two consecutive batches run side by side on two internal streams forked from and joined back
- * into `stream` (joined on error paths too) -- one launch of the loop fills 128 of the 148 SMs at B = 64.  workspace:
- * ifd_convonet_opt_batches_workspace_bytes(B, K) (2 x ifd_convonet_opt_workspace_bytes, each rounded up to 256 bytes).  Results are bit-identical to n_batches calls of
- * ifd_convonet_opt. */
+ * clouds.  The loops of up to four consecutive batches run side by side on internal streams forked from and joined back
+ * into `stream` (joined on error paths too) -- every launch of a loop depends on the one before it and none fills the
+ * machine; in this mode the per-cloud tail runs as ONE CTA per cloud (half the SMs per launch).  workspace:
+ * ifd_convonet_opt_batches_workspace_bytes(B, K) (one 256-byte-rounded ifd_convonet_opt_workspace_bytes per loop in
+ * flight).  Results are bit-identical to n_batches calls of ifd_convonet_opt. */
 size_t ifd_convonet_opt_batches_workspace_bytes(int B, int K);   /* = lanes x the 256-byte-rounded single-loop workspace */
 int ifd_convonet_opt_batches(int n_batches, const float* const* planes_cl, const float* dec_weights, float* const* xyz,
                              int B, int K, int R, int C, int H, int n_blocks, const ifd_opt_params* params,

@@ -55,6 +55,15 @@ def clouds(kind, B, K, seed):
     raise ValueError(kind)
 
 
+@pytest.fixture(params=[2, 1], ids=["pair", "solo"], autouse=True)
+def tail_ctas(request):
+    """Every test of this file runs with the cluster form of cloud_step (two CTAs per cloud, the default) and with the one-CTA
+    form (ifd_test_hook(5, 1)): same lists, same bits."""
+    capi.lib().ifd_test_hook(5, request.param)
+    yield request.param
+    capi.lib().ifd_test_hook(5, 0)
+
+
 def test_tail_golden_lists_loss_and_gradient(geo):
     """Cold (plain scan) and warm (grid range query) calls on the reference fixture: neighbour lists bit-exact,
     loss and summed pair gradients at rounding level, xyz untouched when lr = 0."""
