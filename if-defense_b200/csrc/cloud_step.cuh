@@ -68,6 +68,7 @@ struct CloudStepSmem {
   uint16_t inbox[kCsMaxK][kCsInbox];         // sources of non-mutual in-edges
   uint32_t inbox_cnt[kCsMaxK];
   uint16_t sorted[kCsMaxK];                  // point indices in cell order
+  float4 spos[kCsMaxK];                      // pos in cell order: the range walk reads candidate t with ONE load (no index hop)
   float gmv[3][3 * kCsMaxK];                 // g_occ, m, v of the cloud, flat [K][3] (coalesced in, coalesced out)
   uint16_t cid[kCsMaxK];                     // cell of every point (ownership: cell < split -> CTA 0)
   uint16_t hcnt[kCsMaxK];                    // candidates found by the helper thread of each query slot
@@ -307,7 +308,11 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepArgs& a) {
       }
   }
   __syncthreads();
-  if (live) S.sorted[atomicAdd(&S.cell[cid + 1], 1u)] = (uint16_t)i;
+  if (live) {
+    const uint32_t slot = atomicAdd(&S.cell[cid + 1], 1u);
+    S.sorted[slot] = (uint16_t)i;
+    S.spos[slot] = me0;
+  }
   __syncthreads();                      // now cell[c] .. cell[c + 1] delimit cell c (cell[0] == 0)
 
   // ---- from here on thread t owns the t-th point in CELL order: the lanes of a warp are spatial neighbours, so
@@ -386,14 +391,20 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepArgs& a) {
               t = (int)S.cell[row + bx0];
               t1 = (int)S.cell[row + bx1 + 1];
             }
-          } else {
-            const int j = S.sorted[t++];
-            const float4 c = S.pos[j];
-            const float d = add_rn(add_rn(c.w, dot3_chain(mx, my, mz, c.x, c.y, c.z)), me.w);
-            if (d <= tau) {
-              if (cnt < kCsInbox) col[cnt * kCsThreads] = (uint16_t)j;
+          } else {                                             // two candidates per step (independent loads and key chains)
+            const bool two = t + 1 < t1;
+            const float4 c0 = S.spos[t], c1 = S.spos[two ? t + 1 : t];
+            const float d0 = add_rn(add_rn(c0.w, dot3_chain(mx, my, mz, c0.x, c0.y, c0.z)), me.w);
+            const float d1 = add_rn(add_rn(c1.w, dot3_chain(mx, my, mz, c1.x, c1.y, c1.z)), me.w);
+            if (d0 <= tau) {
+              if (cnt < kCsInbox) col[cnt * kCsThreads] = S.sorted[t];
               ++cnt;
             }
+            if (two && d1 <= tau) {
+              if (cnt < kCsInbox) col[cnt * kCsThreads] = S.sorted[t + 1];
+              ++cnt;
+            }
+            t += two ? 2 : 1;
           }
         }
       }

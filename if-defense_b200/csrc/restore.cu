@@ -716,7 +716,7 @@ int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, f
 }
 
 // ---- cached graphs of the loop --------------------------------------------------------------------------------------------
-constexpr int kJobSlots = 8;       // one LoopJob record + one set of graphs per caller stream (LRU over 8 streams)
+constexpr int kJobSlots = 16;      // one LoopJob record + one set of graphs per caller stream (LRU over 16 streams: the device-batch lanes and the host pipeline use 4 each)
 struct GraphKey {
   int B, K, R, n_blocks, slot, inbox_cap;
   ifd_opt_params P;
@@ -808,7 +808,7 @@ int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, con
     const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (ei != cudaSuccess) return cuda_fail(ei, "cudaGraphInstantiate");
-    if (g.entries.size() >= 16) {                  // evict the least recently used graph
+    if (g.entries.size() >= 32) {                  // evict the least recently used graph
       size_t lru = 0;
       for (size_t i = 1; i < g.entries.size(); ++i)
         if (g.entries[i].used < g.entries[lru].used) lru = i;
