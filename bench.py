@@ -463,6 +463,8 @@ def main():
     xs = [torch.empty_like(x) for _ in range(n_max)]
     if os.environ.get("IFD_LANES"):                         # experiment knob: loops side by side (library default: 4)
         L.ifd_test_hook(2, int(os.environ["IFD_LANES"]))
+    if os.environ.get("IFD_JAC"):                           # experiment knob: 0 = the decode kernel gathers the texels twice
+        L.ifd_test_hook(7, int(os.environ["IFD_JAC"]))
     if os.environ.get("IFD_TAIL_CTAS"):                     # experiment knob: CTAs per cloud of the fused tail (default: by context)
         L.ifd_test_hook(5, int(os.environ["IFD_TAIL_CTAS"]))
     ws2_bytes = int(L.ifd_convonet_opt_batches_workspace_bytes(B, K))

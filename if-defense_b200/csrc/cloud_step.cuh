@@ -374,24 +374,39 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepArgs& a) {
     int cnt = 0;
     {
       const int ny = by1 - by0 + 1, stride = (scan && helped) ? 2 : 1;
-      int cz = bz0, cy = by0 + (helper ? 1 : 0) - stride, t = 0, t1 = 0;    // rows in (cz, cy) order, every stride-th one
+      int cz = bz0, cy = by0 + (helper ? 1 : 0) - stride;      // rows in (cz, cy) order, every stride-th one
+      // The bounds of the NEXT row are fetched while the current row's candidates are evaluated: a step is "take the
+      // prefetched row if the current one is used up, evaluate up to two candidates", so an exhausted row costs no
+      // step of its own and no shared-memory round trip on the critical path.
+      int nt = 0, nt1 = 0;
+      auto fetch_row = [&]() -> bool {
+        cy += stride;
+        while (cy > by1) {
+          cy -= ny;
+          ++cz;
+        }
+        if (cz > bz1) return false;
+        const int row = cs_index(0, cy, cz);
+        nt = (int)S.cell[row + bx0];
+        nt1 = (int)S.cell[row + bx1 + 1];
+        return true;
+      };
       bool more = scan && ny > 0;
+      bool have_next = more && fetch_row();
+      int t = 0, t1 = 0;
+      more = have_next;
       while (__any_sync(0xffffffffu, more)) {
         if (more) {
-          if (t >= t1) {                                       // next row of the box
-            cy += stride;
-            while (cy > by1) {
-              cy -= ny;
-              ++cz;
-            }
-            if (cz > bz1) {
-              more = false;
+          if (t >= t1) {                                       // current row used up: the prefetched one becomes current
+            if (have_next) {
+              t = nt;
+              t1 = nt1;
+              have_next = fetch_row();
             } else {
-              const int row = cs_index(0, cy, cz);
-              t = (int)S.cell[row + bx0];
-              t1 = (int)S.cell[row + bx1 + 1];
+              more = false;
             }
-          } else {                                             // two candidates per step (independent loads and key chains)
+          }
+          if (more && t < t1) {                                // two candidates per step (independent loads and key chains)
             const bool two = t + 1 < t1;
             const float4 c0 = S.spos[t], c1 = S.spos[two ? t + 1 : t];
             const float d0 = add_rn(add_rn(c0.w, dot3_chain(mx, my, mz, c0.x, c0.y, c0.z)), me.w);

@@ -83,6 +83,7 @@ struct LoopJob {
   float* m;              // Adam state (workspace)
   float* v;
   int32_t* nbr;          // [B][K][8] warm-start neighbour lists (workspace)
+  float* jac;            // [B][K][3][32] d c / d xyz of the decode kernel's forward gather (workspace), or nullptr
 };
 bool profile_on();       // api.cu: per-kernel event timing is enabled on this thread
 

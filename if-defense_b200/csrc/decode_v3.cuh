@@ -91,7 +91,9 @@ struct DecodeV3Args {
   double* stat_part;
   int n, K, B, R, n_blocks;
   float denom, target, ginv;
-  const LoopJob* job;    // non-null: planes / W / Wimg / xyz / grad_out come from this record (graph replay)
+  const LoopJob* job;    // non-null: planes / W / Wimg / xyz / grad_out / jac come from this record (graph replay)
+  float* jac;            // [n][3][32] workspace: the forward gather leaves d c / d xyz here, the backward pass reads it back
+                         // instead of gathering the texels again (nullptr: gather twice)
 };
 
 // One layer on the tensor core for this thread's tile: A := split(x) ; D = A.B ; returns D row in `d`.

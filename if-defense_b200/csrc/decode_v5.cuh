@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   const float* __restrict__ g_Wimg = a.job ? a.job->Wimg : a.Wimg;
   const float* __restrict__ g_xyz = a.job ? a.job->xyz : a.xyz;
   float* __restrict__ g_grad = a.job ? a.job->g_occ : a.grad_out;
+  float4* __restrict__ g_jac4 = reinterpret_cast<float4*>(a.job ? a.job->jac : a.jac);
   using L = ConvDecLayout<32>;
   const int nb = a.n_blocks;
   const int n_layers = 3 * nb;
@@ -245,18 +246,47 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     V3Taps ts;
     v3_taps(pk, fr, a.R, (uint32_t)b * plane4 + (uint32_t)j4, (uint32_t)a.B * plane4, ts);
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    // d c / d (grid coordinate of axis ax), this lane's four channels: the bilinear form differentiated tap by tap (the
+    // expressions of the backward gather below, applied to the texel vectors instead of to their dot products with g_c).
+    // The SAME thread reads it back after the MLP: 384 B per point through L2 instead of a second 1536 B texel gather.
+    float4 jx[3] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
+      float4 v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) v[t] = __ldg(planes4 + ts.off[pl][t]);
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float4 v = __ldg(planes4 + ts.off[pl][t]);
-        s.x = fmaf(v.x, ts.w[pl][t], s.x);
-        s.y = fmaf(v.y, ts.w[pl][t], s.y);
-        s.z = fmaf(v.z, ts.w[pl][t], s.z);
-        s.w = fmaf(v.w, ts.w[pl][t], s.w);
+        s.x = fmaf(v[t].x, ts.w[pl][t], s.x);
+        s.y = fmaf(v[t].y, ts.w[pl][t], s.y);
+        s.z = fmaf(v[t].z, ts.w[pl][t], s.z);
+        s.w = fmaf(v[t].w, ts.w[pl][t], s.w);
       }
       c.x += s.x; c.y += s.y; c.z += s.z; c.w += s.w;
+      if (g_jac4) {
+        // d/dw and d/dh of the bilinear form as tap coefficients (a clamped neighbour contributes nothing: has1 == 0)
+        const int aw = plane_axis_w(pl), ah = plane_axis_h(pl);
+        const float mw = ts.has1[aw] ? 1.0f : 0.0f, mh = ts.has1[ah] ? 1.0f : 0.0f;
+        const float fw = ts.f[aw], fh = ts.f[ah], nfw = 1.0f - fw, nfh = 1.0f - fh;
+        const float cw[4] = {-nfh, mw * nfh, -(mh * fh), mw * mh * fh};       // nw, ne, sw, se
+        const float ch[4] = {-nfw, -(mw * fw), mh * nfw, mw * mh * fw};
+        float4& jw = jx[aw];
+        float4& jh = jx[ah];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          jw.x = fmaf(v[t].x, cw[t], jw.x); jw.y = fmaf(v[t].y, cw[t], jw.y); jw.z = fmaf(v[t].z, cw[t], jw.z); jw.w = fmaf(v[t].w, cw[t], jw.w);
+          jh.x = fmaf(v[t].x, ch[t], jh.x); jh.y = fmaf(v[t].y, ch[t], jh.y); jh.z = fmaf(v[t].z, ch[t], jh.z); jh.w = fmaf(v[t].w, ch[t], jh.w);
+        }
+      }
+    }
+    if (g_jac4 && tile0 + gslot < a.n) {
+      float4* dst = g_jac4 + ((size_t)(tile0 + gslot) * 3) * 8 + j4;
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        const bool on = (pk[ax] >> 17) & 1;                      // clamped / dead axis: no gradient
+        __stcg(dst + ax * 8, on ? jx[ax] : make_float4(0.f, 0.f, 0.f, 0.f));
+      }
     }
     feat[(j4 * 4 + 0) * kV4Stride + gslot] = c.x;
     feat[(j4 * 4 + 1) * kV4Stride + gslot] = c.y;
@@ -497,9 +527,40 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   }
   __syncwarp();
 
+  const float dsc = ((float)(a.R - 1) * 0.5f) * 2.0f / a.denom;        // Axis::dscale of a live, unclipped axis
+  if (g_jac4) {
+    // ---------------- backward "gather" from the Jacobian this thread stored in the forward pass (warp-local slots)
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+      const int src = it * 4 + grp, gslot = warp * 32 + src;
+      const int pi_raw = tile0 + gslot;
+      const bool in = pi_raw < a.n;
+      const float4 gc = make_float4(feat[(j4 * 4 + 0) * kV4Stride + gslot], feat[(j4 * 4 + 1) * kV4Stride + gslot],
+                                    feat[(j4 * 4 + 2) * kV4Stride + gslot], feat[(j4 * 4 + 3) * kV4Stride + gslot]);
+      const float4* srcj = g_jac4 + ((size_t)(in ? pi_raw : 0) * 3) * 8 + j4;
+      float gi[3];
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        const float4 j = in ? __ldcg(srcj + ax * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gi[ax] = (j.x * gc.x + j.y * gc.y) + (j.z * gc.z + j.w * gc.w);
+      }
+#pragma unroll
+      for (int ax = 0; ax < 3; ++ax) {
+        gi[ax] += __shfl_xor_sync(0xffffffffu, gi[ax], 1);
+        gi[ax] += __shfl_xor_sync(0xffffffffu, gi[ax], 2);
+        gi[ax] += __shfl_xor_sync(0xffffffffu, gi[ax], 4);
+      }
+      if (j4 == 0 && in) {
+        const float4 gp = gpart[gslot];
+        const size_t o = (size_t)pi_raw * 3;
+        g_grad[o + 0] = gp.x + gi[0] * dsc;
+        g_grad[o + 1] = gp.y + gi[1] * dsc;
+        g_grad[o + 2] = gp.z + gi[2] * dsc;
+      }
+    }
+  } else {
   // ---------------- backward gather (v4's; warp-local: slots 32w .. 32w+31)
   const V3Geom geo2 = v3_geom(p0, p1, p2, a.R, a.denom, pi / a.K);
-  const float dsc = ((float)(a.R - 1) * 0.5f) * 2.0f / a.denom;        // Axis::dscale of a live, unclipped axis
 #pragma unroll 2
   for (int it = 0; it < 8; ++it) {
     const int src = it * 4 + grp, gslot = warp * 32 + src;
@@ -545,6 +606,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
       g_grad[o + 1] = gp.y + gi[1] * (((pk[1] >> 17) & 1) ? dsc : 0.0f);
       g_grad[o + 2] = gp.z + gi[2] * (((pk[2] >> 17) & 1) ? dsc : 0.0f);
     }
+  }
   }
   umma::fence_before_sync();
   __syncthreads();

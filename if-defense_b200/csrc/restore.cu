@@ -497,8 +497,10 @@ static int launch_decode_v2(const DecodeArgs& a, cudaStream_t st) {
   return IFD_OK;
 }
 
-static int launch_decode_v5(const DecodeArgs& a, const float* wimg, cudaStream_t st) {
+static int g_use_jac = 1;            // ifd_test_hook(7, 0 / 1): decode v5 keeps d c / d xyz of its forward gather (0: gathers twice)
+static int launch_decode_v5(const DecodeArgs& a, const float* wimg, float* jac, cudaStream_t st) {
   DecodeV3Args v{};
+  v.jac = g_use_jac ? jac : nullptr;
   v.planes = a.planes; v.W = a.W; v.Wimg = wimg; v.xyz = a.xyz; v.grad_out = a.grad_out; v.stat_part = a.stat_part;
   v.n = a.B * a.K; v.K = a.K; v.B = a.B; v.R = a.R; v.n_blocks = a.n_blocks;
   v.denom = a.denom; v.target = a.target; v.ginv = a.ginv; v.job = a.job;
@@ -540,6 +542,7 @@ struct OptWorkspace {
   double* dec_part;
   int32_t* nbr;
   float* wimg;
+  float* jac;
   size_t bytes;
 };
 static OptWorkspace carve_opt_ws(void* base, int B, int K) {
@@ -559,6 +562,7 @@ static OptWorkspace carve_opt_ws(void* base, int B, int K) {
   w.dec_part = (double*)take((size_t)((B * K + kDecThreads - 1) / kDecThreads) * 2 * sizeof(double));
   w.nbr = (int32_t*)take((size_t)B * K * 8 * sizeof(int32_t));
   w.wimg = (float*)take((size_t)2 * 3 * kMaxBlocks * kV3ImgFloats * sizeof(float));
+  w.jac = (float*)take((size_t)B * K * 3 * 32 * sizeof(float));      // decode v5: d c / d xyz per point (384 B)
   w.bytes = off;
   return w;
 }
@@ -707,7 +711,7 @@ int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, f
     a.stat_part = stat ? w.dec_part : nullptr;
     {
       ProfileScope ps(0, st);
-      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : launch_decode_v2(a, st);
+      rc = dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, w.jac, st) : launch_decode_v2(a, st);
       if (rc) return rc;
     }
     if ((rc = opt_step_tail(xyz, m, v, w.g_occ, B, K, P, i, workspace, stat, w.dec_part, n_dec, stats_out, dk != 1 || grid3d, st, job, fresh))) return rc;
@@ -780,7 +784,7 @@ int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, con
 
   GraphKey key;
   memset(&key, 0, sizeof key);
-  key.B = B; key.K = K; key.R = R; key.n_blocks = n_blocks; key.slot = slot; key.inbox_cap = (g_inbox_cap * 4 + g_bar_mode) * 4 + tail_ctas();
+  key.B = B; key.K = K; key.R = R; key.n_blocks = n_blocks; key.slot = slot; key.inbox_cap = ((g_inbox_cap * 4 + g_bar_mode) * 4 + tail_ctas()) * 2 + g_use_jac;
   memcpy(&key.P, P, sizeof(ifd_opt_params));
   GraphEntry* hit = nullptr;
   for (GraphEntry& e : g.entries)
@@ -939,7 +943,7 @@ extern "C" int ifd_convonet_opt(const float* planes_cl, const float* dec_weights
   // whole loop (pack, n_steps x {decode, cloud_step}, normalise): the kernels read their buffers from a LoopJob record, so
   // the graph does not depend on the pointers and the host enqueues two operations instead of ~400.
   if (g_use_graph && dk >= 4 && !stats && !adam_m && P->step0 == 0 && P->n_steps >= 4 && opt_tail_fused(K, P) && !profile_on()) {
-    LoopJob job{planes_cl, dec_weights, w.wimg, xyz, w.g_occ, m, v, w.nbr};
+    LoopJob job{planes_cl, dec_weights, w.wimg, xyz, w.g_occ, m, v, w.nbr, g_use_jac ? w.jac : nullptr};
     return launch_loop_graph(job, B, K, R, n_blocks, P, st);
   }
   return enqueue_loop(planes_cl, dec_weights, xyz, m, v, !adam_m || P->step0 == 0, B, K, R, n_blocks, P, stats_out, workspace, nullptr, st);
@@ -1070,7 +1074,7 @@ extern "C" int ifd_convonet_decode_bce_grad(const float* planes_cl, const float*
     convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, nullptr);
     IFD_LAUNCH_CHECK("convonet_pack_umma_v5_kernel");
   }
-  return dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, st) : launch_decode_v2(a, st);
+  return dk == 1 ? launch_decode(kBce, a, st) : dk == 5 ? launch_decode_v5(a, w.wimg, w.jac, st) : launch_decode_v2(a, st);
 }
 
 // ---- the 'grid' (feature volume, trilinear) variant ------------------------------------------------------------------------
@@ -1143,6 +1147,7 @@ extern "C" void ifd_test_hook(int key, int value) {
   if (key == 2) g_lanes = value < 1 ? 1 : (value > kMaxLanes ? kMaxLanes : value);
   if (key == 3) g_use_graph = value ? 1 : 0;
   if (key == 4) g_bar_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
+  if (key == 7) g_use_jac = value ? 1 : 0;
   if (key == 5) g_tail_ctas = value == 1 ? 1 : (value == 2 ? 2 : 0);
 }
 
