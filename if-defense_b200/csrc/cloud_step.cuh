@@ -19,9 +19,16 @@
 //     source) in fp64, so the result does not depend on atomic arrival order: bitwise reproducible;
 //   * Adam runs in the same thread; xyz, m, v make one round trip to HBM/L2 per step.
 //
-// Two CTAs (a thread-block cluster) per cloud: both build the whole grid, the cloud is split at the cell boundary
-// nearest the median (a deterministic function of the cell histogram), each CTA ranks / sums / updates the points
-// on its side, neighbour lists and non-mutual in-edges cross through distributed shared memory.
+// Two forms of the same body (template on the cluster size, same bits):
+//   * cloud_step_kernel: two CTAs (a thread-block cluster) per cloud.  Both build the whole grid, the cloud is split at the
+//     cell boundary nearest the median (a deterministic function of the cell histogram), each CTA ranks / sums / updates the
+//     points on its side (the idle half of its threads walks every other row of a query's box), neighbour lists and
+//     non-mutual in-edges cross through distributed shared memory.  Shortest launch (42 us at B = 64): a loop running alone.
+//   * cloud_step_solo_kernel: one CTA per cloud, one thread per query, no cluster traffic.  A longer launch (53 us) on HALF
+//     the SMs -- and a tail CTA takes a whole SM's registers, so nothing shares an SM with it: when the loops of several
+//     batches run side by side this form leaves the other loops' decode launches twice the room (restore.cu picks it then).
+// The range walk reads candidates from a copy of the positions in CELL order (one load per candidate, no index hop), takes
+// two candidates per step, and fetches the next row's bounds while the current row is evaluated.
 #pragma once
 #include <cooperative_groups.h>
 

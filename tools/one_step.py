@@ -15,11 +15,13 @@ ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--B", type=int, default=64)
 ap.add_argument("--decode-kernel", type=int, default=0)
+ap.add_argument("--tail-ctas", type=int, default=0, help="ifd_test_hook(5, n): 1 = one-CTA tail, 2 = cluster pair, 0 = by context")
 a = ap.parse_args()
 case = synth.make_case(a.B, K=1024, seed=0, device="cuda")
 dec = convonet.ConvONetDecoder(case.sd)
 pl = convonet.planes_to_channels_last({k: v.cuda() for k, v in case.c.items()})
 L = capi.lib()
+L.ifd_test_hook(5, a.tail_ctas)
 P = capi.default_params(n_steps=a.iters + 1, B_ref=a.B, decode_kernel=a.decode_kernel)
 ws = torch.empty(L.ifd_convonet_opt_workspace_bytes(a.B, 1024), dtype=torch.uint8, device="cuda")
 C, H, nb = dec.dims
