@@ -514,7 +514,7 @@ def main():
     for case, _, _ in batches:
         pl = torch.stack([case.c[k] for k in ("xz", "xy", "yz")]).contiguous().pin_memory()
         host.append((pl.numpy(), case.p0.clone().pin_memory().numpy()))
-    n_e2e = max(4, min(args.steps, 12))
+    n_e2e = max(4, min(args.steps, 24))          # enough batches that the fill and drain of four loops in flight do not dominate
     seq = [host[j % NB] for j in range(n_e2e)]
     out_pinned = [torch.empty((B, K, 3), dtype=torch.float32).pin_memory() for _ in range(n_e2e)]     # result buffers (host)
     out_np = [t.numpy() for t in out_pinned]

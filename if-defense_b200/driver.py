@@ -219,13 +219,50 @@ class Defender:
         out = {k: torch.cat(v) for k, v in out.items()}
         return out["c"] if list(out) == ["c"] else out
 
+    def _slice_streams(self, lo, hi, seed):
+        """One numpy and one torch RNG stream per cloud, a function of (seed, cloud index) only."""
+        rngs = [np.random.default_rng([int(seed), i]) for i in range(lo, hi)]
+        gens = [torch.Generator().manual_seed((int(seed) * 1000003 + i) % (2 ** 63 - 1)) for i in range(lo, hi)]
+        return rngs, gens
+
+    def restore_slices(self, pc, segments, seed):
+        """restore_slice for a list of (lo, hi, B_ref) segments, as a two-stage pipeline (the device pre-processing path):
+        SOR + preprocess + encoder of segment j + 1 are enqueued on a side stream while the loop of segment j runs, and the
+        restored clouds come back with one D2H per segment after the next stage has been enqueued.  Same bits as
+        restore_slice segment by segment (every draw comes from the per-cloud streams)."""
+        a = self.args
+        if not (a.device_preprocess and isinstance(pc, np.ndarray) and pc.ndim == 3) or not segments:
+            return [self.restore_slice(pc, lo, hi, n, seed) for lo, hi, n in segments]
+        side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+
+        def stage(seg):
+            lo, hi, _ = seg
+            rngs, gens = self._slice_streams(lo, hi, seed)
+            with torch.cuda.stream(side), torch.no_grad():
+                sel, pts = self.prepare_batch_device(np.asarray(pc[lo:hi])[..., :3], rngs, gens)
+                c = self.encode_chunked(sel, lo)
+                done = torch.cuda.Event()
+                done.record(side)
+            return pts, c, done
+
+        out = []
+        nxt = stage(segments[0])
+        for j, (lo, hi, n) in enumerate(segments):
+            pts, c, done = nxt
+            main.wait_event(done)
+            x = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight, iterations=a.iterations, B_ref=n,
+                                              return_tensor=True)
+            nxt = stage(segments[j + 1]) if j + 1 < len(segments) else None
+            out.append(x.cpu().numpy())
+        return out
+
     def restore_slice(self, pc, lo, hi, B_ref, seed):
         """Clouds lo..hi-1 of a reference batch of B_ref clouds, every random draw taken from a per-cloud stream
         (seed, cloud index) so that the result does not depend on how the job is cut into slices."""
         a = self.args
         raw = np.asarray(pc[lo:hi])[..., :3]
-        rngs = [np.random.default_rng([int(seed), i]) for i in range(lo, hi)]
-        gens = [torch.Generator().manual_seed((int(seed) * 1000003 + i) % (2 ** 63 - 1)) for i in range(lo, hi)]
+        rngs, gens = self._slice_streams(lo, hi, seed)
         if a.device_preprocess and raw.ndim == 3:
             sel, pts = self.prepare_batch_device(raw, rngs, gens)
         else:
@@ -245,7 +282,8 @@ class Defender:
         cut into `world` contiguous slices (shard.plan), each rank restores its slices with the batch's B_ref, one
         all_gather returns all N restored clouds in input order on every rank."""
         return shard.restore_sharded(lambda lo, hi, n: self.restore_slice(pc, lo, hi, n, seed), len(pc), self.args.batch_size,
-                                     rank=rank, world=world, device=self.device)
+                                     rank=rank, world=world, device=self.device,
+                                     restore_many=lambda segs: self.restore_slices(pc, segs, seed))
 
 
 class ONetDefender(Defender):

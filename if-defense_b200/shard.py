@@ -59,15 +59,20 @@ def gather_in_order(local, segments_per_rank, n_clouds, rank, world, device=None
     return out
 
 
-def restore_sharded(restore_fn, n_clouds, batch_size, rank=None, world=None, device=None):
+def restore_sharded(restore_fn, n_clouds, batch_size, rank=None, world=None, device=None, restore_many=None):
     """restore_fn(lo, hi, B_ref) -> restored clouds lo..hi-1 ([hi-lo, K, 3]) with the batch-mean factor 1/B_ref.
-    Runs this rank's segments and returns all n_clouds restored clouds in input order (on every rank)."""
+    Runs this rank's segments and returns all n_clouds restored clouds in input order (on every rank).
+    restore_many (optional): callable(list of (lo, hi, B_ref)) -> list of arrays, used instead of one restore_fn call per
+    segment (lets the caller overlap the stages of consecutive segments)."""
     if world is None:
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     if rank is None:
         rank = dist.get_rank() if world > 1 else 0
     segs = plan(n_clouds, batch_size, world)
-    mine = [np.asarray(restore_fn(a, b, n), dtype=np.float32) for a, b, n in segs[rank]]
+    if restore_many is not None:
+        mine = [np.asarray(x, dtype=np.float32) for x in restore_many(list(segs[rank]))]
+    else:
+        mine = [np.asarray(restore_fn(a, b, n), dtype=np.float32) for a, b, n in segs[rank]]
     K = _agree_K(mine[0].shape[1] if mine else None, world)       # a rank with no segment learns K from the others
     local = np.concatenate(mine, axis=0) if mine else np.zeros((0, K, 3), dtype=np.float32)
     return gather_in_order(local, segs, n_clouds, rank, world, device)

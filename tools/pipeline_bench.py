@@ -19,6 +19,9 @@ def main():
     ap.add_argument("--clouds", type=int, default=384)
     ap.add_argument("--batch", type=int, default=192)
     a = ap.parse_args()
+    if os.environ.get("IFD_JAC"):                 # experiment knob (see bench.py)
+        from ifdefense_b200 import capi
+        capi.lib().ifd_test_hook(7, int(os.environ["IFD_JAC"]))
     model = models.build_convonet()
     model.load_state_dict(models.synthetic_state_dict("convonet", 0))
     base = synth.clouds(32)
