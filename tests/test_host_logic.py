@@ -112,11 +112,13 @@ def test_restorer_part_policy():
     from ifdefense_b200 import convonet
     r = convonet.Restorer.__new__(convonet.Restorer)
     r.side_by_side = True
-    assert [r._parts(b) for b in (1, 64, 127, 128, 164, 192, 193, 256, 384)] == [1, 1, 1, 2, 2, 2, 1, 4, 4]
+    # batches of >= 96 clouds run as equal parts of at most 64 clouds side by side (64 clouds = one launch of the one-CTA tail on
+    # 64 of the 148 SMs; the library keeps up to four loops in flight); a prime count stays one loop
+    assert [r._parts(b) for b in (1, 64, 95, 96, 127, 128, 164, 192, 193, 256, 384)] == [1, 1, 1, 2, 1, 2, 4, 3, 1, 4, 6]
     r.side_by_side = False
     assert r._parts(192) == 1
-    r.side_by_side = 3
-    assert r._parts(192) == 3 and r._parts(128) == 1
+    r.side_by_side = 4
+    assert r._parts(192) == 4 and r._parts(190) == 1
 
 
 def test_bench_emits_exactly_one_stdout_line_despite_library_chatter():
