@@ -1028,11 +1028,17 @@ extern "C" int ifd_convonet_opt_batches(int n_batches, const float* const* plane
   cudaStream_t st = as_stream(stream);
   IFD_CUDA_TRY(cudaEventRecord(g_pair.fork, st));
   for (int i = 0; i < lanes; ++i) IFD_CUDA_TRY(cudaStreamWaitEvent(g_pair.s[i], g_pair.fork, 0));
+  // Consecutive calls start on different lanes (a caller that keeps several calls in flight from different streams -- the
+  // sharded driver does -- gets their loops side by side instead of queued behind each other on lane 0, 1, ...); inside a
+  // call batch j uses workspace part j % lanes, which is this call's own.
+  static thread_local int next_lane = 0;
+  const int lane0 = next_lane;
+  next_lane = (next_lane + (n_batches < lanes ? n_batches : lanes)) % lanes;
   t_side_by_side = (lanes > 1 && n_batches > 1) ? 1 : 0;
   for (int j = 0; j < n_batches && rc == IFD_OK; ++j) {
     const int s = j % lanes;
     rc = ifd_convonet_opt(planes_cl[j], dec_weights, xyz[j], nullptr, nullptr, B, K, R, C, H, n_blocks, P, nullptr,
-                          (char*)workspace + (size_t)s * one, one, g_pair.s[s]);
+                          (char*)workspace + (size_t)s * one, one, g_pair.s[(lane0 + j) % lanes]);
   }
   t_side_by_side = 0;
   // join on every exit path: whatever was enqueued on the lanes must be ordered before the caller's later work on `stream`

@@ -74,6 +74,7 @@ def init_points(pcs, npoint=1024, sigma=0.01, padding_scale=0.9, gen=None):
 class Defender:
     """ConvONet-Opt end to end on one GPU.  `model` is a models.ConvolutionalOccupancyNetwork (or any object
     with encode_inputs() returning the 3-plane dict and a `decoder` holding the reference's decoder.* keys)."""
+    loops_in_flight = 4        # sharded driver: segments whose loops may run at the same time (each call owns its workspace)
 
     def __init__(self, model, args=None, device="cuda"):
         self.args = args or Args()
@@ -235,6 +236,11 @@ class Defender:
             return [self.restore_slice(pc, lo, hi, n, seed) for lo, hi, n in segments]
         side = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
+        # up to `depth` segments have their loops in flight, each on its own stream: a loop is a chain of dependent launches
+        # that does not fill the GPU (least of all the small slices of a many-rank job), loops of different segments do
+        depth = 4 if max(hi - lo for lo, hi, _ in segments) <= 64 else 2
+        depth = min(depth, int(os.environ.get("IFD_LOOPS_IN_FLIGHT", self.loops_in_flight)))
+        loops = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
 
         def stage(seg):
             lo, hi, _ = seg
@@ -246,15 +252,30 @@ class Defender:
                 done.record(side)
             return pts, c, done
 
-        out = []
-        nxt = stage(segments[0])
-        for j, (lo, hi, n) in enumerate(segments):
-            pts, c, done = nxt
-            main.wait_event(done)
-            x = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight, iterations=a.iterations, B_ref=n,
-                                              return_tensor=True)
-            nxt = stage(segments[j + 1]) if j + 1 < len(segments) else None
+        out, flying = [], []
+
+        def land():
+            x, keep, ev = flying.pop(0)
+            ev.synchronize()                               # (the stage's tensors in `keep` are released only now)
             out.append(x.cpu().numpy())
+
+        for j, (lo, hi, n) in enumerate(segments):
+            pts, c, done = stage((lo, hi, n))              # enqueued while up to `depth` earlier loops run
+            if len(flying) >= depth:
+                land()
+            S = loops[j % depth]
+            S.wait_event(done)
+            with torch.cuda.stream(S):
+                x = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight, iterations=a.iterations, B_ref=n,
+                                                  return_tensor=True)
+                ev = torch.cuda.Event()
+                ev.record(S)
+            flying.append((x, (pts, c), ev))
+        while flying:
+            land()
+        main.wait_stream(side)
+        for S in loops:
+            main.wait_stream(S)
         return out
 
     def restore_slice(self, pc, lo, hi, B_ref, seed):
@@ -289,6 +310,8 @@ class Defender:
 class ONetDefender(Defender):
     """ONet-Opt end to end (ONet/opt_defense.py, the twin of the ConvONet script: same functions and line numbers, 300 encoder
     points, latent code c [B,512] instead of feature planes, DecoderCBatchNorm).  `model` is a models.OccupancyNetwork."""
+    loops_in_flight = 1        # the ONet restorer keeps ONE cached workspace per shape (1 GB at B = 64): one loop at a time; its
+                               # layer GEMMs are persistent kernels that fill the GPU anyway
 
     def __init__(self, model, args=None, device="cuda"):
         from . import onet
