@@ -154,30 +154,12 @@ class Defender:
         """opt_defense.py:255-314.  pc: [N,K,3] array.  Returns float32 [N,sample_npoint,3]."""
         a = self.args
         if a.device_preprocess and isinstance(pc, np.ndarray) and pc.ndim == 3:
-            # Two-stage pipeline: SOR + preprocess + encoder of batch j+1 are enqueued on a side stream while the loop of
-            # batch j runs on the current one.  The random draws happen in batch order, as in the serial code.
-            out = np.zeros((len(pc), a.sample_npoint, 3), dtype=np.float32)
-            side = torch.cuda.Stream(device=self.device)
-            main = torch.cuda.current_stream(self.device)
-
-            def stage(lo):
-                with torch.cuda.stream(side), torch.no_grad():
-                    sel, pts = self.prepare_batch_device(pc[lo:lo + a.batch_size], rng, gen)
-                    planes = self._encode(sel)
-                    done = torch.cuda.Event()
-                    done.record(side)
-                return pts, planes, done
-
-            starts = list(range(0, len(pc), a.batch_size))
-            nxt = stage(starts[0]) if starts else None
-            for j, lo in enumerate(starts):
-                pts, planes, done = nxt
-                main.wait_event(done)
-                x = self.restorer.optimize_points(pts, None, planes, rep_weight=a.rep_weight, iterations=a.iterations,
-                                                  printing=printing, return_tensor=True)
-                nxt = stage(starts[j + 1]) if j + 1 < len(starts) else None
-                out[lo:lo + a.batch_size] = x.cpu().numpy()
-            return out
+            # pipelined (see _pipelined); the random draws happen in batch order, as in the serial code
+            segs = [(lo, min(lo + a.batch_size, len(pc)), min(lo + a.batch_size, len(pc)) - lo) for lo in range(0, len(pc), a.batch_size)]
+            if not segs:
+                return np.zeros((0, a.sample_npoint, 3), dtype=np.float32)
+            parts = self._pipelined(pc, segs, lambda lo, hi: (rng, gen), lambda sel, lo: self.model.encode_inputs(sel), printing)
+            return np.concatenate(parts, axis=0).astype(np.float32)
         pcs = self.sor_process(pc) if a.sor else [np.asarray(p, dtype=np.float32) for p in pc]
         out = np.zeros((len(pcs), a.sample_npoint, 3), dtype=np.float32)
         for lo in range(0, len(pcs), a.batch_size):
@@ -234,20 +216,30 @@ class Defender:
         a = self.args
         if not (a.device_preprocess and isinstance(pc, np.ndarray) and pc.ndim == 3) or not segments:
             return [self.restore_slice(pc, lo, hi, n, seed) for lo, hi, n in segments]
+        def draws(lo, hi):
+            return self._slice_streams(lo, hi, seed)
+
+        return self._pipelined(pc, segments, draws, lambda sel, lo: self.encode_chunked(sel, lo))
+
+    def _pipelined(self, pc, segments, draws, encode, printing=False):
+        """The batch loop as a pipeline on the device pre-processing path: SOR + preprocess + encoder of a segment are enqueued
+        on a side stream while the loops of up to `depth` earlier segments run, each loop on its own stream (a loop is a chain
+        of dependent launches that does not fill the GPU -- least of all the small slices of a many-rank job -- loops of
+        different segments do); one D2H per segment.  draws(lo, hi) -> (rng, gen) for prepare_batch_device; stages run in
+        segment order, so shared generators see the draws in the serial code's order."""
+        a = self.args
         side = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
-        # up to `depth` segments have their loops in flight, each on its own stream: a loop is a chain of dependent launches
-        # that does not fill the GPU (least of all the small slices of a many-rank job), loops of different segments do
         depth = 4 if max(hi - lo for lo, hi, _ in segments) <= 64 else 2
-        depth = min(depth, int(os.environ.get("IFD_LOOPS_IN_FLIGHT", self.loops_in_flight)))
+        depth = 1 if printing else min(depth, int(os.environ.get("IFD_LOOPS_IN_FLIGHT", self.loops_in_flight)))
         loops = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
 
         def stage(seg):
             lo, hi, _ = seg
-            rngs, gens = self._slice_streams(lo, hi, seed)
+            rng, gen = draws(lo, hi)
             with torch.cuda.stream(side), torch.no_grad():
-                sel, pts = self.prepare_batch_device(np.asarray(pc[lo:hi])[..., :3], rngs, gens)
-                c = self.encode_chunked(sel, lo)
+                sel, pts = self.prepare_batch_device(np.asarray(pc[lo:hi])[..., :3], rng, gen)
+                c = encode(sel, lo)
                 done = torch.cuda.Event()
                 done.record(side)
             return pts, c, done
@@ -267,7 +259,7 @@ class Defender:
             S.wait_event(done)
             with torch.cuda.stream(S):
                 x = self.restorer.optimize_points(pts, None, c, rep_weight=a.rep_weight, iterations=a.iterations, B_ref=n,
-                                                  return_tensor=True)
+                                                  printing=printing, return_tensor=True)
                 ev = torch.cuda.Event()
                 ev.record(S)
             flying.append((x, (pts, c), ev))
