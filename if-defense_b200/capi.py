@@ -76,6 +76,7 @@ SIGNATURES = {
                               ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong), _vp]),
     "ifd_mc_emit": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_d, _c_d, _c_int, _c_d, _vp, _c_sz, _vp, _vp, _vp]),
     "ifd_sample_surface_workspace_bytes": (_c_sz, [ctypes.c_longlong]),
+    "ifd_cumsum_f64": (_c_int, [_vp, ctypes.c_longlong, _vp, _vp]),
     "ifd_sample_surface": (_c_int, [_vp, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp, _c_int, _vp, _vp, _vp, _c_sz, _vp]),
     "ifd_mise_workspace_bytes": (_c_sz, [_c_int, _c_int]),
     "ifd_mise_init": (_c_int, [_c_int, _c_int, _vp, _c_sz, _vp]),

@@ -388,6 +388,10 @@ int ifd_mc_emit(const void* volume, int dtype, int nx, int ny, int nz, int pad, 
  * sum exceeds 1.  verts [V][3] float64, faces [F][3] int64 (device); xyz_out [count][3] float64; face_out [count] or
  * null.  A mesh without faces is IFD_ERR_INVALID (the reference's IndexError, remesh_defense.py:160). */
 size_t ifd_sample_surface_workspace_bytes(long long n_faces);
+/* numpy.cumsum over a device array of non-negative float64 values, in place and bit for bit (the cumulative-area prefix that
+ * trimesh.sample.sample_surface searches: one left-to-right chain of rounded additions, reproduced by an integer prefix sum
+ * per binade of the running sum).  total_out (device, optional): the last element. */
+int ifd_cumsum_f64(double* data, long long n, double* total_out, ifd_stream_t stream);
 int ifd_sample_surface(const double* verts, long long n_verts, const long long* faces, long long n_faces,
                        const double* uniforms, int count, double* xyz_out, long long* face_out, void* workspace,
                        size_t workspace_bytes, ifd_stream_t stream);

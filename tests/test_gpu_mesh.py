@@ -210,3 +210,32 @@ def test_generator3d_mise_path_equals_mise_of_the_dense_lattice():
     v, f = gen.generate_from_latent(None, c)
     wv, wf = co.extract_mesh(want, 0.2, 0.1)
     assert np.array_equal(v.cpu().numpy(), wv) and np.array_equal(f.cpu().numpy(), wf)
+
+
+def test_cumsum_is_numpy_cumsum_bit_for_bit():
+    """ifd_cumsum_f64 (the area prefix of ifd_sample_surface) == np.cumsum on float64, every bit: random magnitudes over many
+    binades, zeros, subnormals, a tie (an addend of exactly half an ulp of the running sum), addends larger than the sum,
+    the real use (triangle areas of a marching-cubes mesh), ragged lengths around the block size."""
+    L = capi.lib()
+    rng = np.random.default_rng(0)
+    cases = []
+    for n in (1, 2, 31, 1023, 1024, 1025, 5000, 116416):
+        cases.append(rng.random(n) * 10.0 ** rng.integers(-12, 3, size=n))
+    x = rng.random(4000)
+    x[::7] = 0.0
+    x[5] = 5e-324
+    x[11] = 2.0 ** -1040
+    cases.append(x)
+    t = np.array([1.0, 2.0 ** -53, 2.0 ** -53, 1.0, 2.0 ** -52, 3 * 2.0 ** -53, 1e30, 1.0, 2.0 ** 60], dtype=np.float64)      # ties, jumps
+    cases.append(t)
+    cases.append(np.concatenate([np.full(3000, 2.0 ** -30), [1.0], np.full(3000, 2.0 ** -54 * 1.5), np.full(10, 2.0 ** -53)]))
+    cases.append(np.sort(rng.random(20000) * 1e-9)[::-1].copy() + 1e-3)
+    for a in cases:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        want = np.cumsum(a)
+        d = torch.from_numpy(a).cuda()
+        tot = torch.zeros(1, dtype=torch.float64, device="cuda")
+        capi.check(L.ifd_cumsum_f64(capi.ptr(d), a.shape[0], capi.ptr(tot), capi.stream()), "ifd_cumsum_f64")
+        got = d.cpu().numpy()
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), (a.shape, np.flatnonzero(got != want)[:5])
+        assert float(tot.item()) == want[-1]
