@@ -24,11 +24,11 @@
 
 namespace ifd {
 
-constexpr int kV4Threads = 256;                    // (names kept from the retired v4 kernel, whose CTA shape this is)
-constexpr int kV4Pts = 256;
-constexpr int kV4Stride = kV4Pts + 1;
-constexpr int kV4StageFloats = 3 * kV3ImgFloats;   // one stage buffer: up to 3 images x (hi + lo) = 24 KB
-constexpr uint32_t kV4TmemCols = 256;
+constexpr int kV5Threads = 256;                    // two tiles of 128 points
+constexpr int kV5Pts = 256;
+constexpr int kV5Stride = kV5Pts + 1;
+constexpr int kV5StageFloats = 3 * kV3ImgFloats;   // one stage buffer: up to 3 images x (hi + lo) = 24 KB
+constexpr uint32_t kV5TmemCols = 256;
 constexpr int kV5TileCols = 128;                   // D | A_hi | A_lo | c_hi (forward) / D_gc (backward)
 constexpr int kV5ColA = 32, kV5ColX = 96;
 
@@ -159,12 +159,12 @@ __device__ __forceinline__ void v5_round_end(uint32_t (&d)[32], uint32_t taddr, 
 
 struct DecodeV5Smem {
   static __host__ __device__ size_t bytes(int n_blocks) {      // stage buffers | feat / c_lo | gpart | barriers | bias / fc_p / fc_out table
-    return (size_t)2 * kV4StageFloats * 4 + (size_t)32 * kV4Stride * 4 + (size_t)kV4Pts * 16 + 256 +
+    return (size_t)2 * kV5StageFloats * 4 + (size_t)32 * kV5Stride * 4 + (size_t)kV5Pts * 16 + 256 +
            (size_t)(3 * n_blocks + 6) * 32 * 4;
   }
 };
 
-__global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const DecodeV3Args a) {
+__global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const DecodeV3Args a) {
   extern __shared__ float4 smem4[];
   const float* __restrict__ g_planes = a.job ? a.job->planes : a.planes;
   const float* __restrict__ g_W = a.job ? a.job->W : a.W;
@@ -176,23 +176,23 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   const int nb = a.n_blocks;
   const int n_layers = 3 * nb;
   float* wimg = reinterpret_cast<float*>(smem4);                           // [2 stage buffers][3 images][2048]
-  float* feat = wimg + (size_t)2 * kV4StageFloats;                          // [32][kV4Stride]; forward MLP: c_lo images [2 tiles][128 x 32]
-  float4* gpart = reinterpret_cast<float4*>(feat + 32 * kV4Stride);         // [kV4Pts]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gpart + kV4Pts);             // [2] tiles, [2] weight stages
+  float* feat = wimg + (size_t)2 * kV5StageFloats;                          // [32][kV5Stride]; forward MLP: c_lo images [2 tiles][128 x 32]
+  float4* gpart = reinterpret_cast<float4*>(feat + 32 * kV5Stride);         // [kV5Pts]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gpart + kV5Pts);             // [2] tiles, [2] weight stages
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
   float* vec = reinterpret_cast<float*>(reinterpret_cast<char*>(bars) + 256);   // [n_layers][32] biases | fc_p 4x32 | fc_out 2x32
   const float* Wb = g_W;
 
-  const int tile0 = blockIdx.x * kV4Pts;
+  const int tile0 = blockIdx.x * kV5Pts;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int group = warp >> 2;                                              // tile of this thread
   const int grp = lane >> 3, j4 = lane & 7;
   const float4* __restrict__ planes4 = reinterpret_cast<const float4*>(g_planes);
   const uint32_t plane4 = (uint32_t)(a.R * a.R * 8);              // one plane of one cloud, in float4 units
 
-  if (warp == 0) umma::tmem_alloc(tmem_slot, kV4TmemCols);
+  if (warp == 0) umma::tmem_alloc(tmem_slot, kV5TmemCols);
   if (threadIdx.x == 32) {
-    for (int g = 0; g < kV4Threads / 128; ++g) umma::mbar_init(&bars[g], 1);
+    for (int g = 0; g < kV5Threads / 128; ++g) umma::mbar_init(&bars[g], 1);
     umma::fence_mbar_init();
   }
   uint64_t* wbar = bars + 2;                                                 // [2]: bytes of stage buffer t & 1 have landed
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   auto prefetch_stage = [&](int t) {                                         // thread 0 only: ONE TMA bulk copy per stage
     const uint32_t bytes = (uint32_t)v5_stage_images(t, nb) * (kV3ImgFloats * 4);
     umma::mbar_arrive_expect_tx(&wbar[t & 1], bytes);
-    umma::bulk_g2s(wimg + (size_t)(t & 1) * kV4StageFloats, g_Wimg + (size_t)v5_stage_first(t, nb) * kV3ImgFloats, bytes, &wbar[t & 1]);
+    umma::bulk_g2s(wimg + (size_t)(t & 1) * kV5StageFloats, g_Wimg + (size_t)v5_stage_first(t, nb) * kV3ImgFloats, bytes, &wbar[t & 1]);
   };
   // every thread: everybody is done with stage t - 1 (whose buffer stage t + 1 takes), the bytes of stage t have landed
   auto begin_stage = [&](int t) {
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     umma::fence_mbar_init();
     prefetch_stage(0);
   }
-  for (int i = threadIdx.x; i < (n_layers + 6) * 32; i += kV4Threads) {
+  for (int i = threadIdx.x; i < (n_layers + 6) * 32; i += kV5Threads) {
     const int row = i >> 5, c = i & 31;
     float v;
     if (row < n_layers) v = Wb[L::kBlk0 + row * L::kLayer + 1024 + c];
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   const int pi = min(tile0 + slot, a.n - 1);
   const float p0 = g_xyz[(size_t)pi * 3 + 0], p1 = g_xyz[(size_t)pi * 3 + 1], p2 = g_xyz[(size_t)pi * 3 + 2];
   const V3Geom geo = v3_geom(p0, p1, p2, a.R, a.denom, pi / a.K);
-  // ---------------- forward gather (v4's): warp w serves tile slots 32w .. 32w+31, four points per pass
+  // ---------------- forward gather  warp w serves tile slots 32w .. 32w+31, four points per pass
 #pragma unroll 2
   for (int it = 0; it < 8; ++it) {
     const int src = it * 4 + grp, gslot = warp * 32 + src;
@@ -288,10 +288,10 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
         __stcg(dst + ax * 8, on ? jx[ax] : make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
-    feat[(j4 * 4 + 0) * kV4Stride + gslot] = c.x;
-    feat[(j4 * 4 + 1) * kV4Stride + gslot] = c.y;
-    feat[(j4 * 4 + 2) * kV4Stride + gslot] = c.z;
-    feat[(j4 * 4 + 3) * kV4Stride + gslot] = c.w;
+    feat[(j4 * 4 + 0) * kV5Stride + gslot] = c.x;
+    feat[(j4 * 4 + 1) * kV5Stride + gslot] = c.y;
+    feat[(j4 * 4 + 2) * kV5Stride + gslot] = c.z;
+    feat[(j4 * 4 + 3) * kV5Stride + gslot] = c.w;
   }
   begin_stage(0);                      // (also publishes feat, vec, the TMEM slot and the mbarriers)
   // warp-uniform copies of everything the MMA issue reads (umma::elect_one: the operands must sit in uniform registers)
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   uint64_t* bar = &bars[group_u];
   uint32_t parity = 0;
   const bool lead_warp = (warp_u & 3) == 0;                                            // first warp of the tile issues its MMAs
-  auto stage_img = [&](int t, int i) { return wimg_saddr + (uint32_t)(t & 1) * (kV4StageFloats * 4) + (uint32_t)i * (kV3ImgFloats * 4); };
+  auto stage_img = [&](int t, int i) { return wimg_saddr + (uint32_t)(t & 1) * (kV5StageFloats * 4) + (uint32_t)i * (kV3ImgFloats * 4); };
 
   // ---------------- MLP forward: thread = point
   float net[32], x[32];
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   const float* fcp = vec + n_layers * 32;
   // c: hi -> TMEM (kept for the whole forward pass), lo -> K-major image over the gather's staging buffer
 #pragma unroll
-  for (int k = 0; k < 32; ++k) x[k] = feat[k * kV4Stride + slot];
+  for (int k = 0; k < 32; ++k) x[k] = feat[k * kV5Stride + slot];
   __syncthreads();                     // every thread holds its c row: the staging buffer may be overwritten
 #pragma unroll
   for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi_fast(x[k]);
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   const float sg = sigmoidf_(logit);
   const float glogit = (sg - a.target) * a.ginv;
   if (a.stat_part) {
-    __shared__ double red[2][kV4Threads / 32];
+    __shared__ double red[2][kV5Threads / 32];
     const bool live = tile0 + slot < a.n;
     double s0 = live ? (double)bce_with_logits(logit, a.target) : 0.0;
     double s1 = live ? (double)sg : 0.0;
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     __syncthreads();
     if (threadIdx.x == 0) {
       double t0 = 0.0, t1 = 0.0;
-      for (int w = 0; w < kV4Threads / 32; ++w) {
+      for (int w = 0; w < kV5Threads / 32; ++w) {
         t0 += red[0][w];
         t1 += red[1][w];
       }
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
       const bool first = blk + 2 == nb;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        float* f = feat + k * kV4Stride + slot;
+        float* f = feat + k * kV5Stride + slot;
         *f = first ? __uint_as_float(d[k]) : *f + __uint_as_float(d[k]);
       }
     }
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     v5_round_end(d, lane_taddr + kV5ColX, bar, parity);
 #pragma unroll
     for (int k = 0; k < 32; ++k) {
-      float* f = feat + k * kV4Stride + slot;
+      float* f = feat + k * kV5Stride + slot;
       *f = nb == 1 ? __uint_as_float(d[k]) : *f + __uint_as_float(d[k]);
     }
   }
@@ -535,8 +535,8 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
       const int src = it * 4 + grp, gslot = warp * 32 + src;
       const int pi_raw = tile0 + gslot;
       const bool in = pi_raw < a.n;
-      const float4 gc = make_float4(feat[(j4 * 4 + 0) * kV4Stride + gslot], feat[(j4 * 4 + 1) * kV4Stride + gslot],
-                                    feat[(j4 * 4 + 2) * kV4Stride + gslot], feat[(j4 * 4 + 3) * kV4Stride + gslot]);
+      const float4 gc = make_float4(feat[(j4 * 4 + 0) * kV5Stride + gslot], feat[(j4 * 4 + 1) * kV5Stride + gslot],
+                                    feat[(j4 * 4 + 2) * kV5Stride + gslot], feat[(j4 * 4 + 3) * kV5Stride + gslot]);
       const float4* srcj = g_jac4 + ((size_t)(in ? pi_raw : 0) * 3) * 8 + j4;
       float gi[3];
 #pragma unroll
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
       }
     }
   } else {
-  // ---------------- backward gather (v4's; warp-local: slots 32w .. 32w+31)
+  // ---------------- backward gather (warp-local: slots 32w .. 32w+31)
   const V3Geom geo2 = v3_geom(p0, p1, p2, a.R, a.denom, pi / a.K);
 #pragma unroll 2
   for (int it = 0; it < 8; ++it) {
@@ -575,8 +575,8 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
     const int b = __shfl_sync(0xffffffffu, geo2.b, src);
     V3Taps ts;
     v3_taps(pk, fr, a.R, (uint32_t)b * plane4 + (uint32_t)j4, (uint32_t)a.B * plane4, ts);
-    const float4 gc = make_float4(feat[(j4 * 4 + 0) * kV4Stride + gslot], feat[(j4 * 4 + 1) * kV4Stride + gslot],
-                                  feat[(j4 * 4 + 2) * kV4Stride + gslot], feat[(j4 * 4 + 3) * kV4Stride + gslot]);
+    const float4 gc = make_float4(feat[(j4 * 4 + 0) * kV5Stride + gslot], feat[(j4 * 4 + 1) * kV5Stride + gslot],
+                                  feat[(j4 * 4 + 2) * kV5Stride + gslot], feat[(j4 * 4 + 3) * kV5Stride + gslot]);
     float gi[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(kV4Threads, 2) convonet_decode_v5_kernel(const
   }
   umma::fence_before_sync();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem_base, kV4TmemCols);
+  if (warp == 0) umma::tmem_dealloc(tmem_base, kV5TmemCols);
 }
 
 }  // namespace ifd

@@ -1,13 +1,14 @@
-// restore.cu -- the restoration loop of optimize_points (ConvONet/opt_defense.py:182-239) as sm_100a kernels.
+// restore.cu -- the restoration loop of optimize_points (ConvONet/opt_defense.py:182-239) as sm_100a kernels, and its drivers.
 //
-// Per Adam step (v1 schedule, three launches on one stream, no host sync anywhere):
-//   convonet_decode_kernel<BCE>   per point: 3-plane bilinear gather (channels-last planes, 128 B per tap),
-//                                 5-block ResNet-MLP forward, BCE gradient, MLP dgrad, gather dgrad -> g_occ
-//   knn_repulsion_kernel          per cloud chunk: brute-force kNN-5 from shared memory (reference association,
-//                                 bit-exact indices), repulsion pair terms, scatter-add into neighbours as
-//                                 integer atomics on an exact long accumulator (bitwise reproducible)
-//   adam_kernel                   g = g_occ + coef * acc ; torch-2.11 Adam update of xyz, m, v ; re-zero acc
-// then normalize_kernel (centre + unit sphere, opt_defense.py:76-83).
+// Per Adam step, two launches on one stream, no host sync anywhere; the whole loop (pack, n_steps x {decode, tail}, normalise) is
+// replayed as ONE cached CUDA graph whose kernels read their buffers from a LoopJob record:
+//   convonet_decode_v5_kernel     decode_v5.cuh: 3-plane bilinear gather (channels-last planes, 128 B per tap), 5-block
+//                                 ResNet-MLP forward on tcgen05 (3xTF32), BCE gradient, MLP dgrad, gather dgrad -> g_occ
+//   cloud_step[_solo]_kernel      cloud_step.cuh: exact kNN-5 on a per-step grid, repulsion pair terms, their scatter-add
+//                                 backward as a gather, g = g_occ + coef * g_rep, torch-2.11 Adam update of xyz, m, v
+// then normalize_kernel (centre + unit sphere, opt_defense.py:76-83).  Up to four loops run side by side (ifd_convonet_opt_batches).
+// Kept next to them: the thread-per-point decode (forward / given-gradient seams, the grid variant), decode v2 (fp32 SIMT
+// cross-check), the first-generation tail (knn_repulsion_kernel + adam_kernel: K > 1024 or knn_k > 7, and the seam ifd_knn_repulsion).
 #include <string.h>
 
 #include <vector>
@@ -39,7 +40,7 @@ struct DecodeArgs {
   double* stat_part;         // optional [gridDim.x][2]: sum bce, sum sigmoid
   int B, K, R, n_blocks, wtotal4;
   float denom, target, ginv;
-  const LoopJob* job;        // decode v4 only (graph replay)
+  const LoopJob* job;        // decode v5 only (graph replay)
   int grid3d;                // 1: `planes` is ONE feature volume [B][R][R][R][C] (the 'grid' variant, grid_point.cuh)
 };
 
@@ -507,7 +508,7 @@ static int launch_decode_v5(const DecodeArgs& a, const float* wimg, float* jac, 
   const size_t smem = DecodeV5Smem::bytes(a.n_blocks);
   if ((unsigned long long)3 * a.B * a.R * a.R * 8 >= (1ull << 32)) return fail(IFD_ERR_UNSUPPORTED, "decode v5: plane array too large for 32-bit texel indices");
   IFD_CUDA_TRY(set_max_dyn_smem((const void*)convonet_decode_v5_kernel, smem));
-  convonet_decode_v5_kernel<<<(v.n + kV4Pts - 1) / kV4Pts, kV4Threads, smem, st>>>(v);
+  convonet_decode_v5_kernel<<<(v.n + kV5Pts - 1) / kV5Pts, kV5Threads, smem, st>>>(v);
   IFD_LAUNCH_CHECK("convonet_decode_v5_kernel");
   return IFD_OK;
 }
@@ -700,7 +701,7 @@ int enqueue_loop(const float* planes_cl, const float* dec_weights, float* xyz, f
   a.ginv = (float)K / (float)((long long)P->B_ref * K);
   const int dk = grid3d ? 1 : (P->decode_kernel == 0 ? kDefaultDecode : P->decode_kernel);      // the grid variant has the thread-per-point kernel only
   const int n_dec = dk == 1 ? (B * K + kDecThreads - 1) / kDecThreads          // CTAs of the decode kernel (stat partials)
-                    : dk >= 4 ? (B * K + kV4Pts - 1) / kV4Pts : (B * K + kV2Pts - 1) / kV2Pts;
+                    : dk >= 4 ? (B * K + kV5Pts - 1) / kV5Pts : (B * K + kV2Pts - 1) / kV2Pts;
   if (dk >= 4) {
     const int nl = 3 * n_blocks;
     convonet_pack_umma_v5_kernel<<<(nl * 1024 + 255) / 256, 256, 0, st>>>(dec_weights, n_blocks, w.wimg, job);

@@ -24,5 +24,6 @@ else:
     case = synth.make_case(B, K=1024, seed=0)
     dec = convonet.ConvONetDecoder(case.sd)
     pl = convonet.planes_to_channels_last({k: v.cuda() for k, v in case.c.items()})
+    capi.lib().ifd_test_hook(5, int(os.environ.get("RC_TAIL_CTAS", "0")))      # 1: the one-CTA form of cloud_step, 2: the cluster pair
     x, _ = run_opt(dec, pl, case.p0, 2)
     print("step ok", float(np.abs(x).max()))
