@@ -202,19 +202,29 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
     umma::mbar_arrive_expect_tx(&wbar[t & 1], bytes);
     umma::bulk_g2s(wimg + (size_t)(t & 1) * kV5StageFloats, g_Wimg + (size_t)v5_stage_first(t, nb) * kV3ImgFloats, bytes, &wbar[t & 1]);
   };
-  // every thread: everybody is done with stage t - 1 (whose buffer stage t + 1 takes), the bytes of stage t have landed
-  auto begin_stage = [&](int t) {
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    umma::mbar_wait(&wbar[t & 1], (uint32_t)((t >> 1) & 1));
-    if (threadIdx.x == 0 && t + 1 < n_stages) prefetch_stage(t + 1);
+  // Weight stages without CTA-wide barriers: the two tiles of a CTA run their chains independently (one in its ALU epilogue
+  // while the other waits for the tensor core).  Only the lane that issues a tile's MMAs touches the weights: it waits for the
+  // bytes of stage t before its first MMA (wait_weights), and after the tile's last round of stage t it releases buffer t & 1
+  // (release_stage) -- the SECOND tile to release it starts the copy of stage t + 2 into it.  A tile can therefore be at most
+  // one stage ahead of the other, which is also what keeps the shared staging buffer (feat / c_lo) safe.
+  uint32_t* rel = tmem_slot + 1;                                             // [2] tiles that released stage buffer t & 1
+  auto wait_weights = [&](int t) { umma::mbar_wait(&wbar[t & 1], (uint32_t)((t >> 1) & 1)); };
+  auto release_stage = [&](int t) {                                          // issuing lane of a tile, after the tile's last round of stage t
+    if (t + 2 >= n_stages) return;
+    __threadfence_block();
+    if (atomicAdd(&rel[t & 1], 1u) == (uint32_t)(kV5Threads / 128 - 1)) {
+      atomicExch(&rel[t & 1], 0u);
+      __threadfence_block();
+      prefetch_stage(t + 2);
+    }
   };
   if (threadIdx.x == 0) {
     umma::mbar_init(&wbar[0], 1);
     umma::mbar_init(&wbar[1], 1);
     umma::fence_mbar_init();
+    rel[0] = rel[1] = 0u;
     prefetch_stage(0);
+    prefetch_stage(1);
   }
   for (int i = threadIdx.x; i < (n_layers + 6) * 32; i += kV5Threads) {
     const int row = i >> 5, c = i & 31;
@@ -293,7 +303,9 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
     feat[(j4 * 4 + 2) * kV5Stride + gslot] = c.z;
     feat[(j4 * 4 + 3) * kV5Stride + gslot] = c.w;
   }
-  begin_stage(0);                      // (also publishes feat, vec, the TMEM slot and the mbarriers)
+  umma::fence_before_sync();
+  __syncthreads();                     // publishes feat, vec, the TMEM slot, the mbarriers and the release counters
+  umma::fence_after_sync();
   // warp-uniform copies of everything the MMA issue reads (umma::elect_one: the operands must sit in uniform registers)
   const int warp_u = (int)umma::warp_bcast((uint32_t)warp), group_u = warp_u >> 2;
   const uint32_t tmem_base = umma::warp_bcast(*tmem_slot);
@@ -334,12 +346,14 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
   umma::tmem_wait_st();
   v5_round_begin(group);
   if (lead_warp && umma::elect_one()) {
+    wait_weights(0);
     umma::fence_after_sync();
     v5_c_small(tile_taddr, clo_saddr, stage_img(0, 0), 0u);
     v5_c_big(tile_taddr, stage_img(0, 0));
     umma::commit(bar);
   }
   v5_round_end(d, lane_taddr, bar, parity);
+  if (lead_warp && umma::elect_one()) release_stage(0);
   // The residual stream and the hidden pre-activations are carried NEGATED (nnet = -net, exact: rounding is symmetric), because
   // then "pre-activation > 0" is the sign bit of the stored value and a 32-bit ReLU mask costs one funnel shift per element
   // instead of compare + select + or (ncu: 470 instructions per thread and round trip, 80 of them for the masks).  Zeros: every
@@ -359,7 +373,6 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
 #pragma unroll 1
   for (int blk = 0; blk < nb; ++blk) {
     const int st = 1 + blk;
-    begin_stage(st);
     const float* b0 = vec + (3 * blk + 1) * 32;
     const float* b1 = vec + (3 * blk + 2) * 32;
     V5Signs sg4;
@@ -373,6 +386,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
     v5_put_a(x, d, lane_taddr);
     v5_round_begin(group);
     if (lead_warp && umma::elect_one()) {
+      wait_weights(st);
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 0), 0u, 0u);
       v5_chain_big(tile_taddr, stage_img(st, 0), 0u);
@@ -401,6 +415,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
       umma::commit(bar);
     }
     v5_round_end(d, lane_taddr, bar, parity);
+    if (lead_warp && umma::elect_one()) release_stage(st);
     if (more) {
       const float* bc = vec + (3 * blk + 3) * 32;
 #pragma unroll
@@ -457,11 +472,11 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
 #pragma unroll 1
   for (int blk = nb - 1; blk >= 0; --blk) {
     const int st = nb + 1 + (nb - 1 - blk);
-    begin_stage(st);
     const bool with_c = blk + 1 < nb;
     v5_put_a(gnet, d, lane_taddr);
     v5_round_begin(group);
     if (lead_warp && umma::elect_one()) {
+      wait_weights(st);
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 0), 0u, 0u);                                      // . W1[blk]
       v5_chain_big(tile_taddr, stage_img(st, 0), 0u);
@@ -493,15 +508,16 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
       }
     }
     v5_round_end(d, lane_taddr, bar, parity);
+    if (lead_warp && umma::elect_one()) release_stage(st);
 #pragma unroll
     for (int k = 0; k < 32; ++k) gnet[k] += ((ma >> (31 - k)) & 1u) ? __uint_as_float(d[k]) : 0.0f;
   }
   {
     const int st = 2 * nb + 1;
-    begin_stage(st);
     v5_put_a(gnet, d, lane_taddr);
     v5_round_begin(group);
     if (lead_warp && umma::elect_one()) {
+      wait_weights(st);
       umma::fence_after_sync();
       v5_chain_small(tile_taddr, stage_img(st, 0), kV5ColX, 0u);                                 // . Wc[0]
       v5_chain_big(tile_taddr, stage_img(st, 0), kV5ColX);
