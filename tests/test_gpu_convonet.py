@@ -116,7 +116,7 @@ def bce_grad(dec, planes, xyz, kernel, B_ref=None):
     L = capi.lib()
     ws = torch.empty(L.ifd_convonet_opt_workspace_bytes(B, K), dtype=torch.uint8, device="cuda")
     g = torch.empty_like(x)
-    capi.check(L.ifd_convonet_decode_bce_grad(capi.ptr(planes), capi.ptr(dec.blob), capi.ptr(x), B, K, planes.shape[2], 32, 32, 5,
+    capi.check(L.ifd_convonet_decode_bce_grad(capi.ptr(planes), capi.ptr(dec.blob), capi.ptr(x), B, K, planes.shape[2], 32, 32, dec.dims[2],
                                               0.1, 0.2, B if B_ref is None else B_ref, kernel, capi.ptr(g), capi.ptr(ws),
                                               ws.numel(), capi.stream()))
     torch.cuda.synchronize()
@@ -140,6 +140,34 @@ def test_bce_grad_seam_all_kernels(conv, conv_sd, conv_planes, dec, planes):
     print("bce-grad max error / max|grad| per kernel:", errs)
     assert errs[1] < 2e-6 and errs[2] < 2e-6
     assert errs[5] < 1e-5                         # 3xTF32 tensor-core path: fp32-class (vs a float64 evaluation: 2.8e-6, the fp32 kernels 3.0e-6)
+
+
+@pytest.mark.parametrize("nb", [1, 2, 3, 8])
+def test_decoder_depths_other_than_five(conv, conv_planes, planes, nb):
+    """LocalDecoder with n_blocks != 5 (the stage table of decode v5 -- which layers ride with which round -- depends on it):
+    BCE gradient of the tensor-core kernel and of the fp32 kernel against torch autograd on the oracle, and a short loop."""
+    import torch.nn.functional as F
+    from oracle import torch_port as tp
+    g = torch.Generator().manual_seed(100 + nb)
+    rnd = lambda *shape: torch.randn(shape, generator=g) / (shape[-1] ** 0.5)
+    sd = {"decoder.fc_p.weight": rnd(32, 3), "decoder.fc_p.bias": rnd(32) * 0.3, "decoder.fc_out.weight": rnd(1, 32),
+          "decoder.fc_out.bias": rnd(1) * 0.1}
+    for i in range(nb):
+        sd["decoder.fc_c.%d.weight" % i], sd["decoder.fc_c.%d.bias" % i] = rnd(32, 32), rnd(32) * 0.3
+        for fc in ("fc_0", "fc_1"):
+            sd["decoder.blocks.%d.%s.weight" % (i, fc)], sd["decoder.blocks.%d.%s.bias" % (i, fc)] = rnd(32, 32), rnd(32) * 0.3
+    d = convonet.ConvONetDecoder(sd, padding=0.1)
+    assert d.dims == (32, 32, nb)
+    p = torch.from_numpy(conv["p0"]).requires_grad_()
+    lg = tp.convonet_decode(sd, p, conv_planes, n_blocks=nb)
+    (F.binary_cross_entropy_with_logits(lg, torch.full_like(lg, 0.2), reduction="none").mean() * p.shape[1]).backward()
+    want = p.grad.numpy()
+    scale = np.abs(want).max()
+    assert np.abs(bce_grad(d, planes, conv["p0"], 2) - want).max() / scale < 2e-6
+    assert np.abs(bce_grad(d, planes, conv["p0"], 5) - want).max() / scale < 1e-5
+    a, _ = run_opt(d, planes, conv["p0"], 5, decode_kernel=5)
+    b, _ = run_opt(d, planes, conv["p0"], 5, decode_kernel=2)
+    assert np.isfinite(a).all() and (np.abs(a - b) < 1e-6).mean() > 0.98
 
 
 @pytest.mark.parametrize("tck", [5])
