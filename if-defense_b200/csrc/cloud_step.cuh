@@ -601,22 +601,18 @@ __device__ __forceinline__ void cloud_step_body(const CloudStepArgs& a) {
       const float g = S.gmv[0][3 * p + c] + r3[c] * a.rep_coef;
       float mm = S.gmv[1][3 * p + c], vv = S.gmv[2][3 * p + c];
       adam_update(p3[c], mm, vv, g, a.omb1, a.b2, a.omb2, a.adam_eps, a.sc);
-      if (CL == 1) {                       // one CTA owns the whole cloud: results go back through the staging arrays and
-        S.gmv[0][3 * p + c] = p3[c];       // leave coalesced below (a thread's point is an arbitrary index: written from
-        S.gmv[1][3 * p + c] = mm;          // here, every store instruction of a warp touches 32 separate sectors)
-        S.gmv[2][3 * p + c] = vv;
-      } else {
-        g_xyz[o3 + c] = p3[c];
-        g_m[o3 + c] = mm;
-        g_v[o3 + c] = vv;
-      }
+      // results go back through the staging arrays and leave coalesced below (a thread's point is an arbitrary index: written
+      // from here, every store instruction of a warp would touch 32 separate sectors)
+      S.gmv[0][3 * p + c] = p3[c];
+      S.gmv[1][3 * p + c] = mm;
+      S.gmv[2][3 * p + c] = vv;
       if (a.rep_grad_out) a.rep_grad_out[o3 + c] = r3[c];
     }
     ls[p] = lsum;                                               // pair-loss sum of point p
   }
-  if (CL == 1) {
-    __syncthreads();
-    for (int e = i; e < 3 * K; e += kCsThreads) {
+  __syncthreads();
+  for (int e = i; e < 3 * K; e += kCsThreads) {                 // each CTA writes the points it owns
+    if (CL == 1 || ((int)S.cid[e / 3] >= S.split_cell) == (half == 1)) {
       g_xyz[cloud3 + e] = S.gmv[0][e];
       g_m[cloud3 + e] = S.gmv[1][e];
       g_v[cloud3 + e] = S.gmv[2][e];
