@@ -624,7 +624,7 @@ def main():
     if rank == 0 and not args.no_onet:
         onet = onet_leg(L)
         if roofs is not None:
-            roofs.append(dict(onet["decoder_gemm"], kernel="tc::gemm_kernel<OnetLayerPolicy, 256> x 20 per Adam step (ONet-Opt leg)"))
+            roofs.append(dict(onet["decoder_gemm"], kernel="tc::gemm_chain_kernel<OnetLayerPolicy, 256>: the ten forward and the ten dgrad layers as one launch each (ONet-Opt leg)"))
     if rank == 0 and not args.no_cpu_baseline:
         import torch as _t
         cores = os.cpu_count() or 1

@@ -10,7 +10,8 @@
 // The ten 256x256 layers per direction are real GEMMs (M = B*K points, N = K = 256): one tcgen05 kernel,
 //   Y[M][256] = prologue(A)[M][256] . W^T  (+ bias, + residual)                       forward
 //   Y[M][256] = (G[M][256] . W) * s_b * [s_b * Xsaved + t_b > 0]  (+ residual)        dgrad through CBN+ReLU
-// Every layer runs on the shared warp-specialised GEMM engine (tc_gemm.cuh: A producers with the CBN + ReLU prologue, weight
+// The ten layers of a direction run as ONE launch of the shared warp-specialised GEMM engine (tc::gemm_chain_kernel: a row tile
+// of layer l + 1 needs only the same row tile of layer l, which the same CTA produced); every layer (tc_gemm.cuh: A producers with the CBN + ReLU prologue, weight
 // chunks [256 x 32] hi/lo by TMA bulk copies multicast across a 2-CTA cluster, twelve tcgen05.mma per chunk into one of two
 // TMEM accumulator stages, epilogue warps with bias / residual / dgrad mask).  The forward pass keeps three activation tensors
 // ([M][256] fp32, warp-transposed layout, see act_off4: net ping, h, net pong) and, for the dgrad, one sign bit per CBN
@@ -128,7 +129,7 @@ struct OnetLayerPolicy {
     const float4* p4 = reinterpret_cast<const float4*>(P.g.A) + act_off4(r.row, kc * 8);      // + 32 per float4 column group
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 v = __ldg(p4 + q * 32);
+      const float4 v = __ldcg(p4 + q * 32);       // coherent: in a chain launch these rows were written by this kernel
       x[4 * q + 0] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
     }
     if (P.g.pro_s) {                    // CBN (eval mode, folded) + ReLU on read
@@ -159,10 +160,10 @@ struct OnetLayerPolicy {
 #pragma unroll
     for (int k = 0; k < 32; ++k) y[k] = y_in[k];
     float4 rv[8];
-    if (a.resid) {                      // plain loads (the dgrad residual buffer is updated in place), issued before any store
-      const float4* r4 = reinterpret_cast<const float4*>(a.resid) + off;
+    if (a.resid) {                      // coherent loads (the dgrad residual buffer is updated in place; in a chain launch an earlier
+      const float4* r4 = reinterpret_cast<const float4*>(a.resid) + off;      // layer of this kernel wrote it), issued before any store
 #pragma unroll
-      for (int q = 0; q < 8; ++q) rv[q] = r4[q * 32];
+      for (int q = 0; q < 8; ++q) rv[q] = __ldcg(r4 + q * 32);
     }
     if (a.mask_bits) {                  // dgrad through relu(s * x + t): scale by s where the pre-activation was positive
       const uint32_t m = __ldg(a.mask_bits + ((size_t)(r.row >> 5) * 8 + (col0 >> 5)) * 32 + (r.row & 31));
@@ -331,6 +332,7 @@ struct OnetWs {
   float* g0;       // [M][256] gradient ping
   float* g1;       // [M][256] gradient pong
   double* stat;    // [M/8 blocks][2]
+  OnetLayerParams* chain;   // [3][10]: the layer records of the forward chain with masks, the forward chain without, the dgrad chain
   size_t bytes;
 };
 OnetWs carve_onet(void* base, int B, int K) {
@@ -351,13 +353,9 @@ OnetWs carve_onet(void* base, int B, int K) {
   w.g0 = (float*)take(MH * 4);
   w.g1 = (float*)take(MH * 4);
   w.stat = (double*)take(((M + 255) / 256) * 2 * sizeof(double));
+  w.chain = (OnetLayerParams*)take((size_t)3 * 10 * sizeof(OnetLayerParams));
   w.bytes = off;
   return w;
-}
-int launch_gemm(const GemmArgs& a, cudaStream_t st) {
-  OnetLayerParams P{};
-  P.M = a.M; P.n_chunks = kOH / kChunk; P.n_tiles_n = 1; P.wimg = a.img; P.g = a;
-  return tc::launch<OnetLayerPolicy>(P, 256, st);
 }
 }  // namespace
 
@@ -412,15 +410,19 @@ extern "C" int ifd_onet_prepare(const float* dec_weights, const float* c, int B,
 }
 
 namespace {
-// forward through the decoder.  net ping-pongs between act slots 0 and 2 (net_5 ends in slot 2, see onet_net5), h lives in slot 1;
-// the sign bits of every CBN pre-activation go to w.mask[layer] when `masks` (the dgrad needs nothing else of the activations).
 inline float* onet_net5(const OnetWs& w, int M) { return w.act + (size_t)2 * act_floats(M); }
 inline uint32_t* onet_mask(const OnetWs& w, int M, int layer) { return w.mask + (size_t)layer * (act_floats(M) / kOH) * 8; }
-int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K, bool masks, cudaStream_t st) {
+int g_onet_chain = 1;      // ifd_test_hook(8, 0 / 1): the ten layers of a direction as ONE launch of the GEMM engine (tc::gemm_chain_kernel)
+
+OnetLayerParams as_layer(const GemmArgs& a) {
+  OnetLayerParams P{};
+  P.M = a.M; P.n_chunks = kOH / kChunk; P.n_tiles_n = 1; P.wimg = a.img; P.g = a;
+  return P;
+}
+// the ten forward layers in order (fc_0, fc_1 of block 0, ...), as onet_forward describes them
+void forward_layers(const float* W, const OnetWs& w, int B, int K, bool masks, OnetLayerParams (&out)[10]) {
   const int M = B * K;
   const size_t MH = act_floats(M);
-  onet_fcp_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xyz, W, W + kOH * 3, M, w.act);
-  IFD_LAUNCH_CHECK("onet_fcp_kernel");
   for (int blk = 0; blk < 5; ++blk) {
     float* net = w.act + (size_t)((blk & 1) ? 2 : 0) * MH;
     float* h = w.act + MH;
@@ -432,8 +434,6 @@ int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K
     a.bias = W + kOffFc + (2 * blk) * kFcFloats + (size_t)kOH * kOH;
     a.mask_out = masks ? onet_mask(w, M, 2 * blk) : nullptr;
     a.out = h;
-    int rc = launch_gemm(a, st);
-    if (rc) return rc;
     GemmArgs c{};
     c.M = M; c.K = K;
     c.A = h; c.pro_s = w.s + (size_t)(2 * blk + 1) * B * kOH; c.pro_t = w.t + (size_t)(2 * blk + 1) * B * kOH;
@@ -442,32 +442,66 @@ int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K
     c.mask_out = masks ? onet_mask(w, M, 2 * blk + 1) : nullptr;
     c.resid = net;
     c.out = net_next;
-    if ((rc = launch_gemm(c, st))) return rc;
+    out[2 * blk] = as_layer(a);
+    out[2 * blk + 1] = as_layer(c);
   }
-  return IFD_OK;
 }
-// dgrad from g_net5 (in w.g0) down to grad_xyz
-int onet_backward(const float* W, const OnetWs& w, int B, int K, float* grad_xyz, cudaStream_t st) {
+// the ten dgrad layers in order (fc_1, fc_0 of block 4, ...): g_net5 in w.g0 -> g_net0 in w.g0
+void backward_layers(const OnetWs& w, int B, int K, OnetLayerParams (&out)[10]) {
   const int M = B * K;
   float* gnet = w.g0;
   float* gtmp = w.g1;
+  int n = 0;
   for (int blk = 4; blk >= 0; --blk) {
     GemmArgs a{};                                   // g_h = (g_net . W1) * s1 * [cbn1(h) > 0]
     a.M = M; a.K = K; a.A = gnet;
     a.img = w.img + ((size_t)10 + 2 * blk + 1) * kLayerImgFloats;
     a.mask_bits = onet_mask(w, M, 2 * blk + 1); a.mask_s = w.s + (size_t)(2 * blk + 1) * B * kOH;
     a.out = gtmp;
-    int rc = launch_gemm(a, st);
-    if (rc) return rc;
     GemmArgs c{};                                   // g_net = g_net + (g_h . W0) * s0 * [cbn0(net) > 0]   (in place on gnet)
     c.M = M; c.K = K; c.A = gtmp;
     c.img = w.img + ((size_t)10 + 2 * blk) * kLayerImgFloats;
     c.mask_bits = onet_mask(w, M, 2 * blk); c.mask_s = w.s + (size_t)(2 * blk) * B * kOH;
     c.resid = gnet;
     c.out = gnet;                                   // each thread reads and writes only its own row chunk
-    if ((rc = launch_gemm(c, st))) return rc;
+    out[n++] = as_layer(a);
+    out[n++] = as_layer(c);
   }
-  onet_fcp_bwd_kernel<<<(M + 255) / 256, 256, 0, st>>>(gnet, W, M, grad_xyz);
+}
+// ten layers: one chain launch (the records go to w.chain[slot] first), or ten launches
+int run_layers(const OnetLayerParams (&L)[10], const OnetWs& w, int slot, bool upload, cudaStream_t st) {
+  if (g_onet_chain) {
+    OnetLayerParams* dev = w.chain + (size_t)slot * 10;
+    if (upload) IFD_CUDA_TRY(cudaMemcpyAsync(dev, L, sizeof(L), cudaMemcpyHostToDevice, st));
+    const int rc = tc::launch_chain<OnetLayerPolicy, 256>(dev, 10, L[0], st);
+    if (rc != 1) return rc;                         // 1: the shape does not fit the chain form
+  }
+  for (int l = 0; l < 10; ++l) {
+    const int rc = tc::launch<OnetLayerPolicy>(L[l], 256, st);
+    if (rc) return rc;
+  }
+  return IFD_OK;
+}
+
+// forward through the decoder.  net ping-pongs between act slots 0 and 2 (net_5 ends in slot 2, see onet_net5), h lives in slot 1;
+// the sign bits of every CBN pre-activation go to w.mask[layer] when `masks` (the dgrad needs nothing else of the activations).
+// `upload`: the layer records of this (workspace, weights) pair are not in w.chain yet (the loop uploads them once).
+int onet_forward(const float* W, const OnetWs& w, const float* xyz, int B, int K, bool masks, cudaStream_t st, bool upload = true) {
+  const int M = B * K;
+  onet_fcp_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xyz, W, W + kOH * 3, M, w.act);
+  IFD_LAUNCH_CHECK("onet_fcp_kernel");
+  OnetLayerParams L[10];
+  forward_layers(W, w, B, K, masks, L);
+  return run_layers(L, w, masks ? 0 : 1, upload, st);
+}
+// dgrad from g_net5 (in w.g0) down to grad_xyz
+int onet_backward(const float* W, const OnetWs& w, int B, int K, float* grad_xyz, cudaStream_t st, bool upload = true) {
+  const int M = B * K;
+  OnetLayerParams L[10];
+  backward_layers(w, B, K, L);
+  int rc = run_layers(L, w, 2, upload, st);
+  if (rc) return rc;
+  onet_fcp_bwd_kernel<<<(M + 255) / 256, 256, 0, st>>>(w.g0, W, M, grad_xyz);
   IFD_LAUNCH_CHECK("onet_fcp_bwd_kernel");
   return IFD_OK;
 }
@@ -510,6 +544,7 @@ extern "C" int ifd_onet_decode_bwd(const float* dec_weights, const float* xyz, c
 
 // Loop pieces shared with the ConvONet path (restore.cu)
 namespace ifd {
+void onet_set_chain(int on) { g_onet_chain = on ? 1 : 0; }
 int opt_step_tail(float* xyz, float* m, float* v, const float* g_occ, int B, int K, const ifd_opt_params* P, int i, void* conv_ws,
                   bool stat, const double* dec_part, int n_dec, double* stats_out, bool warm_ok, cudaStream_t st,
                   const LoopJob* job, bool fresh);
@@ -546,12 +581,12 @@ extern "C" int ifd_onet_opt(const float* dec_weights, const float* c, float* xyz
     const bool stat = P->want_stats && stats_out && (i % 100 == 0);
     {
       ProfileScope ps(0, st);
-      if ((rc = onet_forward(dec_weights, w, xyz, B, K, true, st))) return rc;
+      if ((rc = onet_forward(dec_weights, w, xyz, B, K, true, st, i == 0))) return rc;
       onet_head_kernel<<<n_dec, 256, 0, st>>>(onet_net5(w, M), w.s + (size_t)10 * B * kOH, w.t + (size_t)10 * B * kOH,
                                               dec_weights + kOffOut, dec_weights + kOffOut + kOH, M, K, nullptr, nullptr, 1,
                                               (float)P->occ_target, ginv, w.g0, stat ? w.stat : nullptr);
       IFD_LAUNCH_CHECK("onet_head_kernel");
-      if ((rc = onet_backward(dec_weights, w, B, K, g_occ, st))) return rc;
+      if ((rc = onet_backward(dec_weights, w, B, K, g_occ, st, i == 0))) return rc;
     }
     if ((rc = opt_step_tail(xyz, m, v, g_occ, B, K, P, i, conv_ws, stat, w.stat, n_dec, stats_out, true, st, nullptr, fresh))) return rc;
   }

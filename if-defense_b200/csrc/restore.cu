@@ -1148,6 +1148,7 @@ extern "C" int ifd_convonet_grid_opt(const float* volume_cl, const float* dec_we
 }
 
 namespace ifd { void tc_set_cluster(int n); }
+namespace ifd { void onet_set_chain(int on); }
 extern "C" void ifd_test_hook(int key, int value) {
   if (key == 6) tc_set_cluster(value);
   if (key == 1) g_inbox_cap = value < 0 ? 0 : (value > kCsInbox ? kCsInbox : value);
@@ -1155,6 +1156,7 @@ extern "C" void ifd_test_hook(int key, int value) {
   if (key == 3) g_use_graph = value ? 1 : 0;
   if (key == 4) g_bar_mode = value < 0 ? 0 : (value > 2 ? 2 : value);
   if (key == 7) g_use_jac = value ? 1 : 0;
+  if (key == 8) onet_set_chain(value);
   if (key == 5) g_tail_ctas = value == 1 ? 1 : (value == 2 ? 2 : 0);
 }
 

@@ -41,7 +41,7 @@ constexpr int kAStageBytes = 2 * 128 * kChunk * 4;   // hi + lo images of the A 
 __host__ __device__ constexpr int b_stage_bytes(int NT) { return 2 * NT * kChunk * 4; }
 __host__ __device__ constexpr int stages_for(int NT) { return NT >= 256 ? 2 : (NT >= 128 ? 3 : 4); }
 __host__ __device__ constexpr size_t smem_bytes(int NT) {
-  return (size_t)stages_for(NT) * (kAStageBytes + b_stage_bytes(NT)) + 256;
+  return (size_t)stages_for(NT) * (kAStageBytes + b_stage_bytes(NT)) + 256;      // stages | barriers (<= 24 x 8 B) + TMEM slot
 }
 
 using umma::mma_tf32_ss;       // D[tmem] (+)= A[smem] . B[smem]^T
@@ -108,8 +108,16 @@ __device__ __forceinline__ void commit_multicast(uint64_t* bar, uint16_t mask) {
                : "memory");
 }
 
+// A CHAIN of layers in one launch (n_layers > 1): the layers share M, n_chunks and n_tiles_n, layer l + 1 reads rows that layer l
+// wrote, and nothing else couples them -- a row tile depends only on the same row tile of the layer before.  Tile t of every
+// layer runs on the same CTA, so the only hand-over needed is inside the CTA: the epilogue warps fence their stores and arrive
+// on tile_done[local tile], the producers wait for it before they read that tile's rows for the next layer.  No launch
+// boundary, no pipeline drain and refill between layers (14 us of 58 per 256-wide ONet layer, 20 layers per Adam step).
+// Policies used in a chain must read activations with coherent loads (__ldcg), not through the read-only path.
+constexpr int kMaxLocalTiles = 8;
+
 template <class Policy, int NT, int CL>
-__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy::Params P) {
+__device__ __forceinline__ void gemm_body(const typename Policy::Params* __restrict__ layers, int n_layers) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int S = stages_for(NT);
   constexpr int kBStage = b_stage_bytes(NT);
@@ -125,7 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
   uint64_t* empty = bars + 2 * S;          // [S] tcgen05.commit of every CTA of the cluster
   uint64_t* acc_full = bars + 3 * S;       // [2] tcgen05.commit after the last chunk of a tile
   uint64_t* acc_empty = bars + 3 * S + 2;  // [2] 128 epilogue arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+  uint64_t* tile_done = bars + 3 * S + 4;  // [kMaxLocalTiles] 128 epilogue arrivals per layer (chains only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4 + kMaxLocalTiles);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -139,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
       umma::mbar_init(&acc_full[s], 1);
       umma::mbar_init(&acc_empty[s], 128);
     }
+    for (int s = 0; s < kMaxLocalTiles; ++s) umma::mbar_init(&tile_done[s], 128);
     umma::fence_mbar_init();
   }
   if (warp == 8) umma::tmem_alloc(tmem_slot, kTmemCols);
@@ -150,11 +160,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
 
   // Tiles: cluster tile ct -> column tile ct % n_tiles_n, row tiles (ct / n_tiles_n) * CL + rank.  Every CTA of a cluster runs
   // the same number of rounds; a row tile beyond M is a dummy (the policies load zeros and store nothing for rows >= M).
-  const int m_tiles = (P.M + 127) / 128;
-  const int n_ct = ((m_tiles + CL - 1) / CL) * P.n_tiles_n;
+  const typename Policy::Params& P0 = layers[0];
+  const int m_tiles = (P0.M + 127) / 128;
+  const int n_tiles_n = P0.n_tiles_n;
+  const int n_ct = ((m_tiles + CL - 1) / CL) * n_tiles_n;
   const int n_clusters = gridDim.x / CL, cid = blockIdx.x / CL;
-  const int n_chunks = P.n_chunks;
-  auto row_tile = [&](int ct) { return (ct / P.n_tiles_n) * CL + rank; };
+  const int n_chunks = P0.n_chunks;
+  auto row_tile = [&](int ct) { return (ct / n_tiles_n) * CL + rank; };
 
   if (warp < 4) {
     // ------------------------------------------------------------------ A producers
@@ -163,65 +175,94 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
     // The values of chunk kc + 1 (of the next tile after the last chunk) are fetched BEFORE chunk kc is split and stored: one
     // producer warp per scheduler cannot hide a global-load latency any other way.
     float xn[32];
-    typename Policy::Row row = Policy::row_begin(P, row_tile(cid) * 128 + r);
-    if (cid < n_ct) Policy::load(P, row, 0, xn);
-    for (int ct = cid; ct < n_ct; ct += n_clusters) {
-      for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-        const int s = it % S;
-        const uint32_t ph = (it / S) & 1;
-        float x[32];
+    typename Policy::Row row = Policy::row_begin(P0, row_tile(cid) * 128 + r);
+    bool have = false;                              // xn holds the values of the chunk that comes next
+    if (cid < n_ct) {
+      Policy::load(P0, row, 0, xn);
+      have = true;
+    }
+    for (int l = 0; l < n_layers; ++l) {
+      const typename Policy::Params& P = layers[l];
+      int tloc = 0;
+      for (int ct = cid; ct < n_ct; ct += n_clusters, ++tloc) {
+        for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          if (!have) {                              // first chunk of a layer whose rows this CTA's epilogue may still be writing
+            umma::mbar_wait(&tile_done[tloc], (uint32_t)((l - 1) & 1));
+            row = Policy::row_begin(P, row_tile(ct) * 128 + r);
+            Policy::load(P, row, kc, xn);
+          }
+          float x[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) x[k] = xn[k];
-        if (kc + 1 < n_chunks) {
-          Policy::load(P, row, kc + 1, xn);
-        } else if (ct + n_clusters < n_ct) {
-          row = Policy::row_begin(P, row_tile(ct + n_clusters) * 128 + r);
-          Policy::load(P, row, 0, xn);
-        }
-        umma::mbar_wait(&empty[s], ph ^ 1);
-        unsigned char* hi = a_st + (size_t)s * kAStageBytes + (r >> 3) * 128 + (r & 7) * 16;
-        unsigned char* lo = hi + 128 * kChunk * 4;
+          for (int k = 0; k < 32; ++k) x[k] = xn[k];
+          have = true;
+          if (kc + 1 < n_chunks) {
+            Policy::load(P, row, kc + 1, xn);
+          } else if (ct + n_clusters < n_ct) {      // next tile of this layer (its rows of layer l - 1 were finished a round ago)
+            if (l > 0) umma::mbar_wait(&tile_done[tloc + 1], (uint32_t)((l - 1) & 1));
+            row = Policy::row_begin(P, row_tile(ct + n_clusters) * 128 + r);
+            Policy::load(P, row, 0, xn);
+          } else if (l + 1 < n_layers && tloc > 0) {   // first tile of the next layer: finished while later tiles of this layer ran
+            umma::mbar_wait(&tile_done[0], (uint32_t)(l & 1));
+            row = Policy::row_begin(layers[l + 1], row_tile(cid) * 128 + r);
+            Policy::load(layers[l + 1], row, 0, xn);
+          } else {
+            have = false;                           // (a CTA with ONE tile: its epilogue still needs the chunk stored below)
+          }
+          umma::mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* hi = a_st + (size_t)s * kAStageBytes + (r >> 3) * 128 + (r & 7) * 16;
+          unsigned char* lo = hi + 128 * kChunk * 4;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          uint4 h, l;
-          h.x = umma::tf32_hi_fast(x[4 * g + 0]); h.y = umma::tf32_hi_fast(x[4 * g + 1]);
-          h.z = umma::tf32_hi_fast(x[4 * g + 2]); h.w = umma::tf32_hi_fast(x[4 * g + 3]);
-          l.x = __float_as_uint(x[4 * g + 0] - __uint_as_float(h.x)); l.y = __float_as_uint(x[4 * g + 1] - __uint_as_float(h.y));
-          l.z = __float_as_uint(x[4 * g + 2] - __uint_as_float(h.z)); l.w = __float_as_uint(x[4 * g + 3] - __uint_as_float(h.w));
-          *reinterpret_cast<uint4*>(hi + g * 2048) = h;      // k group g: 16 core-matrix rows of 128 B per 8 tile rows
-          *reinterpret_cast<uint4*>(lo + g * 2048) = l;
+          for (int g = 0; g < 8; ++g) {
+            uint4 h, l4;
+            h.x = umma::tf32_hi_fast(x[4 * g + 0]); h.y = umma::tf32_hi_fast(x[4 * g + 1]);
+            h.z = umma::tf32_hi_fast(x[4 * g + 2]); h.w = umma::tf32_hi_fast(x[4 * g + 3]);
+            l4.x = __float_as_uint(x[4 * g + 0] - __uint_as_float(h.x)); l4.y = __float_as_uint(x[4 * g + 1] - __uint_as_float(h.y));
+            l4.z = __float_as_uint(x[4 * g + 2] - __uint_as_float(h.z)); l4.w = __float_as_uint(x[4 * g + 3] - __uint_as_float(h.w));
+            *reinterpret_cast<uint4*>(hi + g * 2048) = h;      // k group g: 16 core-matrix rows of 128 B per 8 tile rows
+            *reinterpret_cast<uint4*>(lo + g * 2048) = l4;
+          }
+          umma::fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core's async proxy
+          mbar_arrive(&full_a[s]);
         }
-        umma::fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core's async proxy
-        mbar_arrive(&full_a[s]);
       }
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue (warp - 4 = TMEM lane quarter)
     const int r = threadIdx.x - 128;
     uint32_t tl = 0;
-    for (int ct = cid; ct < n_ct; ct += n_clusters, ++tl) {
-      const int nt = ct % P.n_tiles_n;
-      const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-      const typename Policy::Row row = Policy::row_begin(P, row_tile(ct) * 128 + r);
-      umma::mbar_wait(&acc_full[as], aph);
-      umma::fence_after_sync();
-      const uint32_t taddr = tmem + as * kAcc + ((uint32_t)((warp - 4) * 32) << 16);
+    for (int l = 0; l < n_layers; ++l) {
+      const typename Policy::Params& P = layers[l];
+      int tloc = 0;
+      for (int ct = cid; ct < n_ct; ct += n_clusters, ++tl, ++tloc) {
+        const int nt = ct % n_tiles_n;
+        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+        const typename Policy::Row row = Policy::row_begin(P, row_tile(ct) * 128 + r);
+        umma::mbar_wait(&acc_full[as], aph);
+        umma::fence_after_sync();
+        const uint32_t taddr = tmem + as * kAcc + ((uint32_t)((warp - 4) * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < NT / 32; ++c) {
-        uint32_t d[32];
-        umma::tmem_ld32(taddr + c * 32, d);
-        float y[32];
+        for (int c = 0; c < NT / 32; ++c) {
+          uint32_t d[32];
+          umma::tmem_ld32(taddr + c * 32, d);
+          float y[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(d[k]);
-        if (kSplit) {
-          umma::tmem_ld32(taddr + NT + c * 32, d);
+          for (int k = 0; k < 32; ++k) y[k] = __uint_as_float(d[k]);
+          if (kSplit) {
+            umma::tmem_ld32(taddr + NT + c * 32, d);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) y[k] += __uint_as_float(d[k]);
+            for (int k = 0; k < 32; ++k) y[k] += __uint_as_float(d[k]);
+          }
+          Policy::store(P, row, nt * NT + c * 32, y);
         }
-        Policy::store(P, row, nt * NT + c * 32, y);
+        umma::fence_before_sync();
+        mbar_arrive(&acc_empty[as]);
+        if (n_layers > 1) {                           // this tile's rows of layer l are in memory: the next layer may read them
+          __threadfence();
+          mbar_arrive(&tile_done[tloc]);
+        }
       }
-      umma::fence_before_sync();
-      mbar_arrive(&acc_empty[as]);
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issuer
@@ -232,38 +273,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
       const uint32_t tmem_u = umma::warp_bcast(tmem);
       const uint32_t cid_u = umma::warp_bcast((uint32_t)cid), ncl_u = umma::warp_bcast((uint32_t)n_clusters);
       uint32_t it = 0, tl = 0;
-      for (uint32_t ct = cid_u; ct < (uint32_t)n_ct; ct += ncl_u, ++tl) {
-        const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
-        umma::mbar_wait(&acc_empty[as], aph ^ 1);   // the epilogue drained this accumulator stage (two tiles ago)
-        umma::fence_after_sync();
-        const uint32_t d_t = tmem_u + as * kAcc;
-        for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
-          umma::mbar_wait(&full_a[s], ph);
-          umma::mbar_wait(&full_b[s], ph);
+      for (int l = 0; l < n_layers; ++l) {
+        for (uint32_t ct = cid_u; ct < (uint32_t)n_ct; ct += ncl_u, ++tl) {
+          const uint32_t as = tl & 1, aph = (tl >> 1) & 1;
+          umma::mbar_wait(&acc_empty[as], aph ^ 1);   // the epilogue drained this accumulator stage (two tiles ago)
           umma::fence_after_sync();
-          const uint32_t sa = umma::smem_u32(a_st + (size_t)s * kAStageBytes);
-          const uint32_t sb = umma::smem_u32(b_st + (size_t)s * kBStage);
-          if (umma::elect_one()) {
+          const uint32_t d_t = tmem_u + as * kAcc;
+          for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            umma::mbar_wait(&full_a[s], ph);
+            umma::mbar_wait(&full_b[s], ph);
+            umma::fence_after_sync();
+            const uint32_t sa = umma::smem_u32(a_st + (size_t)s * kAStageBytes);
+            const uint32_t sb = umma::smem_u32(b_st + (size_t)s * kBStage);
+            if (umma::elect_one()) {
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {    // lo.hi, hi.lo, hi.hi (small terms first)
-              const uint32_t a_s = sa + (part == 0 ? 128 * kChunk * 4 : 0);
-              const uint32_t b_s = sb + (part == 1 ? NT * kChunk * 4 : 0);
-              const uint32_t d_p = (kSplit && part < 2) ? d_t + NT : d_t;
+              for (int part = 0; part < 3; ++part) {    // lo.hi, hi.lo, hi.hi (small terms first)
+                const uint32_t a_s = sa + (part == 0 ? 128 * kChunk * 4 : 0);
+                const uint32_t b_s = sb + (part == 1 ? NT * kChunk * 4 : 0);
+                const uint32_t d_p = (kSplit && part < 2) ? d_t + NT : d_t;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t later = kSplit ? (part == 1 ? 1u : (uint32_t)q) : (uint32_t)(part | q);    // 0 only for the first MMA into an accumulator
-                mma_tf32_ss(d_p, umma::smem_desc_kmajor(a_s + q * 4096, 2048, 128),
-                            umma::smem_desc_kmajor(b_s + q * (NT * 32), NT * 16, 128), idesc, (kc | later) ? 1u : 0u);
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t later = kSplit ? (part == 1 ? 1u : (uint32_t)q) : (uint32_t)(part | q);    // 0 only for the first MMA into an accumulator
+                  mma_tf32_ss(d_p, umma::smem_desc_kmajor(a_s + q * 4096, 2048, 128),
+                              umma::smem_desc_kmajor(b_s + q * (NT * 32), NT * 16, 128), idesc, (kc | later) ? 1u : 0u);
+                }
               }
+              // the stage is free once these MMAs have read it -- in EVERY CTA of the cluster (their loaders write into it)
+              if (CL > 1) commit_multicast(&empty[s], kMask);
+              else umma::commit(&empty[s]);
+              if (kc + 1 == n_chunks) umma::commit(&acc_full[as]);    // accumulator complete -> epilogue
             }
-            // the stage is free once these MMAs have read it -- in EVERY CTA of the cluster (their loaders write into it)
-            if (CL > 1) commit_multicast(&empty[s], kMask);
-            else umma::commit(&empty[s]);
-            if (kc + 1 == n_chunks) umma::commit(&acc_full[as]);    // accumulator complete -> epilogue
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -272,18 +315,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
     if (lane == 0) {
       constexpr uint32_t kPiece = kBStage / CL;
       uint32_t it = 0;
-      for (int ct = cid; ct < n_ct; ct += n_clusters) {
-        const int nt = ct % P.n_tiles_n;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.wimg + (size_t)nt * n_chunks * (2 * NT * kChunk));
-        for (int kc = 0; kc < n_chunks; ++kc, ++it) {
-          const int s = it % S;
-          const uint32_t ph = (it / S) & 1;
-          umma::mbar_wait(&empty[s], ph ^ 1);
-          umma::mbar_arrive_expect_tx(&full_b[s], kBStage);       // all CL pieces land here, one of them is ours
-          unsigned char* dst = b_st + (size_t)s * kBStage + (size_t)rank * kPiece;
-          const unsigned char* from = src + (size_t)kc * kBStage + (size_t)rank * kPiece;
-          if (CL > 1) bulk_g2s_multicast(dst, from, kPiece, &full_b[s], kMask);
-          else umma::bulk_g2s(dst, from, kPiece, &full_b[s]);
+      for (int l = 0; l < n_layers; ++l) {
+        const float* wimg = layers[l].wimg;
+        for (int ct = cid; ct < n_ct; ct += n_clusters) {
+          const int nt = ct % n_tiles_n;
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(wimg + (size_t)nt * n_chunks * (2 * NT * kChunk));
+          for (int kc = 0; kc < n_chunks; ++kc, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            umma::mbar_wait(&empty[s], ph ^ 1);
+            umma::mbar_arrive_expect_tx(&full_b[s], kBStage);       // all CL pieces land here, one of them is ours
+            unsigned char* dst = b_st + (size_t)s * kBStage + (size_t)rank * kPiece;
+            const unsigned char* from = src + (size_t)kc * kBStage + (size_t)rank * kPiece;
+            if (CL > 1) bulk_g2s_multicast(dst, from, kPiece, &full_b[s], kMask);
+            else umma::bulk_g2s(dst, from, kPiece, &full_b[s]);
+          }
         }
       }
     }
@@ -293,6 +339,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy
   __syncthreads();
   if (CL > 1) cluster_sync_all();          // no CTA leaves while a peer may still multicast into its shared memory
   if (warp == 8) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+template <class Policy, int NT, int CL>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const typename Policy::Params P) {
+  gemm_body<Policy, NT, CL>(&P, 1);
+}
+template <class Policy, int NT, int CL>
+__global__ void __launch_bounds__(kThreads, 1) gemm_chain_kernel(const typename Policy::Params* layers, int n_layers) {
+  gemm_body<Policy, NT, CL>(layers, n_layers);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -357,6 +412,56 @@ int launch_nt(const typename Policy::Params& P, cudaStream_t st) {
   if (cl >= 4) return launch_one<Policy, NT, 4>(P, wanted, st);
   if (cl == 2) return launch_one<Policy, NT, 2>(P, wanted, st);
   return launch_one<Policy, NT, 1>(P, wanted, st);
+}
+
+// A chain of n_layers layers (device array `dev_layers`; `first` = a host copy of its first element, for the shapes) in one
+// launch.  -> IFD_OK, or 1 when the shape does not fit the chain form (more than kMaxLocalTiles row tiles per CTA): the caller
+// then launches the layers one by one.
+template <class Policy, int NT, int CL>
+int launch_chain_one(const typename Policy::Params* dev_layers, int n_layers, const typename Policy::Params& first, cudaStream_t st) {
+  const size_t smem = smem_bytes(NT);
+  const void* fn = (const void*)gemm_chain_kernel<Policy, NT, CL>;
+  IFD_CUDA_TRY(set_max_dyn_smem(fn, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  int max_clusters = sm_count() / CL;
+  if (CL > 1) {
+    static int cached = -1;
+    if (cached < 0) {
+      cfg.gridDim = dim3(sm_count() / CL * CL);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) == cudaSuccess && n > 0) cached = n;
+      else { cudaGetLastError(); cached = max_clusters; }
+    }
+    max_clusters = cached < max_clusters ? cached : max_clusters;
+  }
+  const int m_tiles = (first.M + 127) / 128;
+  const int wanted = ((m_tiles + CL - 1) / CL) * first.n_tiles_n;
+  const int n = wanted < max_clusters ? wanted : max_clusters;
+  if ((wanted + n - 1) / n > kMaxLocalTiles) return 1;
+  cfg.gridDim = dim3(n * CL);
+  IFD_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_chain_kernel<Policy, NT, CL>, dev_layers, n_layers));
+  IFD_LAUNCH_CHECK("tc::gemm_chain_kernel");
+  return IFD_OK;
+}
+template <class Policy, int NT>
+int launch_chain(const typename Policy::Params* dev_layers, int n_layers, const typename Policy::Params& first, cudaStream_t st) {
+  const int m_tiles = (first.M + 127) / 128;
+  if (m_tiles <= 0 || n_layers <= 0) return IFD_OK;
+  int cl = g_cluster_size;
+  while (cl > 1 && m_tiles < 2 * cl) cl >>= 1;
+  if (cl >= 4) return launch_chain_one<Policy, NT, 4>(dev_layers, n_layers, first, st);
+  if (cl == 2) return launch_chain_one<Policy, NT, 2>(dev_layers, n_layers, first, st);
+  return launch_chain_one<Policy, NT, 1>(dev_layers, n_layers, first, st);
 }
 
 template <class Policy>
