@@ -50,6 +50,24 @@ def test_onet_opt_short_horizon(fx, dec):
     assert np.array_equal(out, out2)                                   # bitwise reproducible
 
 
+def test_chain_launch_equals_layer_by_layer():
+    """The ten layers of a direction as one launch of the GEMM engine (tc::gemm_chain_kernel, per-tile hand-over inside a CTA)
+    give the bits of ten launches -- the arithmetic per tile is the same, only the launch boundaries go.  Shapes with one row
+    tile per CTA (the hand-over has no later tile to hide behind), several, and a ragged last tile."""
+    L = capi.lib()
+    for B, K in ((1, 96), (2, 1024), (24, 1024), (3, 1000)):
+        case = synth.make_onet_case(B, K=K, seed=B)
+        rest = onet_mod.ONetRestorer(onet_mod.ONetDecoder(case.sd), threshold=0.2, lr=1e-3)
+        outs = []
+        for chain in (1, 0):
+            L.ifd_test_hook(8, chain)
+            try:
+                outs.append(rest.optimize_points(case.p0.cuda(), None, case.c.cuda(), rep_weight=500., iterations=5, normalize=False))
+            finally:
+                L.ifd_test_hook(8, 1)
+        assert np.isfinite(outs[0]).all() and np.array_equal(outs[0], outs[1]), (B, K)
+
+
 def test_config0_on_gpu(fx, dec):
     """BASELINE.json configs[0] (1 cloud x 1024 points, 20 iterations) against the reference's CPU result."""
     rest = onet_mod.ONetRestorer(dec)

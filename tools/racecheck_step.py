@@ -1,5 +1,5 @@
 """One ConvONet-Opt Adam step at config-2 size (64 x 1024) and one ONet-Mesh extraction, for compute-sanitizer:
-   compute-sanitizer --tool racecheck python tools/racecheck_step.py [--mesh]"""
+   compute-sanitizer --tool racecheck python tools/racecheck_step.py [--mesh | --onet]"""
 import os
 import sys
 
@@ -10,7 +10,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ifdefense_b200 import capi, convonet, synth  # noqa: E402
 from tests.gpu_util import run_opt                # noqa: E402
 
-if "--mesh" in sys.argv:
+if "--onet" in sys.argv:
+    from ifdefense_b200 import onet as onet_mod
+    case = synth.make_onet_case(4, K=1024, seed=0)
+    rest = onet_mod.ONetRestorer(onet_mod.ONetDecoder(case.sd), threshold=0.2, lr=1e-3)
+    out = rest.optimize_points(case.p0.cuda(), None, case.c.cuda(), rep_weight=500., iterations=1, normalize=False)
+    print("onet ok", float(np.abs(out).max()))
+elif "--mesh" in sys.argv:
     from ifdefense_b200 import mesh
     g = np.linspace(-0.55, 0.55, 33)
     X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
