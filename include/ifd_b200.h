@@ -424,16 +424,20 @@ long long ifd_launch_count(int reset);
  * device, sums the elapsed time per kernel kind, clears the record and returns the number of kinds written:
  * 0 = decode (gather + MLP fwd/bwd), 1 = kNN + repulsion, 2 = Adam, 3 = everything else. */
 /* Tensor-core self test: D[128][32] = A[128][32] . Bm[32][32]^T (Bm is [n][k]) through the tcgen05 / TMEM /
- * 3xTF32 path of the v3 decode kernel.  Device pointers. */
+ * 3xTF32 path of the decode kernels (one layer as a tensor-core round trip).  Device pointers. */
 int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t stream);
 
 /* Test instrumentation.  key 1: capacity (0..16, default 16) of the per-point inbox of non-mutual in-edges in the
  * fused tail kernel; lowering it forces the ordered-scan fallback that hubs take.  Results do not depend on it.
- * key 2: number of loops ifd_convonet_opt_batches runs side by side (1..4, default 2; the workspace must then hold that many
- * parts).  Measurement knob: 3 / 4 lanes gave +1.6 / +2.4 % over 2 at B = 64 and were not adopted.
+ * key 2: number of loops ifd_convonet_opt_batches and the host pipeline run side by side (1..4, default 4; size the workspace
+ * with ifd_convonet_opt_batches_workspace_bytes AFTER setting it).
  * key 3: 0 = enqueue the loop of ifd_convonet_opt as direct launches, 1 (default) = replay the cached CUDA graph (same bits).
  * key 4: cluster barrier in front of cloud_step_kernel's first remote store: 0 none, 1 release / acquire, 2 (default) relaxed.
- * key 6: CTAs per thread-block cluster of the GEMM engine (1, 2 (default) or 4): weight chunks are TMA-multicast across it. */
+ * key 5: form of the fused tail -- 0 (default) by context: a 2-CTA cluster per cloud for a loop that runs alone, one CTA per
+ *        cloud for loops that run side by side; 1 / 2 force the one-CTA / cluster form.  Same bits either way.
+ * key 6: CTAs per thread-block cluster of the GEMM engine (1, 2 (default) or 4): weight chunks are TMA-multicast across it.
+ * key 7: 1 (default) = decode v5 keeps d c / d xyz of its forward gather and reads it back, 0 = it gathers the texels twice.
+ * key 8: 1 (default) = the ten ONet decoder layers of a direction run as one chain launch, 0 = ten launches (same bits). */
 void ifd_test_hook(int key, int value);
 
 #define IFD_PROFILE_KINDS 4
