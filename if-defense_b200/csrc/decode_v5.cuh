@@ -86,7 +86,7 @@ __global__ void convonet_pack_umma_v5_kernel(const float* __restrict__ Wb_arg, i
 // A := split(x): hi -> TMEM columns 32..63, lo (exact remainder) -> 64..95 of this thread's lane.  `d` is staging.
 __device__ __forceinline__ void v5_put_a(const float (&x)[32], uint32_t (&d)[32], uint32_t lane_taddr) {
 #pragma unroll
-  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi_fast(x[k]);
+  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi_cvt(x[k]);
   umma::tmem_st32(lane_taddr + kV5ColA, d);
 #pragma unroll
   for (int k = 0; k < 32; ++k) d[k] = __float_as_uint(x[k] - __uint_as_float(d[k]));
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kV5Threads, 2) convonet_decode_v5_kernel(const
   for (int k = 0; k < 32; ++k) x[k] = feat[k * kV5Stride + slot];
   __syncthreads();                     // every thread holds its c row: the staging buffer may be overwritten
 #pragma unroll
-  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi_fast(x[k]);
+  for (int k = 0; k < 32; ++k) d[k] = umma::tf32_hi_cvt(x[k]);
   umma::tmem_st32(lane_taddr + kV5ColX, d);
   {
     const int r = slot & 127;

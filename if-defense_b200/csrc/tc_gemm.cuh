@@ -216,8 +216,8 @@ __device__ __forceinline__ void gemm_body(const typename Policy::Params* __restr
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             uint4 h, l4;
-            h.x = umma::tf32_hi_fast(x[4 * g + 0]); h.y = umma::tf32_hi_fast(x[4 * g + 1]);
-            h.z = umma::tf32_hi_fast(x[4 * g + 2]); h.w = umma::tf32_hi_fast(x[4 * g + 3]);
+            h.x = umma::tf32_hi_cvt(x[4 * g + 0]); h.y = umma::tf32_hi_cvt(x[4 * g + 1]);
+            h.z = umma::tf32_hi_cvt(x[4 * g + 2]); h.w = umma::tf32_hi_cvt(x[4 * g + 3]);
             l4.x = __float_as_uint(x[4 * g + 0] - __uint_as_float(h.x)); l4.y = __float_as_uint(x[4 * g + 1] - __uint_as_float(h.y));
             l4.z = __float_as_uint(x[4 * g + 2] - __uint_as_float(h.z)); l4.w = __float_as_uint(x[4 * g + 3] - __uint_as_float(h.w));
             *reinterpret_cast<uint4*>(hi + g * 2048) = h;      // k group g: 16 core-matrix rows of 128 B per 8 tile rows

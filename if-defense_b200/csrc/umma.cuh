@@ -168,6 +168,13 @@ __device__ __forceinline__ uint32_t tf32_lo(float x) { return tf32_rna(x - __uin
 // Hot-path variants: round-to-nearest (ties away) by integer arithmetic on the bit pattern -- 2 instructions
 // instead of the 3 of cvt.rna (which also screens Inf/NaN; activations on this path are finite).  x - hi is exact.
 __device__ __forceinline__ uint32_t tf32_hi_fast(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// Round-to-nearest-even to TF32 in ONE instruction (SASS F2FP.SATFINITE.TF32.F32.PACK_B; satfinite only clamps +-Inf / NaN,
+// which this path never sees).  Differs from tf32_hi_fast on exact ties only; x - hi stays exact.
+__device__ __forceinline__ uint32_t tf32_hi_cvt(float x) {
+  uint32_t u;
+  asm("cvt.rn.satfinite.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
 __device__ __forceinline__ uint32_t tf32_lo_fast(float x, uint32_t hi) {
   return (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
 }
