@@ -100,6 +100,22 @@ class Defender:
             out += [o.detach().cpu().numpy().astype(np.float32) for o in sor(x)]
         return out
 
+    def _to_device(self, host, tag):
+        """Host array / tensor -> device tensor through a pinned staging buffer this object keeps per (tag, shape, dtype): a
+        copy from pageable memory is staged by the driver and blocks the host for 3-100 ms when the GPU is busy with the
+        loops of earlier batches (measured); from pinned memory it is one asynchronous DMA.  The staging buffer is reused by
+        the next call with the same tag: the stream is synchronised on the copy before this function returns (a few MB)."""
+        t = torch.from_numpy(host) if isinstance(host, np.ndarray) else host
+        key = (tag, tuple(t.shape), t.dtype)
+        pins = self.__dict__.setdefault("_pins", {})
+        buf = pins.get(key)
+        if buf is None:
+            buf = pins[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        buf.copy_(t)
+        out = buf.to(self.device, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
     def prepare_batch_device(self, raw, rng=None, gen=None):
         """sor_process + preprocess_pc + the encoder subset + init_points (opt_defense.py:86-179) for one batch [B,K,3] with the
         arrays on the device: SOR mask (`ifd_sor`), ragged selection + normalisation (`ifd_preprocess_pc`), gathers by the
@@ -108,7 +124,7 @@ class Defender:
         -> (sel [B,T,3], init [B,npoint,3])."""
         from . import capi
         a = self.args
-        x = torch.from_numpy(np.ascontiguousarray(np.asarray(raw)[..., :3], dtype=np.float32)).to(self.device)
+        x = self._to_device(np.ascontiguousarray(np.asarray(raw)[..., :3], dtype=np.float32), "raw")
         B, K, _ = x.shape
         L = capi.lib()
         keep = None
@@ -146,8 +162,8 @@ class Defender:
             ini_idx = torch.stack([torch.randint(0, int(k), (a.sample_npoint,), generator=gen) for k in n])   # init_points :163-167
             noise = torch.randn((B, a.sample_npoint, 3), generator=gen) * a.init_sigma
         rows = torch.arange(B, device=self.device).view(B, 1)
-        sel = allp[rows, torch.from_numpy(sel_idx).to(self.device)]
-        pts = allp[rows, ini_idx.to(self.device)] + noise.to(self.device)
+        sel = allp[rows, self._to_device(sel_idx, "sel")]
+        pts = allp[rows, self._to_device(ini_idx, "ini")] + self._to_device(noise, "noise")
         return sel, torch.clamp(pts, min=-0.5 * a.padding_scale, max=0.5 * a.padding_scale)
 
     def defend_point_cloud(self, pc, rng=None, gen=None, printing=False):
@@ -228,11 +244,18 @@ class Defender:
         different segments do); one D2H per segment.  draws(lo, hi) -> (rng, gen) for prepare_batch_device; stages run in
         segment order, so shared generators see the draws in the serial code's order."""
         a = self.args
-        side = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
         depth = 4 if max(hi - lo for lo, hi, _ in segments) <= 64 else 2
         depth = 1 if printing else min(depth, int(os.environ.get("IFD_LOOPS_IN_FLIGHT", self.loops_in_flight)))
-        loops = [torch.cuda.Stream(device=self.device) for _ in range(depth)]
+        # the streams live as long as the object: torch's allocator keeps one block pool per stream, and a fresh set of streams
+        # per call would start every call with empty pools (cudaMalloc inside the pipeline)
+        pool = self.__dict__.setdefault("_streams", [])
+        while len(pool) < 1 + depth:
+            pool.append(torch.cuda.Stream(device=self.device))
+        side, loops = pool[0], pool[1:1 + depth]
+        side.wait_stream(main)
+        for S in loops:
+            S.wait_stream(main)
 
         def stage(seg):
             lo, hi, _ = seg
