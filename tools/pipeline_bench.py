@@ -29,7 +29,8 @@ def main():
     res = {}
     for dev_path in (True, False):
         d = driver.Defender(model, driver.Args(batch_size=a.batch, iterations=200, device_preprocess=dev_path))
-        d.defend_point_cloud(pc[:a.batch], rng=np.random.default_rng(0), gen=torch.Generator().manual_seed(0))   # warm-up
+        # warm-up: enough batches that every loop stream, lane graph and allocator pool of the pipeline has been used once
+        d.defend_point_cloud(pc[:min(len(pc), 4 * a.batch)], rng=np.random.default_rng(0), gen=torch.Generator().manual_seed(0))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         d.defend_point_cloud(pc, rng=np.random.default_rng(0), gen=torch.Generator().manual_seed(0))
