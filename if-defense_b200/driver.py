@@ -246,7 +246,7 @@ class Defender:
         a = self.args
         main = torch.cuda.current_stream(self.device)
         depth = 4 if max(hi - lo for lo, hi, _ in segments) <= 64 else 2
-        depth = 1 if printing else min(depth, int(os.environ.get("IFD_LOOPS_IN_FLIGHT", self.loops_in_flight)))
+        depth = 1 if printing else min(depth, int(self.loops_in_flight))
         # the streams live as long as the object: torch's allocator keeps one block pool per stream, and a fresh set of streams
         # per call would start every call with empty pools (cudaMalloc inside the pipeline)
         pool = self.__dict__.setdefault("_streams", [])
