@@ -584,9 +584,10 @@ static int g_bar_mode = 2;           // ifd_test_hook(4, mode): CloudStepArgs::b
 // launches twice the SMs: 4549 -> 4870 clouds/s with two loops, 5436 with four (B = 64 x 1024, one B200).
 static int g_tail_ctas = 0;          // ifd_test_hook(5, n): 0 = by context (default), 1 = one CTA, 2 = cluster pair
 static thread_local int t_side_by_side = 0;      // set by the multi-batch entry points around their ifd_convonet_opt calls
-static int tail_ctas() { return g_tail_ctas ? g_tail_ctas : (t_side_by_side ? 1 : 2); }
+// (a batch of more than 74 clouds fills the 148 SMs with the cluster form anyway: no latency to gain from it, only SMs to lose)
+static int tail_ctas(int B) { return g_tail_ctas ? g_tail_ctas : ((t_side_by_side || B > 74) ? 1 : 2); }
 static int launch_cloud_step(const CloudStepArgs& c, int B, cudaStream_t st) {
-  if (tail_ctas() == 1) {
+  if (tail_ctas(B) == 1) {
     IFD_CUDA_TRY(set_max_dyn_smem((const void*)cloud_step_solo_kernel, sizeof(CloudStepSmem)));
     cloud_step_solo_kernel<<<B, kCsThreads, sizeof(CloudStepSmem), st>>>(c);
   } else {
@@ -785,7 +786,7 @@ int launch_loop_graph(const LoopJob& job, int B, int K, int R, int n_blocks, con
 
   GraphKey key;
   memset(&key, 0, sizeof key);
-  key.B = B; key.K = K; key.R = R; key.n_blocks = n_blocks; key.slot = slot; key.inbox_cap = ((g_inbox_cap * 4 + g_bar_mode) * 4 + tail_ctas()) * 2 + g_use_jac;
+  key.B = B; key.K = K; key.R = R; key.n_blocks = n_blocks; key.slot = slot; key.inbox_cap = ((g_inbox_cap * 4 + g_bar_mode) * 4 + tail_ctas(B)) * 2 + g_use_jac;
   memcpy(&key.P, P, sizeof(ifd_opt_params));
   GraphEntry* hit = nullptr;
   for (GraphEntry& e : g.entries)
