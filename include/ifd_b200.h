@@ -433,8 +433,9 @@ int ifd_selftest_umma(const float* A, const float* Bm, float* D, ifd_stream_t st
  * with ifd_convonet_opt_batches_workspace_bytes AFTER setting it).
  * key 3: 0 = enqueue the loop of ifd_convonet_opt as direct launches, 1 (default) = replay the cached CUDA graph (same bits).
  * key 4: cluster barrier in front of cloud_step_kernel's first remote store: 0 none, 1 release / acquire, 2 (default) relaxed.
- * key 5: form of the fused tail -- 0 (default) by context: a 2-CTA cluster per cloud for a loop that runs alone, one CTA per
- *        cloud for loops that run side by side; 1 / 2 force the one-CTA / cluster form.  Same bits either way.
+ * key 5: form of the fused tail -- 0 (default) by context: a 2-CTA cluster per cloud for a loop of at most 74 clouds that runs
+ *        alone, one CTA per cloud for larger batches and for loops that run side by side; 1 / 2 force the one-CTA / cluster form.
+ *        Same bits either way.
  * key 6: CTAs per thread-block cluster of the GEMM engine (1, 2 (default) or 4): weight chunks are TMA-multicast across it.
  * key 7: 1 (default) = decode v5 keeps d c / d xyz of its forward gather and reads it back, 0 = it gathers the texels twice.
  * key 8: 1 (default) = the ten ONet decoder layers of a direction run as one chain launch, 0 = ten launches (same bits). */
